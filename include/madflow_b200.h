@@ -1,0 +1,94 @@
+/* C ABI of the process-independent library  (libmadflow_b200.so).
+ *
+ * HELAS external wavefunctions, ALOHA vertices (test hooks), RAMBO phase space with cuts and
+ * boost, Philox/VEGAS sampling, accumulation and grid refinement, and an FP64 peak probe.
+ * It replaces the TensorFlow graphs of python_package/madflow/wavefunctions_flow.py and
+ * phasespace.py and the vegasflow calls of scripts/madflow_exec.py:487-525 (reference has no
+ * native ABI for these; its only native boundary is the per-process TF custom op, see
+ * madflow_b200_process.h).
+ *
+ * Conventions as in madflow_b200_process.h: `d_` = device pointer, caller owns all memory,
+ * asynchronous on `stream` (cudaStream_t as void*), 0 = success, negative = error,
+ * mf_last_error() gives the text.
+ */
+#ifndef MADFLOW_B200_H
+#define MADFLOW_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_VEGAS_BINS 50
+#define MF_VEGAS_HEADER 4   /* accumulators: sum t, sum t^2, #events with non-zero t, reserved */
+#define MF_MAX_DIM 32
+
+const char* mf_last_error(void);
+int mf_version(void);
+
+/* ---- HELAS external wavefunctions (wavefunctions_flow.py:33-154) -------------------------------
+ * kind: 0 ixxxxx, 1 oxxxxx, 2 vxxxxx, 3 sxxxxx.  d_p: (nevt,4) momenta (E,px,py,pz).
+ * d_out: (6,nevt) complex128 interleaved ((3,nevt) for sxxxxx), the reference's output layout. */
+int mf_wavefunction(int kind, const double* d_p, int64_t nevt, double mass, int nhel, int nsf, double sqh,
+                    double* d_out, void* stream);
+
+/* ---- ALOHA vertex routines (test hook; PyOut_create_aloha.py output) ---------------------------
+ * id: 0 FFV1_0, 1 FFV1_1, 2 FFV1_2, 3 VVV1P0_1, 4 VVV1_0, 5 FFV1P0_3, 6/7/8 VVVV{1,3,4}_0,
+ * 9/10/11 VVVV{1,3,4}P0_1.  Inputs: up to four (6,nevt) complex wavefunctions in the routine's
+ * argument order (unused = NULL).  d_out: (nevt,) complex for amplitudes, (6,nevt) otherwise.  */
+int mf_aloha(int id, const double* d_a, const double* d_b, const double* d_c, const double* d_d, int64_t nevt,
+             double coup_re, double coup_im, double mass, double width, double* d_out, void* stream);
+
+/* ---- phase space (phasespace.py) --------------------------------------------------------------- */
+typedef struct mf_cut {
+  int32_t var;       /* 0 pt, 1 mt, 2 mt2 */
+  int32_t particle;
+  int32_t has_min, has_max;
+  double vmin, vmax;
+} mf_cut;
+
+typedef struct mf_ps_const {
+  double pi, acc, gev2pb;   /* reference (float32-rounded) or exact, see DESIGN.md */
+} mf_ps_const;
+
+/* rambo (phasespace.py:145-212): d_x (nevt, 4*nout) uniforms; sqrts scalar, or per event when
+ * d_sqrts != NULL; masses NULL or nout doubles (host).  d_p (nevt,nout,4), d_w (nevt,).          */
+int mf_rambo(int nout, const double* d_x, int64_t nevt, double sqrts, const double* d_sqrts, const double* masses,
+             const mf_ps_const* k, double* d_p, double* d_w, void* stream);
+
+/* ramboflow + cuts + boost (phasespace.py:257-319, 480-520): d_x (nevt, 4*(next-2)+2).
+ * Outputs for EVERY event (no compaction): d_p (nevt,next,4), d_w, d_x1, d_x2 (nevt,),
+ * d_pass (nevt,) uint8 = all cuts passed (evaluated on the COM momenta); lab_frame boosts d_p.   */
+int mf_phasespace(int next, const double* d_x, int64_t nevt, double com_sqrts, const double* masses,
+                  const mf_ps_const* k, const mf_cut* cuts, int ncuts, int lab_frame, double* d_p, double* d_w,
+                  double* d_x1, double* d_x2, uint8_t* d_pass, void* stream);
+
+/* _boost_to_lab (phasespace.py:322-356) in place on (nevt,next,4)                                 */
+int mf_boost_to_lab(int next, double* d_p, const double* d_x1, const double* d_x2, int64_t nevt, void* stream);
+
+/* ---- VEGAS ([EXT] vegasflow; DESIGN.md "VEGAS") ------------------------------------------------ */
+/* Philox uniforms in [0,1): (nevt, ndim), global event index = first_event + row                  */
+int mf_philox_uniform(uint64_t seed, uint32_t iteration, uint64_t first_event, int64_t nevt, int ndim,
+                      double* d_out, void* stream);
+/* sample: d_x (nevt,ndim) mapped points, d_xjac (nevt,) = vegas weight * inv_total_events,
+ * d_bins (ndim,nevt) uint8 bin indices.  d_grid (ndim,51).                                        */
+int mf_vegas_sample(const double* d_grid, int ndim, uint64_t seed, uint32_t iteration, uint64_t first_event,
+                    int64_t nevt, double inv_total_events, double* d_x, double* d_xjac, uint8_t* d_bins,
+                    void* stream);
+int mf_vegas_blocks(void);
+/* accumulate: t = xjac*f; partial (nblocks, 4+ndim*50): header (see MF_VEGAS_HEADER), histogram of t^2 */
+int mf_vegas_accumulate(const double* d_f, const double* d_xjac, const uint8_t* d_bins, int64_t nevt, int ndim,
+                        int with_hist, double* d_partial, int nblocks, void* stream);
+/* sums (4+ndim*50) = [add ? sums : 0] + sum over blocks, in fixed order (deterministic)           */
+int mf_vegas_reduce(const double* d_partial, int nblocks, int ndim, int add, double* d_sums, void* stream);
+/* Lepage refinement (alpha = 1.5) of d_grid in place from the histogram in d_sums[4:]             */
+int mf_vegas_refine(double* d_grid, const double* d_sums, int ndim, void* stream);
+
+/* ---- measurement -------------------------------------------------------------------------------
+ * FP64 FMA throughput of the current device, measured: `iters` dependent DFMA per chain, 8 chains
+ * per thread, full grid.  Synchronous.  Returns TFLOP/s in *tflops (2 flop per DFMA).            */
+int mf_fp64_peak(int iters, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

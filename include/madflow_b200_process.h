@@ -1,0 +1,112 @@
+/* C ABI of one compiled process library  (libmfp_<process>.so).
+ *
+ * One library per MG5 subprocess, produced by madflow_b200.codegen from the process IR
+ * (built-in generator or the `pyout` MG5 plugin in CUDA mode).  It replaces what the reference
+ * builds per subprocess with `--custom_op`:  the TensorFlow custom op `Matrix<proc>` registered by
+ * python_package/madflow/custom_op/constants.py:104-161 and driven once PER HELICITY from
+ * `cusmatrix` (custom_op/generation.py:234-294).  Here one call evaluates all helicities.
+ *
+ * Conventions: plain pointers and sizes; `d_` pointers are DEVICE addresses, others host;
+ * the caller owns every buffer; every call is asynchronous on `stream` (a cudaStream_t passed as
+ * void*, NULL = default stream) unless stated; return 0 on success, negative on error with the
+ * text available from mfp_last_error().  No global state besides the last-error string.
+ */
+#ifndef MADFLOW_B200_PROCESS_H
+#define MADFLOW_B200_PROCESS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFP_MAX_PARAMS 8     /* masses and widths (real)            */
+#define MFP_MAX_COUPLINGS 8  /* couplings (complex)                 */
+#define MFP_MAX_OUT 8        /* outgoing particles                  */
+#define MFP_MAX_CUTS 16
+#define MFP_LAYOUT_AOS 0     /* (nevt, nexternal, 4)  -- the reference's layout, phasespace.py:4-5 */
+#define MFP_LAYOUT_SOA 1     /* (nexternal, 4, nevt)  -- coalesced                                 */
+
+typedef struct mfp_info {
+  char name[64];            /* MG5 shell string, e.g. "1_gg_ttx"  (matrix_method_python.inc:77)  */
+  int32_t nexternal, ninitial, ncomb, ncolor, ndiags, namps, nwavefuncs;
+  int32_t nparams, ncouplings;
+  int32_t ndim;             /* 4*(nexternal-2)+2 random numbers per event (madflow_exec.py:360)  */
+  int32_t block_threads;    /* CUDA block size the kernels were compiled for                     */
+  double denominator;       /* helicity/colour/identical-particle average (inc:104)              */
+  double flops_per_event;   /* algorithmic FP64 flop of smatrix, reference call list */
+} mfp_info;
+
+int mfp_get_info(mfp_info* out);
+/* names of the real parameters / complex couplings, in the order smatrix expects them
+ * (sorted masses+widths, then sorted couplings: PyOut_exporter.py:244,407)                      */
+const char* mfp_param_name(int i);
+const char* mfp_coupling_name(int i);
+/* coupling i = (re + i*im) * G^power, G = 2 sqrt(pi alpha_s)   (parameters.py:13-15)            */
+int mfp_coupling_def(int i, double* re, double* im, int* power);
+/* helicity table entry (generated order)                                                         */
+int mfp_helicity(int icomb, int leg);
+
+/* Matrix_<proc>.smatrix (matrix_method_python.inc:80-104): |M|^2 summed over helicities and
+ * colours, averaged.  d_p: momenta (E,px,py,pz) in `layout`; par: nparams host doubles;
+ * d_coup: complex couplings, interleaved re/im, shape (ncouplings, nevt) if coup_stride==1 or
+ * (ncouplings, 1) if coup_stride==0 (frozen model, parameters.py:44-53);
+ * sqh: the sqrt(1/2) to use (reference: float32-rounded, wavefunctions_flow.py:10);
+ * d_out: nevt doubles.                                                                           */
+int mfp_smatrix(const double* d_p, int layout, int64_t nevt, const double* par, const double* d_coup,
+                int64_t coup_stride, double sqh, double* d_out, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies in, runs, copies out, synchronises. */
+int mfp_smatrix_host(const double* h_p, int layout, int64_t nevt, const double* par, const double* h_coup,
+                     int64_t coup_stride, double sqh, double* h_out);
+
+/* Per-helicity values Matrix_<proc>.matrix (inc:106-138) for one helicity row; test hook.      */
+int mfp_matrix_hel(const double* d_p, int layout, int64_t nevt, int icomb, const double* par,
+                   const double* d_coup, int64_t coup_stride, double sqh, double* d_out, void* stream);
+
+typedef struct mfp_cut {
+  int32_t var;        /* 0 = pt, 1 = mt, 2 = mt2   (phasespace.py:405-422)   */
+  int32_t particle;   /* index into the nexternal momenta                     */
+  int32_t has_min, has_max;
+  double vmin, vmax;  /* strict: vmin < var < vmax (phasespace.py:444-461)   */
+} mfp_cut;
+
+typedef struct mfp_integrand_args {
+  /* VEGAS sampling ([EXT] vegasflow; DESIGN.md "VEGAS") */
+  const double* d_grid;     /* (ndim, 51) bin edges                                              */
+  uint64_t seed;            /* Philox key                                                        */
+  uint32_t iteration;       /* Philox counter word 2                                             */
+  uint64_t first_event;     /* global index of this call's first event (Philox counter 0-1)      */
+  int64_t nevents;          /* events this call generates                                        */
+  double inv_total_events;  /* 1/N of the whole iteration: xjac = vegas weight / N               */
+  /* phase space (phasespace.py:359-520) */
+  double com_sqrts;
+  double masses[MFP_MAX_OUT];
+  int32_t lab_frame;        /* boost to the lab before the matrix element (com_output=False)     */
+  int32_t ncuts;
+  mfp_cut cuts[MFP_MAX_CUTS];
+  double pi, acc, gev2pb;   /* constants: reference (float32-rounded) or exact                   */
+  /* model (parameters.py) */
+  double par[MFP_MAX_PARAMS];
+  int32_t alpha_mode;       /* 0: frozen alpha_s;  1: one-loop running at q2 = (sum mT / 2)^2    */
+  double alpha_s;           /* frozen value, or alpha_s(mz2) for the running                      */
+  double mz2, b0;           /* running: alpha_s / (1 + alpha_s*b0*log(q2/mz2))                    */
+  double sqh;
+  /* output */
+  double* d_partial;        /* (nblocks, 4 + ndim*50) block partials, fully overwritten:
+                             * [sum t, sum t^2, #events that reached the matrix element, 0] + hist */
+  int32_t nblocks;          /* grid size, from mfp_integrand_blocks()                             */
+  int32_t accumulate_hist;  /* 0 when the grid is frozen                                          */
+} mfp_integrand_args;
+
+/* recommended persistent grid size for the current device (multiple of the SM count)          */
+int mfp_integrand_blocks(void);
+/* One pass of the integrand of scripts/madflow_exec.py:422-470 (--no_pdf) over `nevents` events:
+ * Philox -> VEGAS map -> x1,x2 -> RAMBO -> cuts -> boost -> alpha_s -> smatrix -> weight ->
+ * block partial sums of xjac*f, (xjac*f)^2 and the per-dimension histogram of (xjac*f)^2.      */
+int mfp_integrand(const mfp_integrand_args* args, void* stream);
+
+const char* mfp_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,44 @@
+"""Build every CUDA library of the package for sm_100a, in-tree (madflow_b200/lib/*.so)."""
+import os
+import subprocess
+import sys
+
+from . import codegen, process_ir
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def builtin_irs():
+    irs = [process_ir.gg_ttx_pinned()]
+    try:
+        from . import procgen
+
+        irs += procgen.builtin_irs()
+    except ImportError:
+        pass
+    return irs
+
+
+def build_core(verbose=False):
+    os.makedirs(codegen.LIBDIR, exist_ok=True)
+    out = os.path.join(codegen.LIBDIR, "libmadflow_b200.so")
+    src = os.path.join(codegen.CSRC, "core.cu")
+    if os.path.exists(out) and os.path.getmtime(out) >= codegen._newest_header_mtime():
+        return out
+    cmd = ["nvcc"] + codegen.NVCC_FLAGS + ["-I", codegen.CSRC, "-o", out, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for core.cu:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
+def build_all(verbose=False):
+    libs = [build_core(verbose)]
+    for ir in builtin_irs():
+        libs.append(codegen.build_process(ir, verbose=verbose))
+    return libs
+
+
+if __name__ == "__main__":
+    for lib in build_all("-v" in sys.argv):
+        print(lib)

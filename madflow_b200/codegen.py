@@ -1,0 +1,273 @@
+"""CUDA emitter: process IR -> one sm_100a translation unit per process.
+
+This is the backend the north star asks the `pyout` plugin to gain.  It does the job of the
+reference's regex transpiler (python_package/madflow/custom_op_generator.py:22-118 and
+custom_op/*.py, which turn the generated Python `matrix()` into a TensorFlow custom op evaluated
+one helicity per launch) -- but from the structured IR instead of from Python text, and into ONE
+fused kernel per process: all helicities, JAMP sums and the colour contraction
+(see csrc/process_kernels.cuh).
+
+The emitted `Proc::matrix()` is straight-line code: the ordered HELAS call list with MG5-style
+wavefunction slot reuse, JAMPs accumulated as soon as each amplitude exists (same left-to-right
+order as the reference's jamp line, PyOut_exporter.py:334-375), and the colour quadratic form
+Re sum_ij J_i cf_ij conj(J_j)/denom_j (matrix_method_python.inc:137) with the integer matrix as
+compile-time constants (symmetric form when all row denominators are equal).
+"""
+import os
+import subprocess
+from fractions import Fraction
+
+from . import process_ir
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+GENDIR = os.path.join(CSRC, "generated")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
+]
+
+# Algorithmic FP64 flop per call, reference form of each routine (complex*complex = 6,
+# complex*real = 2, complex+-complex = 2, complex/complex = 11, *(+-1), *(+-i) free; momenta,
+# masses, widths real).  The first four are SURVEY.md section 8(d)'s counts of the frozen MG5
+# routines; the others are counted the same way on the expression MG5's ALOHA writes for them.
+FLOPS = {
+    "vxxxxx": 30, "ixxxxx": 30, "oxxxxx": 30, "sxxxxx": 2,
+    "FFV1_0": 108, "FFV1_1": 370, "FFV1_2": 370, "VVV1P0_1": 248,
+    "VVV1_0": 208, "FFV1P0_3": 176,
+    "VVVV1_0": 140, "VVVV3_0": 140, "VVVV4_0": 140,
+    "VVVV1P0_1": 176, "VVVV3P0_1": 176, "VVVV4P0_1": 176,
+}
+
+# known alpha_s dependence of the SM QCD couplings: c = (re + i im) * G^power
+# GC_10, GC_11 pinned by tests/mockup_debug_me.py:24-25; GC_12 = i G^2 is [EXT] models/sm.
+COUPLING_DEFS = {"GC_10": (-1.0, 0.0, 1), "GC_11": (0.0, 1.0, 1), "GC_12": (0.0, 1.0, 2)}
+
+
+def flops_per_event(ir):
+    """F_alg of SURVEY.md section 8(d): ncomb*(sum calls + F_jamp + F_colour) + ncomb + 1."""
+    per_hel = sum(FLOPS[c["op"]] for c in ir["calls"])
+    fj = 0
+    for terms in ir["jamp"]:
+        fj += 2 * (len(terms) - 1)
+        for _, re, im in terms:
+            if (abs(re), abs(im)) not in ((1.0, 0.0), (0.0, 1.0)):
+                fj += 2
+    ncolor = len(ir["jamp"])
+    per_hel += fj + ncolor * ncolor * 10 + 2 * ncolor
+    return ir["ncomb"] * per_hel + ir["ncomb"] + 1
+
+
+def _cname(ir):
+    return "".join(ch if ch.isalnum() else "_" for ch in ir["name"])
+
+
+def _par_expr(ir, name):
+    if name == "ZERO":
+        return "0.0"
+    return f"par[{ir['params'].index(name)}]"
+
+
+def _coup_expr(ir, c):
+    e = f"coup[{ir['couplings'].index(c['coup'])}]"
+    return f"(-{e})" if c.get("coup_sign", 1) < 0 else e
+
+
+def _emit_call(ir, c):
+    op = c["op"]
+    if op in ("vxxxxx", "ixxxxx", "oxxxxx"):
+        extra = "sqh, " if op == "vxxxxx" else ""
+        return (f"mf::{op}(p[{c['leg']}], {_par_expr(ir, c['mass'])}, P_hel(icomb, {c['leg']}), {c['nsf']}, "
+                f"{extra}w{c['out']});")
+    if op == "sxxxxx":
+        return f"mf::sxxxxx(p[{c['leg']}], {c['nsf']}, w{c['out']});"
+    ins = ", ".join(f"w{i}" for i in c["in"])
+    fn = op
+    if op.startswith("VVVV"):
+        kind = op[4]
+        fn = f"VVVV_0<{kind}>" if op.endswith("_0") else f"VVVVP0_1<{kind}>"
+    if "amp" in c:
+        return f"mf::{fn}({ins}, {_coup_expr(ir, c)})"
+    return (f"mf::{fn}({ins}, {_coup_expr(ir, c)}, {_par_expr(ir, c['mass'])}, {_par_expr(ir, c['width'])}, "
+            f"w{c['out']});")
+
+
+def _jamp_update(j, re, im, amp):
+    """C++ statement adding (re + i im)*amp to jamp j."""
+    if im == 0.0:
+        if re == 1.0:
+            return f"J{j} += {amp};"
+        if re == -1.0:
+            return f"J{j} -= {amp};"
+        return f"J{j} += {re!r} * {amp};"
+    if re == 0.0:
+        if im == 1.0:
+            return f"J{j} += mul_i({amp});"
+        if im == -1.0:
+            return f"J{j} += mul_mi({amp});"
+        return f"J{j} += {im!r} * mul_i({amp});"
+    return f"J{j} += mk({re!r}, {im!r}) * {amp};"
+
+
+def emit_matrix_body(ir):
+    lines = []
+    slots = sorted({c["out"] for c in ir["calls"] if "out" in c})
+    lines.append("    cxd " + ", ".join(f"w{s}[6]" for s in slots) + ";")
+    ncolor = len(ir["jamp"])
+    lines.append("    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(ncolor)) + ";")
+    by_amp = {}
+    for j, terms in enumerate(ir["jamp"]):
+        for k, re, im in terms:
+            by_amp.setdefault(k, []).append((j, float(re), float(im)))
+    for c in ir["calls"]:
+        if "amp" in c:
+            k = c["amp"]
+            uses = by_amp.get(k, [])
+            if not uses:
+                continue
+            lines.append(f"    {{ const cxd amp = {_emit_call(ir, c)};")
+            for j, re, im in uses:
+                lines.append("      " + _jamp_update(j, re, im, "amp"))
+            lines.append("    }")
+        else:
+            lines.append("    " + _emit_call(ir, c))
+    # colour contraction
+    cf, den = ir["color_num"], ir["color_denom"]
+    uniform = len(set(den)) == 1 and all(cf[i][j] == cf[j][i] for i in range(ncolor) for j in range(ncolor))
+    if uniform:
+        lines.append("    double me = 0.0;")
+        for i in range(ncolor):
+            terms = []
+            for j in range(i + 1, ncolor):
+                if cf[i][j] != 0:
+                    terms.append((j, 2 * cf[i][j]))
+            # row i: J_i . (cf_ii J_i + sum_{j>i} 2 cf_ij J_j)
+            lines.append(f"    {{ double tr = {float(cf[i][i])!r} * J{i}.re, ti = {float(cf[i][i])!r} * J{i}.im;")
+            for j, v in terms:
+                lines.append(f"      tr += {float(v)!r} * J{j}.re; ti += {float(v)!r} * J{j}.im;")
+            lines.append(f"      me += J{i}.re * tr + J{i}.im * ti; }}")
+        lines.append(f"    return me / {float(den[0])!r};")
+    else:
+        lines.append("    double me = 0.0;")
+        for j in range(ncolor):
+            lines.append("    { cxd z = mk(0.0, 0.0);")
+            for i in range(ncolor):
+                if cf[i][j] != 0:
+                    lines.append(f"      z += {float(cf[i][j])!r} * J{i};")
+            lines.append(f"      me += (z.re * J{j}.re + z.im * J{j}.im) / {float(den[j])!r}; }}")
+        lines.append("    return me;")
+    return "\n".join(lines)
+
+
+def choose_launch(ir):
+    """Block size / minimum resident blocks per SM by process size (one event per thread)."""
+    ncalls = len(ir["calls"])
+    if ncalls <= 16:
+        return 128, 3
+    if ncalls <= 64:
+        return 128, 2
+    return 128, 1
+
+
+def emit_process_source(ir, block=None, minblocks=None):
+    process_ir.validate(ir)
+    n = ir["nexternal"]
+    ncolor = len(ir["jamp"])
+    namps = len({c["amp"] for c in ir["calls"] if "amp" in c})
+    b, mb = choose_launch(ir)
+    block = block or b
+    minblocks = minblocks or mb
+    hel_flat = ", ".join(str(int(h)) for row in ir["helicities"] for h in row)
+    cdefs = []
+    for cname in ir["couplings"]:
+        if cname not in COUPLING_DEFS:
+            raise ValueError(f"coupling {cname}: alpha_s dependence unknown to the CUDA backend")
+        cdefs.append(COUPLING_DEFS[cname])
+
+    def switch(vals, fmt):
+        body = " ".join(f"case {i}: return {fmt(v)};" for i, v in enumerate(vals))
+        return f"switch (i) {{ {body} default: return {fmt(0)}; }}"
+
+    pnames = ", ".join(f'"{p}"' for p in ir["params"]) or '""'
+    cnames = ", ".join(f'"{c}"' for c in ir["couplings"]) or '""'
+    src = f"""// GENERATED by madflow_b200.codegen -- do not edit.  Process: {ir.get('process', ir['name'])}
+// One fused FP64 kernel per process: HELAS wavefunctions -> ALOHA vertices -> JAMP -> colour matrix.
+#include "process_kernels.cuh"
+
+namespace {{
+__device__ __constant__ signed char d_hel[{ir['ncomb'] * n}] = {{{hel_flat}}};
+static const signed char h_hel[{ir['ncomb'] * n}] = {{{hel_flat}}};
+
+MF_DEV int P_hel(int icomb, int leg) {{
+#ifdef __CUDA_ARCH__
+  return d_hel[icomb * {n} + leg];
+#else
+  return h_hel[icomb * {n} + leg];
+#endif
+}}
+
+struct Proc {{
+  static constexpr int NEXT = {n}, NINIT = {ir['ninitial']}, NCOMB = {ir['ncomb']}, NCOLOR = {ncolor};
+  static constexpr int NDIAGS = {ir['ndiags']}, NAMPS = {namps}, NWF = {ir['nwavefuncs']};
+  static constexpr int NPAR = {len(ir['params'])}, NCOUP = {len(ir['couplings'])};
+  static constexpr int BLOCK = {block}, MINBLOCKS = {minblocks};
+  static constexpr double DENOM = {float(ir['denominator'])!r};
+  static constexpr double FLOPS = {float(flops_per_event(ir))!r};
+  static const char* name() {{ return "{ir['name']}"; }}
+  static const char* param_name(int i) {{ static const char* n[] = {{{pnames}}}; return n[i]; }}
+  static const char* coupling_name(int i) {{ static const char* n[] = {{{cnames}}}; return n[i]; }}
+  MF_DEV static constexpr double coup_re(int i) {{ {switch([c[0] for c in cdefs], lambda v: repr(float(v)))} }}
+  MF_DEV static constexpr double coup_im(int i) {{ {switch([c[1] for c in cdefs], lambda v: repr(float(v)))} }}
+  MF_DEV static constexpr int coup_power(int i) {{ {switch([c[2] for c in cdefs], lambda v: str(int(v)))} }}
+  MF_DEV static int hel(int icomb, int leg) {{ return P_hel(icomb, leg); }}
+
+  // Matrix_{_cname(ir)}.matrix for helicity row `icomb`
+  MF_DEV static double matrix(const double (*p)[4], int icomb, const double* par, const cxd* coup, double sqh) {{
+{emit_matrix_body(ir)}
+  }}
+}};
+}}  // namespace
+
+MF_DEFINE_PROCESS(Proc)
+"""
+    return src
+
+
+def lib_path(ir_or_name):
+    name = ir_or_name if isinstance(ir_or_name, str) else ir_or_name["name"]
+    return os.path.join(LIBDIR, f"libmfp_{name}.so")
+
+
+def build_process(ir, out=None, verbose=False, extra_flags=()):
+    """Emit and compile one process.  Returns the path of the shared library."""
+    os.makedirs(GENDIR, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    src_path = os.path.join(GENDIR, f"proc_{ir['name']}.cu")
+    text = emit_process_source(ir)
+    old = open(src_path).read() if os.path.exists(src_path) else None
+    out = out or lib_path(ir)
+    if old == text and os.path.exists(out) and os.path.getmtime(out) >= _newest_header_mtime():
+        return out
+    with open(src_path, "w") as fh:
+        fh.write(text)
+    with open(os.path.join(GENDIR, f"proc_{ir['name']}.json"), "w") as fh:
+        fh.write(process_ir.dumps(ir))
+    cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-I", CSRC, "-o", out, src_path]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {ir['name']}:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return out
+
+
+def _newest_header_mtime():
+    t = 0.0
+    for f in os.listdir(CSRC):
+        if f.endswith((".cuh", ".h", ".cu")):
+            t = max(t, os.path.getmtime(os.path.join(CSRC, f)))
+    t = max(t, os.path.getmtime(os.path.join(os.path.dirname(CSRC), "..", "include", "madflow_b200_process.h")))
+    return t

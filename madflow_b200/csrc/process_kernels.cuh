@@ -1,0 +1,395 @@
+// Kernels and C-ABI glue shared by every generated process translation unit.
+//
+// A generated file defines `struct Proc` (constants, helicity table, `matrix()` = the ordered HELAS
+// call list + JAMP + colour contraction of ONE helicity, i.e. the body of the reference's
+// Matrix_<proc>.matrix, madgraph_plugin/template_files/matrix_method_python.inc:106-138) and then
+// expands MF_DEFINE_PROCESS(Proc), which instantiates:
+//
+//   smatrix_kernel<Proc>    Matrix_<proc>.smatrix (inc:80-104): one event per thread, runtime
+//                           (warp-uniform) loop over all helicity rows, result / denominator.
+//   integrand_kernel<Proc>  the whole per-event integrand of scripts/madflow_exec.py:422-470 fused
+//                           in one persistent kernel: Philox -> VEGAS map (grid in shared memory)
+//                           -> x1,x2 -> RAMBO -> cuts -> boost -> alpha_s/couplings -> smatrix ->
+//                           weight -> per-block sums + shared-memory histogram.  Events that fail
+//                           the cuts are dropped before the matrix element: accepted events are
+//                           queued in shared memory and the matrix element always runs on full
+//                           blocks (the reference compacts with tf.boolean_mask, phasespace.py:506-515).
+#pragma once
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/madflow_b200_process.h"
+#include "aloha_sm.cuh"
+#include "helas.cuh"
+#include "phasespace.cuh"
+#include "philox.cuh"
+#include "vegas.cuh"
+
+namespace mf {
+
+static thread_local char g_err[512] = "";
+static inline int fail(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -1;
+}
+static inline int fail_msg(const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return -2;
+}
+
+struct SmatrixArgs {
+  const double* p;
+  int layout;
+  long long nevt;
+  double par[MFP_MAX_PARAMS];
+  const double* coup;
+  long long coup_stride;
+  double sqh;
+  double* out;
+  int only_comb;  // >= 0: evaluate this helicity row only and do not average (test hook)
+};
+
+template <class P>
+MF_DEV void load_momenta(const double* p, int layout, long long nevt, long long ev, double m[P::NEXT][4]) {
+  if (layout == MFP_LAYOUT_AOS) {
+    const double4* q = reinterpret_cast<const double4*>(p) + ev * P::NEXT;
+#pragma unroll
+    for (int i = 0; i < P::NEXT; ++i) {
+      const double4 v = q[i];
+      m[i][0] = v.x, m[i][1] = v.y, m[i][2] = v.z, m[i][3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < P::NEXT; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m[i][k] = p[(long long)(i * 4 + k) * nevt + ev];
+  }
+}
+
+template <class P>
+MF_DEV double smatrix_event(const double m[P::NEXT][4], const double* par, const cxd* coup, double sqh) {
+  double acc = 0.0;
+#pragma unroll 1
+  for (int ic = 0; ic < P::NCOMB; ++ic) acc += P::matrix(m, ic, par, coup, sqh);
+  return acc / P::DENOM;
+}
+
+template <class P>
+__global__ void __launch_bounds__(P::BLOCK, P::MINBLOCKS) smatrix_kernel(const SmatrixArgs a) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < a.nevt; ev += stride) {
+    double m[P::NEXT][4];
+    load_momenta<P>(a.p, a.layout, a.nevt, ev, m);
+    cxd coup[P::NCOUP > 0 ? P::NCOUP : 1];
+    const double2* c2 = reinterpret_cast<const double2*>(a.coup);
+#pragma unroll
+    for (int c = 0; c < P::NCOUP; ++c) {
+      const double2 v = a.coup_stride ? c2[(long long)c * a.nevt + ev] : c2[c];
+      coup[c] = mk(v.x, v.y);
+    }
+    if (a.only_comb >= 0)
+      a.out[ev] = P::matrix(m, a.only_comb, a.par, coup, a.sqh);
+    else
+      a.out[ev] = smatrix_event<P>(m, a.par, coup, a.sqh);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused integrand
+struct IntegrandArgs {
+  mfp_integrand_args u;  // the caller's description
+  // derived on the host
+  int massive;
+  double shat_min;
+  PSConst ps;
+  CutList cuts;
+};
+
+template <class P>
+struct IntegrandSmem {
+  static constexpr int NDIM = 4 * (P::NEXT - 2) + 2;
+  static constexpr int QCAP = 2 * P::BLOCK;
+  double grid[NDIM * VEGAS_EDGES];
+  double hist[NDIM * VEGAS_BINS];
+  double qmom[P::NEXT * 4][QCAP];
+  double qw[QCAP];      // xjac * phase-space weight
+  double qas[QCAP];     // alpha_s
+  unsigned char qbin[NDIM][QCAP];
+  int warp_count[32];
+  double red[3][32];
+};
+
+MF_DEV double alpha_s_of(const mfp_integrand_args& u, double q2) {
+  if (u.alpha_mode == 0) return u.alpha_s;
+  return u.alpha_s / (1.0 + u.alpha_s * u.b0 * log(q2 / u.mz2));
+}
+
+template <class P>
+__device__ __forceinline__ void integrand_process_entry(const IntegrandArgs& a, IntegrandSmem<P>& s, int slot,
+                                                        double& s1, double& s2, double& cnt) {
+  constexpr int NDIM = IntegrandSmem<P>::NDIM;
+  double m[P::NEXT][4];
+#pragma unroll
+  for (int i = 0; i < P::NEXT; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[i][k] = s.qmom[i * 4 + k][slot];
+  // couplings from alpha_s: G = 2 sqrt(pi alpha_s) (parameters.py:13-15), c = (re + i im) G^power
+  const double G = 2.0 * sqrt(M_PI * s.qas[slot]);
+  cxd coup[P::NCOUP > 0 ? P::NCOUP : 1];
+#pragma unroll
+  for (int c = 0; c < P::NCOUP; ++c) {
+    double g = 1.0;
+    for (int k = 0; k < P::coup_power(c); ++k) g *= G;
+    coup[c] = mk(P::coup_re(c) * g, P::coup_im(c) * g);
+  }
+  const double me = smatrix_event<P>(m, a.u.par, coup, a.u.sqh);
+  const double t = me * s.qw[slot];
+  const double t2 = t * t;
+  s1 += t;
+  s2 += t2;
+  cnt += 1.0;
+  if (a.u.accumulate_hist) {
+#pragma unroll 1
+    for (int d = 0; d < NDIM; ++d) atomicAdd(&s.hist[d * VEGAS_BINS + s.qbin[d][slot]], t2);
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(P::BLOCK, P::MINBLOCKS) integrand_kernel(const IntegrandArgs a) {
+  constexpr int NDIM = IntegrandSmem<P>::NDIM;
+  constexpr int B = P::BLOCK;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IntegrandSmem<P>& s = *reinterpret_cast<IntegrandSmem<P>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = B / 32;
+
+  for (int i = tid; i < NDIM * VEGAS_EDGES; i += B) s.grid[i] = a.u.d_grid[i];
+  for (int i = tid; i < NDIM * VEGAS_BINS; i += B) s.hist[i] = 0.0;
+  __syncthreads();
+
+  double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+  int qcount = 0;
+  const long long ntiles = (a.u.nevents + B - 1) / B;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long local = tile * B + tid;
+    bool ok = false;
+    double m[P::NEXT][4];
+    double wgt = 0.0, as = 0.0;
+    unsigned char bins[NDIM];
+    if (local < a.u.nevents) {
+      const unsigned long long ev = a.u.first_event + (unsigned long long)local;
+      double xr[NDIM];
+      double w = 1.0;
+#pragma unroll
+      for (int j = 0; j < (NDIM + 1) / 2; ++j) {
+        double u0, u1;
+        philox_pair(a.u.seed, a.u.iteration, ev, j, u0, u1);
+        int b;
+        xr[2 * j] = vegas_map(&s.grid[(2 * j) * VEGAS_EDGES], vegas_confine(u0), b, w);
+        bins[2 * j] = (unsigned char)b;
+        if (2 * j + 1 < NDIM) {
+          xr[2 * j + 1] = vegas_map(&s.grid[(2 * j + 1) * VEGAS_EDGES], vegas_confine(u1), b, w);
+          bins[2 * j + 1] = (unsigned char)b;
+        }
+      }
+      double x1, x2;
+      ramboflow<P::NEXT>(xr, a.u.com_sqrts, a.u.masses, a.massive != 0, a.shat_min, a.ps, m, wgt, x1, x2);
+      ok = pass_cuts<P::NEXT>(a.cuts, m);  // on centre-of-mass momenta (phasespace.py:506-508)
+      // a vanishing or non-finite weight cannot contribute; drop it like a cut event
+      ok = ok && (wgt == wgt) && (wgt != 0.0);
+      if (ok) {
+        if (a.u.lab_frame) boost_to_lab<P::NEXT>(m, x1, x2);
+        double q2 = 0.0;
+        if (a.u.alpha_mode != 0) {
+          double smt = 0.0;  // madflow_exec.py:428-430: q2 = (sum_out mT / 2)^2
+#pragma unroll
+          for (int i = 2; i < P::NEXT; ++i) smt += cut_value(CUT_MT, m[i]);
+          q2 = (smt / 2.0) * (smt / 2.0);
+        }
+        as = alpha_s_of(a.u, q2);
+        wgt *= w * a.u.inv_total_events;
+      }
+    }
+    // block-wide stable compaction of the accepted events into the shared queue
+    const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s.warp_count[warp] = __popc(ballot);
+    __syncthreads();
+    int base = qcount, total = 0;
+#pragma unroll
+    for (int wv = 0; wv < NWARP; ++wv) {
+      const int c = s.warp_count[wv];
+      if (wv < warp) base += c;
+      total += c;
+    }
+    if (ok) {
+      const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+#pragma unroll
+      for (int i = 0; i < P::NEXT; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.qmom[i * 4 + k][slot] = m[i][k];
+      s.qw[slot] = wgt;
+      s.qas[slot] = as;
+#pragma unroll
+      for (int d = 0; d < NDIM; ++d) s.qbin[d][slot] = bins[d];
+    }
+    qcount += total;
+    __syncthreads();
+    if (qcount >= B) {  // at most once per tile: qcount < 2B always
+      integrand_process_entry<P>(a, s, qcount - B + tid, s1, s2, cnt);
+      qcount -= B;
+      __syncthreads();
+    }
+  }
+  if (tid < qcount) integrand_process_entry<P>(a, s, tid, s1, s2, cnt);
+
+  // deterministic block reduction of the two sums
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+    s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) s.red[0][warp] = s1, s.red[1][warp] = s2, s.red[2][warp] = cnt;
+  __syncthreads();
+  double* out = a.u.d_partial + (long long)blockIdx.x * (VEGAS_HEADER + NDIM * VEGAS_BINS);
+  if (tid == 0) {
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int wv = 0; wv < NWARP; ++wv) t1 += s.red[0][wv], t2 += s.red[1][wv], t3 += s.red[2][wv];
+    out[0] = t1, out[1] = t2, out[2] = t3, out[3] = 0.0;
+  }
+  for (int i = tid; i < NDIM * VEGAS_BINS; i += B) out[VEGAS_HEADER + i] = s.hist[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+template <class P>
+int launch_smatrix(const double* d_p, int layout, long long nevt, const double* par, const double* d_coup,
+                   long long coup_stride, double sqh, double* d_out, int only_comb, cudaStream_t st) {
+  if (nevt <= 0) return 0;
+  if (layout != MFP_LAYOUT_AOS && layout != MFP_LAYOUT_SOA) return fail_msg("mfp_smatrix: unknown layout");
+  if (P::NCOUP > 0 && d_coup == nullptr) return fail_msg("mfp_smatrix: couplings missing");
+  SmatrixArgs a;
+  a.p = d_p, a.layout = layout, a.nevt = nevt, a.coup = d_coup, a.coup_stride = coup_stride, a.sqh = sqh;
+  a.out = d_out, a.only_comb = only_comb;
+  for (int i = 0; i < MFP_MAX_PARAMS; ++i) a.par[i] = i < P::NPAR ? par[i] : 0.0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (nevt + P::BLOCK - 1) / P::BLOCK;
+  const long long cap = (long long)sms * P::MINBLOCKS * 8;
+  if (blocks > cap) blocks = cap;  // grid-stride; a whole multiple of the resident set
+  smatrix_kernel<P><<<(unsigned)blocks, P::BLOCK, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("smatrix_kernel launch", e);
+  return 0;
+}
+
+template <class P>
+int integrand_blocks() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 1;
+  cudaFuncSetAttribute(integrand_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(IntegrandSmem<P>));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, integrand_kernel<P>, P::BLOCK, sizeof(IntegrandSmem<P>));
+  if (per_sm < 1) per_sm = 1;
+  return sms * per_sm;
+}
+
+template <class P>
+int launch_integrand(const mfp_integrand_args* u, cudaStream_t st) {
+  constexpr int NOUT = P::NEXT - 2;
+  if (u->nevents <= 0) return fail_msg("mfp_integrand: nevents must be positive");
+  if (u->ncuts > MFP_MAX_CUTS) return fail_msg("mfp_integrand: too many cuts");
+  if (u->nblocks <= 0) return fail_msg("mfp_integrand: nblocks must come from mfp_integrand_blocks()");
+  IntegrandArgs a;
+  a.u = *u;
+  double msum = 0.0;
+  for (int i = 0; i < NOUT; ++i) msum += u->masses[i];
+  a.massive = msum != 0.0;
+  a.shat_min = msum * msum;
+  a.ps.pi = u->pi, a.ps.acc = u->acc, a.ps.gev2pb = u->gev2pb;
+  a.ps.wt0 = std::log(u->pi / 2.0) * (NOUT - 1) - 2.0 * std::lgamma((double)(NOUT - 1)) - std::log((double)(NOUT - 1));
+  a.ps.inv_norm = 1.0 / std::pow(2 * u->pi, 3 * NOUT - 4);
+  a.cuts.n = u->ncuts;
+  for (int i = 0; i < u->ncuts; ++i) {
+    const mfp_cut& c = u->cuts[i];
+    if (c.particle < 0 || c.particle >= P::NEXT) return fail_msg("mfp_integrand: cut on a non-existent particle");
+    a.cuts.c[i] = Cut{c.var, c.particle, c.has_min, c.has_max, c.vmin, c.vmax};
+  }
+  cudaError_t e = cudaFuncSetAttribute(integrand_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(IntegrandSmem<P>));
+  if (e != cudaSuccess) return fail("integrand_kernel smem attribute", e);
+  integrand_kernel<P><<<u->nblocks, P::BLOCK, sizeof(IntegrandSmem<P>), st>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("integrand_kernel launch", e);
+  return 0;
+}
+
+template <class P>
+int smatrix_host(const double* h_p, int layout, long long nevt, const double* par, const double* h_coup,
+                 long long coup_stride, double sqh, double* h_out) {
+  if (nevt <= 0) return 0;
+  double *d_p = nullptr, *d_c = nullptr, *d_o = nullptr;
+  const size_t pb = (size_t)nevt * P::NEXT * 4 * sizeof(double);
+  const size_t cb = (size_t)(coup_stride ? nevt : 1) * P::NCOUP * 2 * sizeof(double);
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_p, pb)) != cudaSuccess) return fail("cudaMalloc momenta", e);
+  if ((e = cudaMalloc(&d_o, nevt * sizeof(double))) != cudaSuccess) { cudaFree(d_p); return fail("cudaMalloc out", e); }
+  if (cb && (e = cudaMalloc(&d_c, cb)) != cudaSuccess) { cudaFree(d_p); cudaFree(d_o); return fail("cudaMalloc coup", e); }
+  int rc = 0;
+  if ((e = cudaMemcpy(d_p, h_p, pb, cudaMemcpyHostToDevice)) != cudaSuccess) rc = fail("H2D momenta", e);
+  if (!rc && cb && (e = cudaMemcpy(d_c, h_coup, cb, cudaMemcpyHostToDevice)) != cudaSuccess) rc = fail("H2D coup", e);
+  if (!rc) rc = launch_smatrix<P>(d_p, layout, nevt, par, d_c, coup_stride, sqh, d_o, -1, 0);
+  if (!rc && (e = cudaMemcpy(h_out, d_o, nevt * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
+    rc = fail("D2H result", e);
+  cudaFree(d_p), cudaFree(d_o);
+  if (d_c) cudaFree(d_c);
+  return rc;
+}
+
+}  // namespace mf
+
+#define MF_DEFINE_PROCESS(P)                                                                                   \
+  extern "C" {                                                                                                 \
+  int mfp_get_info(mfp_info* o) {                                                                              \
+    if (!o) return mf::fail_msg("mfp_get_info: null pointer");                                                 \
+    memset(o, 0, sizeof(*o));                                                                                  \
+    strncpy(o->name, P::name(), sizeof(o->name) - 1);                                                          \
+    o->nexternal = P::NEXT, o->ninitial = P::NINIT, o->ncomb = P::NCOMB, o->ncolor = P::NCOLOR;                \
+    o->ndiags = P::NDIAGS, o->namps = P::NAMPS, o->nwavefuncs = P::NWF, o->nparams = P::NPAR;                  \
+    o->ncouplings = P::NCOUP, o->ndim = 4 * (P::NEXT - 2) + 2, o->block_threads = P::BLOCK;                    \
+    o->denominator = P::DENOM, o->flops_per_event = P::FLOPS;                                                  \
+    return 0;                                                                                                  \
+  }                                                                                                            \
+  const char* mfp_param_name(int i) { return (i >= 0 && i < P::NPAR) ? P::param_name(i) : ""; }                \
+  const char* mfp_coupling_name(int i) { return (i >= 0 && i < P::NCOUP) ? P::coupling_name(i) : ""; }         \
+  int mfp_coupling_def(int i, double* re, double* im, int* power) {                                            \
+    if (i < 0 || i >= P::NCOUP) return mf::fail_msg("mfp_coupling_def: index out of range");                   \
+    *re = P::coup_re(i), *im = P::coup_im(i), *power = P::coup_power(i);                                       \
+    return 0;                                                                                                  \
+  }                                                                                                            \
+  int mfp_helicity(int ic, int leg) {                                                                          \
+    return (ic >= 0 && ic < P::NCOMB && leg >= 0 && leg < P::NEXT) ? P::hel(ic, leg) : 0;                      \
+  }                                                                                                            \
+  int mfp_smatrix(const double* d_p, int layout, int64_t nevt, const double* par, const double* d_coup,        \
+                  int64_t cs, double sqh, double* d_out, void* st) {                                           \
+    return mf::launch_smatrix<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, -1, (cudaStream_t)st);        \
+  }                                                                                                            \
+  int mfp_matrix_hel(const double* d_p, int layout, int64_t nevt, int ic, const double* par,                   \
+                     const double* d_coup, int64_t cs, double sqh, double* d_out, void* st) {                  \
+    if (ic < 0 || ic >= P::NCOMB) return mf::fail_msg("mfp_matrix_hel: helicity row out of range");            \
+    return mf::launch_smatrix<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, ic, (cudaStream_t)st);        \
+  }                                                                                                            \
+  int mfp_smatrix_host(const double* h_p, int layout, int64_t nevt, const double* par, const double* h_coup,   \
+                       int64_t cs, double sqh, double* h_out) {                                                \
+    return mf::smatrix_host<P>(h_p, layout, nevt, par, h_coup, cs, sqh, h_out);                                \
+  }                                                                                                            \
+  int mfp_integrand_blocks(void) { return mf::integrand_blocks<P>(); }                                         \
+  int mfp_integrand(const mfp_integrand_args* a, void* st) {                                                   \
+    if (!a) return mf::fail_msg("mfp_integrand: null args");                                                   \
+    return mf::launch_integrand<P>(a, (cudaStream_t)st);                                                       \
+  }                                                                                                            \
+  const char* mfp_last_error(void) { return mf::g_err; }                                                       \
+  }

@@ -1,0 +1,30 @@
+// VEGAS grid mapping (device side).  Replaces vegasflow's `_generate_random_array`
+// ([EXT] vegasflow 1.x, not under /root/reference; call sites scripts/madflow_exec.py:487-525).
+//   u in (1e-8, 1-1e-8);  xn = BINS*(1-u);  k = floor(xn);  x = lo_k + (hi_k - lo_k)*(xn - k);
+//   weight *= BINS*(hi_k - lo_k).      Grid: edges[ndim][BINS+1], edges[d][0]=0, edges[d][BINS]=1.
+#pragma once
+#include "mf_complex.cuh"
+
+namespace mf {
+
+constexpr int VEGAS_BINS = 50;
+constexpr int VEGAS_EDGES = VEGAS_BINS + 1;
+constexpr double VEGAS_TECH_CUT = 1e-8;
+// accumulator layout: [sum t, sum t^2, events that reached the matrix element, reserved] + histogram
+constexpr int VEGAS_HEADER = 4;
+
+MF_DEV double vegas_confine(double u) { return VEGAS_TECH_CUT + u * (1.0 - 2.0 * VEGAS_TECH_CUT); }
+
+// edges: this dimension's VEGAS_EDGES numbers (shared or global memory)
+MF_DEV double vegas_map(const double* edges, double r, int& bin, double& w) {
+  const double xn = VEGAS_BINS * (1.0 - r);
+  int k = (int)xn;
+  k = k < 0 ? 0 : (k > VEGAS_BINS - 1 ? VEGAS_BINS - 1 : k);
+  const double lo = edges[k], hi = edges[k + 1];
+  const double delta = hi - lo;
+  bin = k;
+  w *= delta * VEGAS_BINS;
+  return lo + delta * (xn - k);
+}
+
+}  // namespace mf

@@ -1,0 +1,117 @@
+"""The cross-section integrand of scripts/madflow_exec.py:422-470 as ONE fused kernel.
+
+    sigma-integrand(xrand) = smatrix(ps(xrand); couplings(alpha_s)) * ps_weight   (--no_pdf: luminosity 1)
+
+`FusedIntegrand` describes it (process, collider energy, masses, cuts, frame, alpha_s mode) and
+`VegasFlow` launches it (include/madflow_b200_process.h: mfp_integrand).  `python_integrand` gives
+the same function assembled from the separate API calls, exactly as the reference's
+`cross_section` closure is -- it is what the tests compare the fused kernel with.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _runtime as rt
+from . import config
+from .phasespace import PhaseSpaceGenerator
+
+MZ = 91.188
+
+
+def one_loop_b0(nf=5):
+    return (33.0 - 2.0 * nf) / (12.0 * math.pi)
+
+
+def alpha_s_one_loop(q2, alpha_mz=0.118, mz2=MZ * MZ, b0=None):
+    """alpha_s(q2) = a/(1 + a*b0*log(q2/mz2)).  Stands in for pdfflow.alphasQ2 (reference:
+    scripts/madflow_exec.py:431), which needs an LHAPDF grid that is not available offline."""
+    b0 = one_loop_b0() if b0 is None else b0
+    return alpha_mz / (1.0 + alpha_mz * b0 * torch.log(q2 / mz2))
+
+
+class FusedIntegrand:
+    def __init__(self, matrix, model, sqrts=13e3, masses=None, pt_cut=None, cuts=None, lab_frame=True,
+                 alpha_s=None, running=False, alpha_mz=0.118, mz=MZ, nf=5):
+        """alpha_s: frozen value (default: 0.118 as `madflow --no_pdf -q`, madflow_exec.py:379-380);
+        running=True: q2 = (sum mT/2)^2 per event (madflow_exec.py:428-431) with one-loop alpha_s."""
+        self.matrix, self.model = matrix, model
+        self._lib = matrix._lib
+        n = int(matrix.nexternal)
+        self.nexternal = n
+        self.n_dim = 4 * (n - 2) + 2
+        self.sqrts = float(sqrts)
+        self.masses = [float(m) for m in (masses if masses is not None else [0.0] * (n - 2))]
+        if len(self.masses) != n - 2:
+            raise ValueError("one mass per outgoing particle")
+        self.cuts = list(cuts or [])
+        if pt_cut is not None:  # madflow_exec.py:392-395
+            self.cuts += [("pt", i, float(pt_cut), None) for i in range(2, n)]
+        self.lab_frame = bool(lab_frame)
+        self.running = bool(running)
+        if alpha_s is None:
+            alpha_s = 0.118
+        if not running and config.get_constants().mode == "reference":
+            import numpy as np
+
+            alpha_s = float(np.float32(alpha_s))  # Model.freeze_alpha_s goes through float_me([a]) (parameters.py:53)
+        self.alpha_s = float(alpha_mz if running else alpha_s)
+        self.mz2, self.b0 = float(mz) ** 2, one_loop_b0(nf)
+        consts = list(model._constants)
+        self.par = [float(c.item() if isinstance(c, torch.Tensor) else c) for c in consts[: len(matrix.param_names)]]
+
+    def nblocks(self):
+        return self._lib.integrand_blocks()
+
+    def _args(self):
+        a = rt.mfp_integrand_args()
+        a.com_sqrts = self.sqrts
+        for i, m in enumerate(self.masses):
+            a.masses[i] = m
+        a.lab_frame = int(self.lab_frame)
+        a.ncuts = len(self.cuts)
+        for i, (var, particle, lo, hi) in enumerate(self.cuts):
+            a.cuts[i] = rt.mf_cut(rt.CUT_VARS[var], int(particle), lo is not None, hi is not None,
+                                  float(lo) if lo is not None else 0.0, float(hi) if hi is not None else 0.0)
+        k = config.get_constants()
+        a.pi, a.acc, a.gev2pb, a.sqh = k.PI, k.ACC, k.GEV2PB, k.SQH
+        for i, v in enumerate(self.par):
+            a.par[i] = v
+        a.alpha_mode = 1 if self.running else 0
+        a.alpha_s, a.mz2, a.b0 = self.alpha_s, self.mz2, self.b0
+        return a
+
+    def launch(self, divisions, seed, iteration, first_event, nevents, inv_total, partial, nblocks, train):
+        a = self._args()
+        a.d_grid = divisions.data_ptr()
+        a.seed, a.iteration, a.first_event, a.nevents = int(seed), int(iteration), int(first_event), int(nevents)
+        a.inv_total_events = float(inv_total)
+        a.d_partial = partial.data_ptr()
+        a.nblocks = int(nblocks)
+        a.accumulate_hist = int(bool(train))
+        self._lib.integrand(a)
+
+    # -- the same integrand from the separate API calls (reference structure, madflow_exec.py:422-470)
+    def python_integrand(self):
+        n = self.nexternal
+        psg = PhaseSpaceGenerator(n, self.sqrts, self.masses, com_output=not self.lab_frame)
+        for var, particle, lo, hi in self.cuts:
+            psg.register_cut(var, particle=particle, min_val=lo, max_val=hi)
+        if not self.running and not self.model.frozen:
+            self.model.freeze_alpha_s(self.alpha_s)
+
+        def cross_section(xrand, n_dim=None, weight=None):
+            all_ps, wts, x1, x2, idx = psg(xrand)
+            if self.running:
+                full_mt = torch.sum(psg.mt(all_ps[:, 2:n, :]), dim=-1)
+                alpha = alpha_s_one_loop((full_mt / 2.0) ** 2, self.alpha_s, self.mz2, self.b0)
+            else:
+                alpha = None
+            ret = self.matrix.smatrix(all_ps, *self.model.evaluate(alpha)) * wts
+            if self.cuts:
+                out = torch.zeros(xrand.shape[0], dtype=torch.float64, device=ret.device)
+                out[idx[:, 0].long()] = ret
+                return out
+            return ret
+
+        return cross_section

@@ -1,0 +1,357 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the golden vectors that the
+reference's own sources produced.  Needs a GPU."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from conftest import G, MT, WT, sm_params
+from oracle import EXACT, REFERENCE, SQH_REF, aloha, helas, philox
+from oracle import matrix as omatrix
+from oracle import phasespace as ops
+from oracle import vegas as ovegas
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+REL_ME = 1e-12  # north star: per-event |M|^2 within 1e-12 relative in FP64
+
+
+@pytest.fixture(scope="module")
+def mf():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    import madflow_b200  # noqa: F401
+    from madflow_b200 import _runtime as rt
+    from madflow_b200 import integrand, matrix, parameters, phasespace, vegas, wavefunctions_flow
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.rt, ns.matrix, ns.phasespace, ns.vegas, ns.wf = rt, matrix, phasespace, vegas, wavefunctions_flow
+    ns.integrand, ns.parameters = integrand, parameters
+    return ns
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------ HELAS
+def test_wavefunctions_vs_reference_golden(mf, golden):
+    g = golden("wavefunctions")
+    fns = {"i": mf.wf.ixxxxx, "o": mf.wf.oxxxxx, "v": mf.wf.vxxxxx}
+    for key in g.files:
+        if key.startswith("p_"):
+            continue
+        kind, m, h, s = key.split("_")
+        mass, nhel, ns = float(m[1:]), int(h[1:]), int(s[1:])
+        out = cpu(fns[kind](g[f"p_m{int(mass)}"], mass, nhel, ns))
+        assert out.shape == g[key].shape
+        np.testing.assert_allclose(out, g[key], rtol=1e-14, atol=1e-300, err_msg=key)
+
+
+def test_wavefunctions_large_random_vs_oracle(mf):
+    rng = np.random.default_rng(8)
+    pv = rng.normal(size=(20000, 3)) * 500
+    for mass in (0.0, MT):
+        p = np.concatenate([np.sqrt(np.sum(pv**2, axis=1, keepdims=True) + mass**2), pv], axis=1)
+        for nhel in (-1, 1):
+            for ns in (-1, 1):
+                np.testing.assert_allclose(cpu(mf.wf.ixxxxx(p, mass, nhel, ns)), helas.ixxxxx(p, mass, nhel, ns), rtol=1e-13, atol=1e-300)
+                np.testing.assert_allclose(cpu(mf.wf.oxxxxx(p, mass, nhel, ns)), helas.oxxxxx(p, mass, nhel, ns), rtol=1e-13, atol=1e-300)
+                np.testing.assert_allclose(cpu(mf.wf.vxxxxx(p, mass, nhel, ns)), helas.vxxxxx(p, mass, nhel, ns), rtol=1e-13, atol=1e-300)
+    s = cpu(mf.wf.sxxxxx(p, -1))
+    np.testing.assert_allclose(s, helas.sxxxxx(p, -1), rtol=1e-15)
+    assert cpu(mf.wf.vxxxxx(np.zeros((0, 4)), 0.0, 1, 1)).shape == (6, 0)
+
+
+# ------------------------------------------------------------------------------ ALOHA
+def _aloha(mf, rid, ins, coup, M=0.0, W=0.0, amp=False):
+    n = ins[0].shape[1]
+    dev = [mf.rt.to_device(a, torch.complex128) for a in ins] + [None] * (4 - len(ins))
+    out = torch.empty(n if amp else (6, n), dtype=torch.complex128, device="cuda")
+    lib = mf.rt.core()
+    rc = lib.mf_aloha(rid, *[mf.rt.ptr(d) for d in dev], ctypes.c_int64(n), ctypes.c_double(coup.real),
+                      ctypes.c_double(coup.imag), ctypes.c_double(M), ctypes.c_double(W), mf.rt.ptr(out), mf.rt.stream_ptr())
+    mf.rt.check(lib, rc)
+    return cpu(out)
+
+
+def test_aloha_vs_reference_golden_and_oracle(mf, golden):
+    g = golden("aloha_mockup")
+    F1, F2, V2, V3 = g["F1"], g["F2"], g["V2"], g["V3"]
+    c10, c11, M, W = complex(g["GC_10"]), complex(g["GC_11"]), float(g["M"]), float(g["W"])
+    np.testing.assert_allclose(_aloha(mf, 0, [F1, F2, V3], c11, amp=True), g["FFV1_0"], rtol=1e-13)
+    np.testing.assert_allclose(_aloha(mf, 1, [F2, V3], c11, M, W), g["FFV1_1"], rtol=1e-13)
+    np.testing.assert_allclose(_aloha(mf, 2, [F1, V3], c11, M, W), g["FFV1_2"], rtol=1e-13)
+    np.testing.assert_allclose(_aloha(mf, 3, [V2, V3], c10), g["VVV1P0_1"], rtol=1e-13)
+    rng = np.random.default_rng(3)
+    V4 = rng.normal(size=V2.shape) + 1j * rng.normal(size=V2.shape)
+    c12 = 1j * 1.2177**2
+    np.testing.assert_allclose(_aloha(mf, 4, [V2, V3, V4], c10, amp=True), aloha.VVV1_0(V2, V3, V4, c10), rtol=1e-13)
+    np.testing.assert_allclose(_aloha(mf, 5, [F1, F2], c11), aloha.FFV1P0_3(F1, F2, c11, 0.0, 0.0), rtol=1e-13)
+    for rid, k in ((6, 1), (7, 3), (8, 4)):
+        np.testing.assert_allclose(_aloha(mf, rid, [F1, V2, V3, V4], c12, amp=True),
+                                   aloha._vvvv_0(k, F1, V2, V3, V4, c12), rtol=1e-12)
+    for rid, k in ((9, 1), (10, 3), (11, 4)):
+        np.testing.assert_allclose(_aloha(mf, rid, [V2, V3, V4], c12), aloha._vvvv_1(k, V2, V3, V4, c12, 0.0, 0.0), rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------ matrix element
+def test_smatrix_gg_ttx_vs_reference_golden(mf, golden):
+    g = golden("matrix_gg_ttx")
+    m, model = mf.matrix.get_process("1_gg_ttx")
+    assert str(m) == "1_gg_ttx" and m.nexternal == 4 and m.ncomb == 16 and m.denominator == 256
+    np.testing.assert_array_equal(np.array(m.helicities), g["helicities"])
+    params = (g["params"][0], g["params"][1], np.array([g["GC_10"]]), np.array([g["GC_11"]]))
+    for key in ("13tev_com", "13tev_lab", "7tev_com", "7tev_lab"):
+        p = g[key + "_p"]
+        out = cpu(m.smatrix(p, *params))
+        np.testing.assert_allclose(out, g[key + "_smatrix"], rtol=REL_ME)
+        soa = np.ascontiguousarray(np.transpose(p, (1, 2, 0)))
+        np.testing.assert_array_equal(cpu(m.smatrix(soa, *params, layout="soa")), out)
+        np.testing.assert_array_equal(m.smatrix_host(p, *params), out)
+        scale = np.abs(g[key + "_smatrix"]) * 256
+        for ic in range(16):
+            one = cpu(m.matrix(p, ic, *params))
+            assert np.max(np.abs(one - g[key + "_matrix"][ic].real) / scale) < REL_ME
+    gs = g["run_gs"]
+    out = cpu(m.smatrix(g["13tev_lab_p"], g["params"][0], g["params"][1], -gs, 1j * gs))
+    np.testing.assert_allclose(out, g["run_smatrix"], rtol=REL_ME)
+    assert cpu(m.smatrix(np.zeros((0, 4, 4)), *params)).shape == (0,)
+    with pytest.raises(TypeError):
+        m.smatrix(g["13tev_com_p"], 173.0)
+    with pytest.raises(ValueError):
+        m.smatrix(np.zeros((3, 5, 4)), *params)
+
+
+def test_smatrix_gg_ttx_1e5_points_and_model(mf):
+    """>= 1e5 RAMBO points against the oracle, couplings from Model.evaluate (frozen and running)."""
+    from madflow_b200 import process_ir
+
+    ir = process_ir.gg_ttx_pinned()
+    m, model = mf.matrix.get_process("1_gg_ttx")
+    x = np.random.default_rng(42).random((100_000, 10))
+    p, w, x1, x2 = ops.ramboflow(x, 4, 13e3, [MT, MT], xfactor="converged")
+    lab = ops.boost_to_lab(p, x1, x2)
+    a_s = 0.09 + 0.05 * np.random.default_rng(1).random(x.shape[0])
+    ref = omatrix.smatrix(ir, lab, sm_params(alpha_s=a_s))
+    out = cpu(m.smatrix(lab, *model.evaluate(a_s)))
+    np.testing.assert_allclose(out, ref, rtol=REL_ME)
+    model.freeze_alpha_s(0.118)
+    a32 = float(np.float32(0.118))
+    ref = omatrix.smatrix(ir, p, sm_params(alpha_s=a32))
+    out = cpu(m.smatrix(p, *model.evaluate(None)))
+    np.testing.assert_allclose(out, ref, rtol=REL_ME)
+    # closed form (Gamma_t = 0): the only deviation is the reference's float32 SQH
+    from test_oracle import closed_form_gg_ttx
+
+    g = 2 * math.sqrt(math.pi * a32)
+    out0 = cpu(m.smatrix(p, MT, 0.0, np.array([-g + 0j]), np.array([1j * g])))
+    np.testing.assert_allclose(out0 / closed_form_gg_ttx(p, g=g), (SQH_REF / math.sqrt(0.5)) ** 4, rtol=2e-11)
+
+
+# ------------------------------------------------------------------------------ phase space
+def test_rambo_and_ramboflow_vs_reference_golden(mf, golden):
+    g = golden("phasespace")
+    for n in range(2, 8):
+        p, w = mf.phasespace.rambo(g[f"rambo{n}_x"], n, 7e3)
+        assert tuple(p.shape) == (16, n, 4)
+        np.testing.assert_allclose(cpu(p), g[f"rambo{n}_p"], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(cpu(w), g[f"rambo{n}_w"], rtol=1e-12)
+        np.testing.assert_allclose(cpu(w), ops.massless_volume(n, 7e3), rtol=1e-6)  # reference tests/test_ps.py:9-39
+    p, w = mf.phasespace.rambo(g["rambo7v_x"], 7, g["rambo7v_s"])
+    np.testing.assert_allclose(cpu(w), g["rambo7v_w"], rtol=1e-12)
+    cases = {"tt": (4, 13e3, [MT, MT]), "m50_125": (4, 7e3, [50.0, 125.0]), "massless5": (5, 7e3, None),
+             "tt7": (4, 7e3, [MT, MT])}
+    for name, (n, s, ms) in cases.items():
+        p, w, x1, x2 = mf.phasespace.ramboflow(g[f"rf_{name}_x"], n, s, ms)
+        # n=2 massive: the start value is already the root up to rounding, so batch and per-event agree
+        np.testing.assert_allclose(cpu(p), g[f"rf_{name}_p"], rtol=1e-9, atol=1e-7)
+        np.testing.assert_allclose(cpu(w), g[f"rf_{name}_w"], rtol=1e-9)
+        np.testing.assert_allclose(cpu(x1), g[f"rf_{name}_x1"], rtol=1e-14)
+        np.testing.assert_allclose(cpu(mf.phasespace._boost_to_lab(p, x1, x2)), g[f"rf_{name}_lab"], rtol=1e-9, atol=1e-7)
+    for name, (n, ms) in {"ttg": (5, [MT, MT, 0.0]), "ttgg": (6, [MT, MT, 0.0, 0.0]), "ttggg": (7, [MT, MT, 0.0, 0.0, 0.0])}.items():
+        # per-event Newton == the reference evaluated on one-event batches
+        p, w, x1, x2 = mf.phasespace.ramboflow(g[f"rf_{name}_x"][:16], n, 13e3, ms)
+        np.testing.assert_allclose(cpu(p), g[f"rf_{name}_p_single"], rtol=1e-12, atol=1e-8)
+        np.testing.assert_allclose(cpu(w), g[f"rf_{name}_w_single"], rtol=1e-12)
+    p, w, x1, x2 = mf.phasespace.ramboflow(g["rf_21_x"], 3, 13e3, [91.188])
+    np.testing.assert_allclose(cpu(p), g["rf_21_p"], rtol=1e-13)
+    np.testing.assert_allclose(cpu(w), g["rf_21_w"], rtol=1e-12)
+
+
+def test_phasespace_generator_cuts(mf, golden):
+    """reference tests/test_ps.py:42-78 on the CUDA path + the golden cut selections."""
+    g = golden("phasespace")
+    gen = mf.phasespace.PhaseSpaceGenerator(5, 7e3, algorithm="ramboflow")
+    gen.register_cut("pt", particle=3, min_val=60, max_val=300.0)
+    a, w, x1, x2, idx = gen(g["psg5_x"])
+    np.testing.assert_array_equal(cpu(idx), g["psg5_idx"])
+    np.testing.assert_allclose(cpu(a), g["psg5_p"], rtol=1e-12, atol=1e-8)
+    np.testing.assert_allclose(cpu(w), g["psg5_w"], rtol=1e-12)
+    gen.clear_cuts()
+    full, fw, _, _, one = gen(g["psg5_x"])
+    assert int(one) == 1 and full.shape[0] == 200
+    pt = cpu(gen.pt(full[:, 3, :]))
+    mask = (pt > 60.0) & (pt < 300.0)
+    np.testing.assert_array_equal(cpu(a), cpu(full)[mask])
+    gen = mf.phasespace.PhaseSpaceGenerator(5, 13e3, [MT, MT, 0.0], com_output=False)
+    for i in range(2, 5):
+        gen.register_cut("pt", particle=i, min_val=30.0)
+    a, w, x1, x2, idx = gen(g["psglab_x"])
+    np.testing.assert_array_equal(cpu(idx)[:, 0], np.flatnonzero(g["psglab_pass"]))
+    np.testing.assert_allclose(cpu(a), g["psglab_p"], rtol=1e-12, atol=1e-8)
+    np.testing.assert_allclose(cpu(w), g["psglab_w"], rtol=1e-12)
+    np.testing.assert_allclose(cpu(gen.mt(a[:, 2:5, :])), g["psglab_mt"], rtol=1e-11)
+    gen = mf.phasespace.PhaseSpaceGenerator(4, 7e3, masses=[50.0, 125.0])
+    a, *_ = gen(np.random.default_rng(3).random((100, 10)))
+    m2 = cpu(mf.phasespace._invariant_mass(a))
+    np.testing.assert_allclose(m2[:, 0], 0.0, atol=1e-9)
+    np.testing.assert_allclose(m2[:, 2], 50.0**2, atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose(m2[:, 3], 125.0**2, atol=1e-4, rtol=1e-4)
+    with pytest.raises(ValueError):
+        mf.phasespace.PhaseSpaceGenerator(5, 7e3, masses=[1.0])
+    with pytest.raises(ValueError):
+        gen.register_cut("rapidity", particle=2, min_val=0)
+    with pytest.raises(ValueError):
+        gen.register_cut("pt", particle=9, min_val=0)
+
+
+def test_ramboflow_full_size_properties(mf):
+    """BASELINE config sizes: momentum conservation and mass shells on 1e6 tt~gg points."""
+    n = 1_000_000
+    x = torch.rand((n, 18), dtype=torch.float64, device="cuda")
+    p, w, x1, x2 = mf.phasespace.ramboflow(x, 6, 13e3, [MT, MT, 0.0, 0.0])
+    tot = p[:, 2:].sum(dim=1) - p[:, 0] - p[:, 1]
+    roots = p[:, 0, 0] * 2
+    assert float((tot.abs().max(dim=1).values / roots).max()) < 1e-9
+    m2 = mf.phasespace._invariant_mass(p)
+    assert float((m2[:, 2] - MT**2).abs().max()) < 1e-3 and float(m2[:, 4].abs().max() / (13e3**2)) < 1e-12
+    assert bool(torch.isfinite(w).all()) and float(w.min()) > 0
+
+
+# ------------------------------------------------------------------------------ VEGAS pieces
+def test_philox_and_sampling_vs_oracle(mf):
+    lib = mf.rt.core()
+    out = torch.empty((1000, 7), dtype=torch.float64, device="cuda")
+    mf.rt.check(lib, lib.mf_philox_uniform(ctypes.c_uint64(4), ctypes.c_uint32(3), ctypes.c_uint64(2**33 + 5),
+                                           ctypes.c_int64(1000), 7, mf.rt.ptr(out), mf.rt.stream_ptr()))
+    np.testing.assert_array_equal(cpu(out), philox.uniforms(4, 3, 2**33 + 5, 1000, 7))
+    ndim, n = 5, 4096
+    grid = ovegas.refine_grid(np.random.default_rng(1).random((ndim, 50)) + 0.1, ovegas.uniform_grid(ndim))
+    dg = mf.rt.to_device(grid)
+    x = torch.empty((n, ndim), dtype=torch.float64, device="cuda")
+    xjac = torch.empty(n, dtype=torch.float64, device="cuda")
+    bins = torch.empty((ndim, n), dtype=torch.uint8, device="cuda")
+    mf.rt.check(lib, lib.mf_vegas_sample(mf.rt.ptr(dg), ndim, ctypes.c_uint64(9), ctypes.c_uint32(2), ctypes.c_uint64(77),
+                                         ctypes.c_int64(n), ctypes.c_double(1.0 / 12345), mf.rt.ptr(x), mf.rt.ptr(xjac),
+                                         mf.rt.ptr(bins), mf.rt.stream_ptr()))
+    xr, kr, wr = ovegas.map_to_grid(ovegas.confine(philox.uniforms(9, 2, 77, n, ndim)), grid)
+    np.testing.assert_array_equal(cpu(bins).T, kr)
+    np.testing.assert_allclose(cpu(x), xr, rtol=1e-14)
+    np.testing.assert_allclose(cpu(xjac), wr / 12345, rtol=1e-13)
+    # accumulate + reduce + refine
+    f = np.random.default_rng(3).random(n) * (np.random.default_rng(4).random(n) > 0.3)
+    nb = int(lib.mf_vegas_blocks())
+    partial = torch.empty(nb * (4 + ndim * 50), dtype=torch.float64, device="cuda")
+    sums = torch.zeros(4 + ndim * 50, dtype=torch.float64, device="cuda")
+    df = mf.rt.to_device(f)
+    mf.rt.check(lib, lib.mf_vegas_accumulate(mf.rt.ptr(df), mf.rt.ptr(xjac), mf.rt.ptr(bins), ctypes.c_int64(n), ndim, 1,
+                                             mf.rt.ptr(partial), nb, mf.rt.stream_ptr()))
+    mf.rt.check(lib, lib.mf_vegas_reduce(mf.rt.ptr(partial), nb, ndim, 0, mf.rt.ptr(sums), mf.rt.stream_ptr()))
+    a, b, c = ovegas.accumulate(f, wr / 12345, kr)
+    s = cpu(sums)
+    np.testing.assert_allclose(s[0], a, rtol=1e-12)
+    np.testing.assert_allclose(s[1], b, rtol=1e-12)
+    assert s[2] == np.count_nonzero(f) and s[3] == 0
+    np.testing.assert_allclose(s[4:].reshape(ndim, 50), c, rtol=1e-11, atol=1e-300)
+    mf.rt.check(lib, lib.mf_vegas_refine(mf.rt.ptr(dg), mf.rt.ptr(sums), ndim, mf.rt.stream_ptr()))
+    np.testing.assert_allclose(cpu(dg), ovegas.refine_grid(c, grid), rtol=1e-10, atol=1e-14)
+
+
+def test_vegasflow_generic_integrand_known_integral(mf):
+    ndim, sig = 4, 0.05
+    exact = (sig * math.sqrt(2 * math.pi) * math.erf(0.5 / (sig * math.sqrt(2)))) ** ndim
+
+    def f(x, n_dim=None, weight=None):
+        return torch.exp(-torch.sum((x - 0.5) ** 2, dim=1) / (2 * sig**2))
+
+    v = mf.vegas.VegasFlow(ndim, 200_000, seed=4)
+    v.compile(f)
+    res, err = v.run_integration(6)
+    assert abs(res - exact) < 4 * err and err / res < 2e-3
+    # same stream as the oracle driver => same numbers, iteration by iteration
+    ov = ovegas.Vegas(ndim, 20000, seed=11)
+    ov.compile(lambda x, **_: np.exp(-np.sum((x - 0.5) ** 2, axis=1) / (2 * sig**2)))
+    gv = mf.vegas.VegasFlow(ndim, 20000, seed=11)
+    gv.compile(f)
+    for _ in range(3):
+        r0, s0 = ov.run_iteration()
+        r1, s1 = gv.run_iteration()
+        assert abs(r1 / r0 - 1) < 1e-9 and abs(s1 / s0 - 1) < 1e-7
+    np.testing.assert_allclose(cpu(gv.divisions), ov.grid, rtol=1e-7, atol=1e-12)
+    res2 = mf.vegas.vegas_wrapper(f, ndim, 3, 50_000)
+    assert abs(res2[0] - exact) < 5 * res2[1]
+
+
+# ------------------------------------------------------------------------------ fused integrand
+@pytest.mark.parametrize("pt_cut,running,lab", [(None, False, False), (30.0, False, True), (30.0, True, True)])
+def test_fused_integrand_equals_separate_calls_and_oracle(mf, pt_cut, running, lab):
+    """One iteration of the fused kernel vs (a) the same integrand assembled from the separate C-ABI
+    calls and (b) the CPU oracle's cross_section, all on the same Philox points."""
+    from madflow_b200 import process_ir
+
+    n_events = 40_000
+    m, model = mf.matrix.get_process("1_gg_ttx")
+    fi = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT], pt_cut=pt_cut, lab_frame=lab,
+                                     running=running)
+    v1 = mf.vegas.VegasFlow(10, n_events, seed=4)
+    v1.compile(fi)
+    r1 = v1.run_iteration()
+    v2 = mf.vegas.VegasFlow(10, n_events, seed=4)
+    v2.compile(fi.python_integrand())
+    r2 = v2.run_iteration()
+    assert abs(r1[0] / r2[0] - 1) < 1e-11 and abs(r1[1] / r2[1] - 1) < 1e-9
+    np.testing.assert_allclose(cpu(v1.divisions), cpu(v2.divisions), rtol=1e-8, atol=1e-13)
+    ir = process_ir.gg_ttx_pinned()
+    if running:
+        def a_fn(q2):
+            return 0.118 / (1 + 0.118 * fi.b0 * np.log(q2 / fi.mz2))
+        pf = lambda a: sm_params(alpha_s=a)
+    else:
+        a_fn = None
+        pf = lambda a: sm_params(alpha_s=float(np.float32(0.118)))
+    xs = ovegas.make_cross_section(ir, pf, 13e3, [MT, MT], pt_cut=pt_cut, lab_frame=lab, alpha_s_fn=a_fn)
+    ov = ovegas.Vegas(10, n_events, seed=4)
+    ov.compile(xs)
+    r0 = ov.run_iteration()
+    assert abs(r1[0] / r0[0] - 1) < 1e-10 and abs(r1[1] / r0[1] - 1) < 1e-8
+    np.testing.assert_allclose(cpu(v1.divisions), ov.grid, rtol=1e-7, atol=1e-12)
+
+
+def test_cross_section_gg_ttx_integration(mf):
+    """Integrated sigma: fused path vs separate-call path within 1 sigma of the combined MC error,
+    and chunked launches give the same answer as a single launch."""
+    m, model = mf.matrix.get_process("1_gg_ttx")
+    fi = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT], pt_cut=30.0, lab_frame=True)
+    va = mf.vegas.VegasFlow(10, 200_000, seed=4)
+    va.compile(fi)
+    ra = va.run_integration(5, log_time=False)
+    vb = mf.vegas.VegasFlow(10, 200_000, seed=1234)
+    vb.compile(fi.python_integrand())
+    rb = vb.run_integration(5, log_time=False)
+    assert abs(ra[0] - rb[0]) < math.hypot(ra[1], rb[1]) * 3
+    assert ra[1] / ra[0] < 5e-3
+    vc = mf.vegas.VegasFlow(10, 200_000, seed=4, events_limit=33_333)
+    vc.compile(fi)
+    rc = vc.run_integration(5, log_time=False)
+    assert abs(rc[0] / ra[0] - 1) < 1e-9
+    from madflow_b200.utilities import one_matrix_integration
+
+    m2, model2 = mf.matrix.get_process("1_gg_ttx")
+    r = one_matrix_integration(m2, model2, out_masses=[MT, MT], n_events=50_000, n_iter=3)
+    assert r[0] > 0 and r[1] / r[0] < 0.02

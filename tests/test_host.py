@@ -1,0 +1,128 @@
+"""Host logic and the C-ABI surface, CPU only (no kernel is launched)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from madflow_b200 import codegen, process_ir
+from madflow_b200.vegas import combine_iterations, iteration_sigma, shard_events
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mfp?_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_core_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(os.path.join(ROOT, "madflow_b200", "lib", "libmadflow_b200.so"))
+    names = _declared("madflow_b200.h")
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.mf_version.restype = ctypes.c_int
+    assert lib.mf_version() == 1
+
+
+def test_process_library_exports_every_declared_symbol():
+    from madflow_b200 import _runtime as rt
+
+    names = _declared("madflow_b200_process.h")
+    assert len(names) >= 10
+    lib = rt.process_lib("1_gg_ttx")
+    for n in names:
+        assert hasattr(lib.lib, n), n
+    # metadata calls are host-only
+    assert lib.name == "1_gg_ttx"
+    assert (lib.info.nexternal, lib.info.ncomb, lib.info.ncolor, lib.info.ndiags, lib.info.ndim) == (4, 16, 2, 3, 10)
+    assert lib.info.denominator == 256.0
+    assert lib.info.flops_per_event == 23697.0
+    assert lib.param_names == ["mdl_MT", "mdl_WT"] and lib.coupling_names == ["GC_10", "GC_11"]
+    assert lib.coupling_defs == [(-1.0, 0.0, 1), (0.0, 1.0, 1)]
+    assert lib.helicities == process_ir.gg_ttx_pinned()["helicities"]
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from madflow_b200 import _runtime as rt
+    from madflow_b200.matrix import Matrix
+
+    m = Matrix("1_gg_ttx")
+    with pytest.raises(RuntimeError):
+        m.smatrix(np.zeros((2, 4, 4)), 173.0, 1.5, np.array([-1.2 + 0j]), np.array([1.2j]))
+    with pytest.raises(rt.MadflowB200Error):
+        rt.process_lib("no_such_process")
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "madflow_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_flop_count_matches_survey():
+    assert codegen.flops_per_event(process_ir.gg_ttx_pinned()) == 23697
+
+
+def test_shard_events_partitions_the_range():
+    for n in (1, 7, 1000, 10**8 + 3):
+        for world in (1, 2, 3, 8):
+            parts = [shard_events(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+            for (f0, c0), (f1, _) in zip(parts, parts[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_iteration_statistics():
+    rng = np.random.default_rng(0)
+    f = rng.random(10000)
+    n = f.size
+    t = f / n
+    res, res2 = t.sum(), (t * t).sum()
+    assert abs(iteration_sigma(res, res2, n) - f.std(ddof=1) / np.sqrt(n)) < 1e-12
+    final, err, chi2 = combine_iterations([(1.0, 0.1), (1.2, 0.2)])
+    assert abs(final - (1.0 / 0.01 + 1.2 / 0.04) / (1 / 0.01 + 1 / 0.04)) < 1e-14
+    assert abs(err - (1 / (1 / 0.01 + 1 / 0.04)) ** 0.5) < 1e-14
+
+
+_GLOO = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from madflow_b200.vegas import allreduce_sums, shard_events
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 1001
+first, count = shard_events(n, rank, world)
+f = torch.arange(n, dtype=torch.float64)[first:first + count]
+sums = torch.zeros(4 + 3 * 50, dtype=torch.float64)
+sums[0], sums[1] = f.sum(), (f * f).sum()
+sums[4 + rank] = 1.0
+allreduce_sums(sums)
+full = torch.arange(n, dtype=torch.float64)
+assert sums[0] == full.sum() and sums[1] == (full * full).sum(), sums[:2]
+assert sums[4:4 + world].tolist() == [1.0] * world
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gloo_allreduce(tmp_path):
+    script = tmp_path / "gloo_check.py"
+    script.write_text(_GLOO)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29671", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2

@@ -1,0 +1,89 @@
+"""The CUDA device code executed on the CPU (tests/hostcheck) against the oracle and the golden
+vectors: the functions are __host__ __device__, so this checks the very source the GPU kernels are
+compiled from, in the container that has no GPU.  Needs nvcc; CPU only."""
+import ctypes
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import MT, WT, sm_params
+from madflow_b200 import process_ir
+from oracle import ACC_REF, GEV2PB_REF, PI_REF, SQH_REF, aloha, philox
+from oracle import matrix as omatrix
+from oracle import phasespace as ops
+from oracle import vegas as ovegas
+
+pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    import hostcheck
+
+    return hostcheck
+
+
+def test_device_helas_on_host(hc, golden):
+    lib, g = hc.core(), golden("wavefunctions")
+    for key in g.files:
+        if key.startswith("p_"):
+            continue
+        kind, m, h, s = key.split("_")
+        mass, nhel, ns = float(m[1:]), int(h[1:]), int(s[1:])
+        p = np.ascontiguousarray(g[f"p_m{int(mass)}"])
+        out = np.empty((6, p.shape[0]), dtype=np.complex128)
+        lib.hc_wavefunction({"i": 0, "o": 1, "v": 2}[kind], hc._dp(p), ctypes.c_longlong(p.shape[0]),
+                            ctypes.c_double(mass), nhel, ns, ctypes.c_double(SQH_REF), hc._dp(out.view(np.float64)))
+        np.testing.assert_allclose(out, g[key], rtol=1e-14, atol=1e-300, err_msg=key)
+
+
+def test_device_process_on_host(hc, golden):
+    g = golden("matrix_gg_ttx")
+    ir = process_ir.gg_ttx_pinned()
+    lib = hc.process(ir)
+    coup = np.array([g["GC_10"], g["GC_11"]])
+    for key in ("13tev_com", "13tev_lab", "7tev_com", "7tev_lab"):
+        out = hc.smatrix(lib, ir, g[key + "_p"], g["params"], coup, SQH_REF)
+        np.testing.assert_allclose(out, g[key + "_smatrix"], rtol=1e-13)
+    gs = g["run_gs"]
+    out = hc.smatrix(lib, ir, g["13tev_lab_p"], g["params"], np.stack([-gs, 1j * gs]), SQH_REF)
+    np.testing.assert_allclose(out, g["run_smatrix"], rtol=1e-13)
+
+
+def test_device_ramboflow_on_host(hc, golden):
+    lib, g = hc.core(), golden("phasespace")
+    cases = {"tt": (4, 13e3, [MT, MT]), "ttg": (5, 13e3, [MT, MT, 0.0]), "ttgg": (6, 13e3, [MT, MT, 0.0, 0.0]),
+             "ttggg": (7, 13e3, [MT, MT, 0.0, 0.0, 0.0]), "m50_125": (4, 7e3, [50.0, 125.0])}
+    for name, (nx, s, ms) in cases.items():
+        x = np.ascontiguousarray(g[f"rf_{name}_x"])
+        ne = x.shape[0]
+        p, w, x1, x2 = np.empty((ne, nx, 4)), np.empty(ne), np.empty(ne), np.empty(ne)
+        ma = np.array(ms + [0.0] * (8 - len(ms)))
+        lib.hc_ramboflow(nx, hc._dp(x), ctypes.c_longlong(ne), ctypes.c_double(s), hc._dp(ma), ctypes.c_double(PI_REF),
+                         ctypes.c_double(ACC_REF), ctypes.c_double(GEV2PB_REF), 0, hc._dp(p), hc._dp(w), hc._dp(x1),
+                         hc._dp(x2))
+        pr, wr, _, _ = ops.ramboflow(x, nx, s, ms, xfactor="converged")
+        np.testing.assert_allclose(p, pr, rtol=1e-12, atol=1e-8)
+        np.testing.assert_allclose(w, wr, rtol=1e-12)
+
+
+def test_device_philox_on_host(hc):
+    lib = hc.core()
+    u = np.empty((100, 7))
+    lib.hc_philox(ctypes.c_ulonglong(4), 3, ctypes.c_ulonglong(2**33 + 5), ctypes.c_longlong(100), 7, hc._dp(u))
+    np.testing.assert_array_equal(u, philox.uniforms(4, 3, 2**33 + 5, 100, 7))
+
+
+def test_device_vegas_map_on_host(hc):
+    lib = hc.core()
+    grid = ovegas.refine_grid(np.random.default_rng(1).random((5, 50)) + 0.1, ovegas.uniform_grid(5))
+    r = ovegas.confine(np.random.default_rng(2).random((300, 5)))
+    x, w = np.empty((300, 5)), np.empty(300)
+    bins = np.empty((300, 5), dtype=np.int32)
+    lib.hc_vegas_map(hc._dp(np.ascontiguousarray(grid)), hc._dp(r), ctypes.c_longlong(300), 5, hc._dp(x),
+                     bins.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), hc._dp(w))
+    xr, kr, wr = ovegas.map_to_grid(r, grid)
+    np.testing.assert_array_equal(bins, kr)
+    np.testing.assert_allclose(x, xr, rtol=1e-15)
+    np.testing.assert_allclose(w, wr, rtol=1e-14)
