@@ -1,0 +1,114 @@
+"""The built-in process generator (madflow_b200/procgen.py), CPU only.
+
+MG5_aMC is not available offline, so nothing here can be compared with MG5 output directly except
+g g > t t~ (frozen in the reference's tests/mockup_debug_me.py).  The other processes are pinned by
+MG5's known counts and by physics: gauge invariance, Bose symmetry, two independent organisations of
+the same amplitude, colour-matrix identities."""
+import itertools
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import G, MT, WT, sm_params
+from madflow_b200 import codegen, process_ir, procgen
+from oracle import EXACT, SQH_REF
+from oracle import matrix as omatrix
+from oracle import phasespace as ops
+
+
+@pytest.fixture(scope="module")
+def irs():
+    return {k: procgen.generate_ir(k) for k in (0, 1, 2)}
+
+
+def test_gg_ttx_reproduces_the_references_generated_code(irs):
+    pin, gen = process_ir.gg_ttx_pinned(), irs[0]
+    assert gen["calls"] == pin["calls"]
+    assert [list(map(tuple, t)) for t in gen["jamp"]] == [list(t) for t in pin["jamp"]]
+    assert gen["helicities"] == pin["helicities"]
+    assert (gen["color_num"], gen["color_denom"], gen["denominator"]) == ([[16, -2], [-2, 16]], [3, 3], 256)
+
+
+def test_counts_match_mg5():
+    """ndiag 3/16/123/1240, amplitudes 3/18/159, ncolor 2/6/24/120,
+    denominators 256/256/512/1536."""
+    expect = {0: (3, 3, 2, 256), 1: (16, 18, 6, 256), 2: (123, 159, 24, 512), 3: (1240, None, 120, 1536)}
+    for k, (ndiag, namp, ncolor, den) in expect.items():
+        ir = procgen.generate_ir(k)
+        assert process_ir.validate(ir)
+        assert ir["ndiags"] == ndiag and len(ir["jamp"]) == ncolor and ir["denominator"] == den
+        if namp:
+            assert len({c["amp"] for c in ir["calls"] if "amp" in c}) == namp
+        assert ir["ncomb"] == 2 ** (4 + k)
+    # g g > t t~ g colour matrix, first row as MG5 prints it
+    assert procgen.generate_ir(1)["color_num"][0] == [64, -8, -8, 1, 1, 10] and procgen.generate_ir(1)["color_denom"][0] == 9
+
+
+def test_colour_matrix_identities(irs):
+    for k, ir in irs.items():
+        c = np.array(ir["color_num"], dtype=float) / np.array(ir["color_denom"], dtype=float)[:, None]
+        assert np.allclose(c, c.T)
+        assert np.min(np.linalg.eigvalsh(c)) > -1e-10           # a Gram matrix
+        ng = 2 + k
+        cf = 4.0 / 3.0
+        assert np.allclose(np.diag(c), 3 * cf**ng)              # Tr(T^a1..T^an T^an..T^a1) = N CF^n
+        assert len({round(v, 9) for v in c.sum(axis=1)}) == 1   # rows are permutations of each other
+
+
+def _points(k, n=24, seed=0):
+    nn = 4 + k
+    x = np.random.default_rng(seed).random((n, 4 * (nn - 2) + 2))
+    p, _, x1, x2 = ops.ramboflow(x, nn, 13e3, [MT, MT] + [0.0] * k, const=EXACT, xfactor="converged")
+    return p
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_gauge_invariance_and_two_organisations(irs, k):
+    ir = irs[k]
+    alt = procgen.generate_ir(k, root="tbar")  # every diagram closed on the t~ leg instead of the centroid
+    p = _points(k)
+    params = dict(sm_params(), mdl_WT=0.0)
+    a = omatrix.smatrix(ir, p, params, EXACT)
+    b = omatrix.smatrix(alt, p, params, EXACT)
+    np.testing.assert_allclose(a, b, rtol=5e-12)
+    hel = [1, -1, 1, -1] + [1, -1, 1][:k]
+    phys = np.max(np.abs(omatrix.matrix(ir, p, hel, params, EXACT, return_jamp=True)))
+    for gl in [0, 1] + list(range(4, 4 + k)):
+        h = list(hel)
+        h[gl] = 4  # BRST polarisation (wavefunctions_flow.py:146-152)
+        assert np.max(np.abs(omatrix.matrix(ir, p, h, params, EXACT, return_jamp=True))) < 1e-10 * phys
+
+
+def test_bose_symmetry(irs):
+    params = sm_params()
+    for k in (1, 2):
+        p = _points(k, seed=3)
+        a = omatrix.smatrix(irs[k], p, params)
+        q = p.copy()
+        q[:, [0, 1]] = q[:, [1, 0]]
+        np.testing.assert_allclose(omatrix.smatrix(irs[k], q, params), a, rtol=1e-11)
+    q = p.copy()
+    q[:, [4, 5]] = q[:, [5, 4]]
+    np.testing.assert_allclose(omatrix.smatrix(irs[2], q, params), a, rtol=1e-11)
+
+
+def test_flops_per_event(irs):
+    assert codegen.flops_per_event(irs[0]) == 23697
+    assert 1.5e5 < codegen.flops_per_event(irs[1]) < 2.5e5
+    assert 2e6 < codegen.flops_per_event(irs[2]) < 4e6
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+def test_generated_cuda_source_on_host_ttxg(irs):
+    """The emitted straight-line code for g g > t t~ g, executed on the CPU, against the oracle."""
+    import hostcheck as hc
+
+    ir = irs[1]
+    lib = hc.process(ir)
+    p = _points(1, n=100, seed=7)
+    a_s = 0.09 + 0.05 * np.random.default_rng(9).random(100)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    out = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF)
+    np.testing.assert_allclose(out, omatrix.smatrix(ir, p, params), rtol=1e-12)
