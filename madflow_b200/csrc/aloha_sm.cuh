@@ -24,8 +24,10 @@ MF_DEV Mom mom_of(const cxd w[6], double s) { return Mom{s * w[0].re, s * w[1].r
 
 // COUP / (P^2 - M(M - iW))  (mockup_debug_me.py:87)
 MF_DEV cxd propagator(cxd coup, const Mom& P, double M, double W) {
-  const double p2 = P.e * P.e - P.x * P.x - P.y * P.y - P.z * P.z;
-  return cdiv(coup, mk(p2 - M * M, M * W));
+  // rounded like the reference's P0**2 - P1**2 - P2**2 - P3**2 - M*(M - iW): no FMA contraction,
+  // the cancellation in P^2 amplifies any differently rounded product by E^2/P^2
+  const double p2 = ((mul_rn(P.e, P.e) - mul_rn(P.x, P.x)) - mul_rn(P.y, P.y)) - mul_rn(P.z, P.z);
+  return cdiv(coup, mk(p2 - mul_rn(M, M), M * W));
 }
 
 // X = F2bar * Vslash : X[0..3] <-> spinor slots 2..5

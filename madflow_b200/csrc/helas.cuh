@@ -37,7 +37,7 @@ MF_DEV void pp_zero_spinor(double fmass, int nsf, int ip, int im, double v[4]) {
 // ysign = +1 (ixxxxx) or -1 (oxxxxx).  Returns sfomeg[2], chi[2] (chi[0] real).
 MF_DEV void massive_blocks(const double p[4], double fmass, int nsf, int nh, double ysign, double& pp,
                            double sfomeg[2], cxd chi[2]) {
-  pp = fmin(p[0], sqrt(p[1] * p[1] + p[2] * p[2] + p[3] * p[3]));
+  pp = fmin(p[0], sqrt(mul_rn(p[1], p[1]) + mul_rn(p[2], p[2]) + mul_rn(p[3], p[3])));
   const double sf0 = (1 + nsf + (1 - nsf) * nh) * 0.5;
   const double sf1 = (1 + nsf - (1 - nsf) * nh) * 0.5;
   const double sq = sqrt(p[0] + pp);
@@ -126,12 +126,12 @@ MF_DEV void vxxxxx(const double p[4], double vmass, int nhel, int nsv, double sq
     for (int k = 0; k < 4; ++k) w[2 + k] = mk(p[k] / d, 0.0);
     return;
   }
-  const double pt2 = p[1] * p[1] + p[2] * p[2];
+  const double pt2 = mul_rn(p[1], p[1]) + mul_rn(p[2], p[2]);
   const int ahel = abs(nhel);
   const double hel0 = 1.0 - ahel;
   const double nsvahl = nsv * ahel;
   if (vmass != 0.0) {  // :548-678
-    const double pp = fmin(p[0], sqrt(pt2 + p[3] * p[3]));
+    const double pp = fmin(p[0], sqrt(pt2 + mul_rn(p[3], p[3])));
     const double pt = fmin(pp, sqrt(pt2));
     if (pp == 0.0) {
       w[2] = mk(1.0, 0.0);  // sic: the reference leaves v[0] = 1 in the rest frame (:588)
@@ -142,11 +142,11 @@ MF_DEV void vxxxxx(const double p[4], double vmass, int nhel, int nsv, double sq
     }
     const double emp = p[0] / (vmass * pp);
     w[2] = mk(hel0 * pp / vmass, 0.0);
-    w[5] = mk(hel0 * p[3] * emp + nhel * pt / pp * sqh, 0.0);
+    w[5] = mk(mul_rn(hel0 * p[3], emp) + mul_rn(nhel * pt / pp, sqh), 0.0);
     if (pt != 0.0) {
       const double pzpt = p[3] / (pp * pt) * sqh * nhel;
-      w[3] = mk(hel0 * p[1] * emp - p[1] * pzpt, -nsvahl * p[2] / pt * sqh);
-      w[4] = mk(hel0 * p[2] * emp - p[2] * pzpt, nsvahl * p[1] / pt * sqh);
+      w[3] = mk(mul_rn(hel0 * p[1], emp) - mul_rn(p[1], pzpt), -nsvahl * p[2] / pt * sqh);
+      w[4] = mk(mul_rn(hel0 * p[2], emp) - mul_rn(p[2], pzpt), nsvahl * p[1] / pt * sqh);
     } else {
       w[3] = mk(-nhel * sqh, 0.0);
       w[4] = mk(0.0, nsvahl * sign_tf(sqh, p[3]));

@@ -10,6 +10,22 @@
 #define MF_DEV __host__ __device__ __forceinline__
 #define MF_HD __host__ __device__ __forceinline__
 
+// Product that is never contracted into an FMA.  Used where the reference's expression is
+// ill-conditioned (external wavefunctions of forward/backward particles, P^2 of nearly on-shell
+// propagators): there a differently rounded intermediate is amplified by E/(E+pz) or E^2/P^2, so
+// these few operations are rounded exactly like the reference's separate multiply and add.
+MF_HD double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  double r = a * b;
+#ifdef __FMA__
+  asm volatile("" : "+x"(r));
+#endif
+  return r;
+#endif
+}
+
 struct cxd {
   double re, im;
 };
