@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--process", default=None)
     ap.add_argument("--events", type=int, default=None, help="generated events per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="default", choices=["default", "thread", "hp"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     proc = args.process or default_process()
@@ -185,6 +186,7 @@ def main():
     from madflow_b200 import vegas as mfv
 
     m, model = mfm.get_process(proc)
+    m.set_variant(args.variant)
     fi = mfi.FusedIntegrand(m, model, sqrts=13e3, masses=wl["masses"], pt_cut=wl["pt_cut"], lab_frame=True,
                             running=wl["running"])
     n_per_gpu = wl["events"]
@@ -324,12 +326,12 @@ def main():
             "generated_events_per_sec": generated / (ms * 1e-3),
             "l2": "inputs are generated in-kernel from Philox counters (no per-event HBM input); e2e inputs "
                   f"{h2d / 2**20:.0f} MiB per step exceed the 126 MB L2",
-            "sigma_pb": final, "sigma_err_pb": err, "constants": "reference",
+            "sigma_pb": final, "sigma_err_pb": err, "constants": "reference", "kernel_variant": m.variant,
         },
         "roofline": {
             "bound": "fp64", "achieved": achieved, "peak": fp64_sustained, "unit": "TFLOP/s",
             "frac": achieved / fp64_sustained, "traffic": None,
-            "kernel": "integrand_kernel<Proc>", "kernel_ms": kernel_ms,
+            "kernel": "integrand_kernel_hp<Proc>" if m.variant == "hp" else "integrand_kernel<Proc>", "kernel_ms": kernel_ms,
             "flops_per_event_algorithmic": flops,
             "peak_source": "mf_fp64_peak DFMA probe in this run (sustained, after the timed kernels); burst "
                            f"{fp64_burst:.1f} TFLOP/s; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2; "

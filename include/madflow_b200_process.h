@@ -104,6 +104,12 @@ int mfp_integrand_blocks(void);
  * block partial sums of xjac*f, (xjac*f)^2 and the per-dimension histogram of (xjac*f)^2.      */
 int mfp_integrand(const mfp_integrand_args* args, void* stream);
 
+/* Kernel flavour (DESIGN.md "Kernel mapping"): 0 = the process's default, 1 = one event per thread,
+ * 2 = helicity-parallel thread blocks.  Both flavours compute the same numbers; the switch exists so
+ * that the choice per process is made on measurements.  mfp_get_variant returns 1 or 2.            */
+int mfp_set_variant(int variant);
+int mfp_get_variant(void);
+
 const char* mfp_last_error(void);
 
 #ifdef __cplusplus

@@ -126,10 +126,21 @@ class ProcessLib:
             self.coupling_defs.append((re.value, im.value, pw.value))
         self.helicities = [[self.lib.mfp_helicity(ic, leg) for leg in range(info.nexternal)]
                            for ic in range(info.ncomb)]
+        if os.environ.get("MADFLOW_B200_VARIANT"):
+            self.set_variant(os.environ["MADFLOW_B200_VARIANT"])
 
     def _check(self, rc):
         if rc != 0:
             raise MadflowB200Error((self.lib.mfp_last_error() or b"unknown error").decode())
+
+    def set_variant(self, variant):
+        """Kernel flavour: 0/'default', 1/'thread' (one event per thread), 2/'hp' (helicity-parallel)."""
+        v = {"default": 0, "thread": 1, "hp": 2}.get(variant, variant)
+        self._check(self.lib.mfp_set_variant(int(v)))
+
+    @property
+    def variant(self):
+        return {1: "thread", 2: "hp"}[int(self.lib.mfp_get_variant())]
 
     def smatrix(self, d_p, layout, nevt, par, d_coup, coup_stride, sqh, d_out, only_comb=None):
         _require_cuda()

@@ -110,29 +110,11 @@ def _jamp_update(j, re, im, amp):
     return f"J{j} += mk({re!r}, {im!r}) * {amp};"
 
 
-def emit_matrix_body(ir):
+def _emit_colour(ir):
+    """Colour quadratic form Re sum_ij J_i cf_ij conj(J_j)/denom_j (matrix_method_python.inc:137) with the
+    integer matrix as compile-time constants; symmetric form when all row denominators are equal."""
     lines = []
-    slots = sorted({c["out"] for c in ir["calls"] if "out" in c})
-    lines.append("    cxd " + ", ".join(f"w{s}[6]" for s in slots) + ";")
     ncolor = len(ir["jamp"])
-    lines.append("    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(ncolor)) + ";")
-    by_amp = {}
-    for j, terms in enumerate(ir["jamp"]):
-        for k, re, im in terms:
-            by_amp.setdefault(k, []).append((j, float(re), float(im)))
-    for c in ir["calls"]:
-        if "amp" in c:
-            k = c["amp"]
-            uses = by_amp.get(k, [])
-            if not uses:
-                continue
-            lines.append(f"    {{ const cxd amp = {_emit_call(ir, c)};")
-            for j, re, im in uses:
-                lines.append("      " + _jamp_update(j, re, im, "amp"))
-            lines.append("    }")
-        else:
-            lines.append("    " + _emit_call(ir, c))
-    # colour contraction
     cf, den = ir["color_num"], ir["color_denom"]
     uniform = len(set(den)) == 1 and all(cf[i][j] == cf[j][i] for i in range(ncolor) for j in range(ncolor))
     if uniform:
@@ -158,6 +140,155 @@ def emit_matrix_body(ir):
             lines.append(f"      me += (z.re * J{j}.re + z.im * J{j}.im) / {float(den[j])!r}; }}")
         lines.append("    return me;")
     return "\n".join(lines)
+
+
+def emit_matrix_body(ir):
+    lines = []
+    slots = sorted({c["out"] for c in ir["calls"] if "out" in c})
+    lines.append("    cxd " + ", ".join(f"w{s}[6]" for s in slots) + ";")
+    ncolor = len(ir["jamp"])
+    lines.append("    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(ncolor)) + ";")
+    by_amp = {}
+    for j, terms in enumerate(ir["jamp"]):
+        for k, re, im in terms:
+            by_amp.setdefault(k, []).append((j, float(re), float(im)))
+    for c in ir["calls"]:
+        if "amp" in c:
+            k = c["amp"]
+            uses = by_amp.get(k, [])
+            if not uses:
+                continue
+            lines.append(f"    {{ const cxd amp = {_emit_call(ir, c)};")
+            for j, re, im in uses:
+                lines.append("      " + _jamp_update(j, re, im, "amp"))
+            lines.append("    }")
+        else:
+            lines.append("    " + _emit_call(ir, c))
+    lines.append(_emit_colour(ir))
+    return "\n".join(lines)
+
+
+# ------------------------------------------------------------------------------------------------
+# helicity-parallel variant (csrc/process_kernels_hp.cuh)
+HP_TYPES = {"vxxxxx": 0, "oxxxxx": 1, "ixxxxx": 2, "FFV1_1": 3, "FFV1_2": 4, "FFV1P0_3": 5, "VVV1P0_1": 6,
+            "VVVV1P0_1": 7, "VVVV3P0_1": 8, "VVVV4P0_1": 9}
+
+
+def hp_analyse(ir):
+    """Undo the slot reuse of the call list: every write creates a distinct wavefunction with the set
+    of external legs below it.  Returns (wfs, exts, items, amps, cxd per event)."""
+    cur = {}      # slot -> wavefunction id
+    wfs, exts, items, amps = [], [], [], []
+    for c in ir["calls"]:
+        if "leg" in c:
+            w = len(wfs)
+            wfs.append({"legs": (c["leg"],)})
+            cur[c["out"]] = w
+            exts.append({"call": c, "out": w})
+        elif "amp" in c:
+            amps.append({"call": c, "in": [cur[s] for s in c["in"]]})
+        else:
+            ins = [cur[s] for s in c["in"]]
+            legs = tuple(sorted(set().union(*[wfs[i]["legs"] for i in ins])))
+            assert len(legs) == sum(len(wfs[i]["legs"]) for i in ins), "children must not share legs"
+            w = len(wfs)
+            wfs.append({"legs": legs})
+            cur[c["out"]] = w
+            items.append({"call": c, "in": ins, "out": w})
+    off = 0
+    for w in wfs:
+        w["level"] = len(w["legs"])
+        w["nv"] = 1 << w["level"]
+        w["off"] = off
+        w["mask"] = sum(1 << l for l in w["legs"])
+        off += 2 + 4 * w["nv"]
+    items.sort(key=lambda it: (wfs[it["out"]]["level"], HP_TYPES[it["call"]["op"]]))
+    return wfs, exts, items, amps, off
+
+
+def _vmap(out_legs, in_legs):
+    word = 0
+    for v in range(1 << len(out_legs)):
+        idx = 0
+        for q, l in enumerate(in_legs):
+            idx |= ((v >> out_legs.index(l)) & 1) << q
+        word |= idx << (4 * v)
+    return word
+
+
+def hp_events_per_block(ir):
+    return max(1, 128 // ir["ncomb"])
+
+
+def emit_hp(ir):
+    """Tables + the straight-line amplitude/JAMP/colour code of the helicity-parallel kernels."""
+    wfs, exts, items, amps, wfsize = hp_analyse(ir)
+    n = ir["nexternal"]
+    assert ir["ncomb"] == 2**n, "the hp kernels need the full 2^n helicity table"
+    maxlevel = max(w["level"] for w in wfs)
+    assert maxlevel <= 4, "variant maps hold up to 16 variants per current"
+
+    def pidx(name):
+        return -1 if name == "ZERO" else ir["params"].index(name)
+
+    def both(ctype, name, count, body):
+        return (f"__device__ __constant__ {ctype} d_{name}[{count}] = {{{body}}};\n"
+                f"static const {ctype} h_{name}[{count}] = {{{body}}};")
+
+    L = []
+    L.append(both("mf::HpWf", "wf", len(wfs), ", ".join(f"{{{w['off']}u, {w['nv']}, {w['mask']}}}" for w in wfs)))
+    ext_by_leg = sorted(exts, key=lambda x: x["call"]["leg"])
+    assert [x["call"]["leg"] for x in ext_by_leg] == list(range(n))
+    L.append(both("mf::HpExt", "ext", n, ", ".join(
+        f"{{{HP_TYPES[x['call']['op']]}, {x['call']['leg']}, {x['call']['nsf']}, {pidx(x['call']['mass'])}, {x['out']}}}"
+        for x in ext_by_leg)))
+    rows = []
+    for it in items:
+        c = it["call"]
+        ins = it["in"] + [0] * (3 - len(it["in"]))
+        vm = [_vmap(wfs[it["out"]]["legs"], wfs[i]["legs"]) for i in it["in"]] + [0] * (3 - len(it["in"]))
+        rows.append(f"{{{HP_TYPES[c['op']]}, {len(it['in'])}, {pidx(c['mass'])}, {pidx(c['width'])}, "
+                    f"{ir['couplings'].index(c['coup'])}, {1 if c.get('coup_sign', 1) < 0 else 0}, {it['out']}, "
+                    f"{{{ins[0]}, {ins[1]}, {ins[2]}}}, {{{vm[0]}ull, {vm[1]}ull, {vm[2]}ull}}}}")
+    L.append(both("mf::HpItem", "items", max(len(rows), 1), ",\n  ".join(rows) if rows else "{0}"))
+    begins = [sum(1 for it in items if wfs[it["out"]]["level"] < lev) for lev in range(0, maxlevel + 2)]
+    L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
+    tables = "\n".join(L)
+
+    A = []
+    ncolor = len(ir["jamp"])
+    A.append("    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(ncolor)) + ";")
+    A.append("    cxd a[6], b[6], c[6], d[6];")
+    by_amp = {}
+    for j, terms in enumerate(ir["jamp"]):
+        for k, re, im in terms:
+            by_amp.setdefault(k, []).append((j, float(re), float(im)))
+    names = "abcd"
+    for am in amps:
+        c = am["call"]
+        uses = by_amp.get(c["amp"], [])
+        if not uses:
+            continue
+        A.append("    {")
+        for q, w in enumerate(am["in"]):
+            W = wfs[w]
+            A.append(f"      mf::HpRef{{wf + {W['off']} * E + e * {2 + 4 * W['nv']}, {W['nv']}, "
+                     f"mf::hp_pext<{W['mask']}u>(h)}}.load({names[q]});")
+        op = c["op"]
+        fn = f"VVVV_0<{op[4]}>" if op.startswith("VVVV") else op
+        args = ", ".join(names[: len(am["in"])])
+        A.append(f"      const cxd amp = mf::{fn}({args}, {_coup_expr(ir, c)});")
+        for j, re, im in uses:
+            A.append("      " + _jamp_update(j, re, im, "amp"))
+        A.append("    }")
+    A.append(_emit_colour(ir))
+    return tables, "\n".join(A), dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items))
+
+
+def use_hp_default(ir):
+    """Default kernel flavour per process: one event per thread while the wavefunctions of one
+    helicity fit in registers, helicity-parallel blocks beyond (DESIGN.md "Kernel mapping")."""
+    return len(ir["calls"]) > 16
 
 
 def choose_launch(ir):
@@ -189,15 +320,27 @@ def emit_process_source(ir, block=None, minblocks=None):
         body = " ".join(f"case {i}: return {fmt(v)};" for i, v in enumerate(vals))
         return f"switch (i) {{ {body} default: return {fmt(0)}; }}"
 
+    hp_tables, hp_amps, hp = emit_hp(ir)
+    hp_e = hp_events_per_block(ir)
+    use_hp = "true" if use_hp_default(ir) else "false"
+    hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = 2, hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
     pnames = ", ".join(f'"{p}"' for p in ir["params"]) or '""'
     cnames = ", ".join(f'"{c}"' for c in ir["couplings"]) or '""'
     src = f"""// GENERATED by madflow_b200.codegen -- do not edit.  Process: {ir.get('process', ir['name'])}
 // One fused FP64 kernel per process: HELAS wavefunctions -> ALOHA vertices -> JAMP -> colour matrix.
-#include "process_kernels.cuh"
+#include "process_kernels_hp.cuh"
 
 namespace {{
 __device__ __constant__ signed char d_hel[{ir['ncomb'] * n}] = {{{hel_flat}}};
 static const signed char h_hel[{ir['ncomb'] * n}] = {{{hel_flat}}};
+
+{hp_tables}
+
+#ifdef __CUDA_ARCH__
+#define MF_TAB(name) d_##name
+#else
+#define MF_TAB(name) h_##name
+#endif
 
 MF_DEV int P_hel(int icomb, int leg) {{
 #ifdef __CUDA_ARCH__
@@ -221,6 +364,19 @@ struct Proc {{
   MF_DEV static constexpr double coup_im(int i) {{ {switch([c[1] for c in cdefs], lambda v: repr(float(v)))} }}
   MF_DEV static constexpr int coup_power(int i) {{ {switch([c[2] for c in cdefs], lambda v: str(int(v)))} }}
   MF_DEV static int hel(int icomb, int leg) {{ return P_hel(icomb, leg); }}
+
+  // helicity-parallel variant (process_kernels_hp.cuh)
+  static constexpr bool USE_HP = {use_hp};
+  static constexpr int HP_E = {hp_e}, HP_MINBLOCKS = {hp_minblocks}, HP_WFSIZE = {hp_wfsize}, HP_MAXLEVEL = {hp_maxlevel};
+  static constexpr int HP_NWF = {hp_nwf}, HP_NITEMS = {hp_nitems};
+  MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
+  MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
+  MF_DEV static mf::HpItem item(int i) {{ return MF_TAB(items)[i]; }}
+  MF_DEV static int level_begin(int L) {{ return MF_TAB(level_begin)[L]; }}
+  // amplitudes, JAMPs and colour sum of thread (event e, helicity bits h); currents in shared memory
+  MF_DEV static double hp_amps(const cxd* wf, int E, int e, int h, const cxd* coup) {{
+{hp_amps}
+  }}
 
   // Matrix_{_cname(ir)}.matrix for helicity row `icomb`
   MF_DEV static double matrix(const double (*p)[4], int icomb, const double* par, const cxd* coup, double sqh) {{

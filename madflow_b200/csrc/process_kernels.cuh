@@ -298,12 +298,12 @@ int integrand_blocks() {
 }
 
 template <class P>
-int launch_integrand(const mfp_integrand_args* u, cudaStream_t st) {
+int prepare_integrand_args(const mfp_integrand_args* u, IntegrandArgs& a) {
   constexpr int NOUT = P::NEXT - 2;
   if (u->nevents <= 0) return fail_msg("mfp_integrand: nevents must be positive");
-  if (u->ncuts > MFP_MAX_CUTS) return fail_msg("mfp_integrand: too many cuts");
+  if (u->ncuts < 0 || u->ncuts > MFP_MAX_CUTS) return fail_msg("mfp_integrand: too many cuts");
   if (u->nblocks <= 0) return fail_msg("mfp_integrand: nblocks must come from mfp_integrand_blocks()");
-  IntegrandArgs a;
+  if (!u->d_grid || !u->d_partial) return fail_msg("mfp_integrand: null grid or partial buffer");
   a.u = *u;
   double msum = 0.0;
   for (int i = 0; i < NOUT; ++i) msum += u->masses[i];
@@ -316,8 +316,16 @@ int launch_integrand(const mfp_integrand_args* u, cudaStream_t st) {
   for (int i = 0; i < u->ncuts; ++i) {
     const mfp_cut& c = u->cuts[i];
     if (c.particle < 0 || c.particle >= P::NEXT) return fail_msg("mfp_integrand: cut on a non-existent particle");
+    if (c.var < 0 || c.var > 2) return fail_msg("mfp_integrand: unknown cut variable");
     a.cuts.c[i] = Cut{c.var, c.particle, c.has_min, c.has_max, c.vmin, c.vmax};
   }
+  return 0;
+}
+
+template <class P>
+int launch_integrand(const mfp_integrand_args* u, cudaStream_t st) {
+  IntegrandArgs a;
+  if (int rc = prepare_integrand_args<P>(u, a)) return rc;
   cudaError_t e = cudaFuncSetAttribute(integrand_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(IntegrandSmem<P>));
   if (e != cudaSuccess) return fail("integrand_kernel smem attribute", e);
@@ -327,9 +335,9 @@ int launch_integrand(const mfp_integrand_args* u, cudaStream_t st) {
   return 0;
 }
 
-template <class P>
-int smatrix_host(const double* h_p, int layout, long long nevt, const double* par, const double* h_coup,
-                 long long coup_stride, double sqh, double* h_out) {
+template <class P, class Launch>
+int smatrix_host(Launch launch, const double* h_p, int layout, long long nevt, const double* par,
+                 const double* h_coup, long long coup_stride, double sqh, double* h_out) {
   if (nevt <= 0) return 0;
   double *d_p = nullptr, *d_c = nullptr, *d_o = nullptr;
   const size_t pb = (size_t)nevt * P::NEXT * 4 * sizeof(double);
@@ -341,7 +349,7 @@ int smatrix_host(const double* h_p, int layout, long long nevt, const double* pa
   int rc = 0;
   if ((e = cudaMemcpy(d_p, h_p, pb, cudaMemcpyHostToDevice)) != cudaSuccess) rc = fail("H2D momenta", e);
   if (!rc && cb && (e = cudaMemcpy(d_c, h_coup, cb, cudaMemcpyHostToDevice)) != cudaSuccess) rc = fail("H2D coup", e);
-  if (!rc) rc = launch_smatrix<P>(d_p, layout, nevt, par, d_c, coup_stride, sqh, d_o, -1, 0);
+  if (!rc) rc = launch(d_p, layout, nevt, par, d_c, coup_stride, sqh, d_o, -1, (cudaStream_t)0);
   if (!rc && (e = cudaMemcpy(h_out, d_o, nevt * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
     rc = fail("D2H result", e);
   cudaFree(d_p), cudaFree(d_o);
@@ -350,46 +358,3 @@ int smatrix_host(const double* h_p, int layout, long long nevt, const double* pa
 }
 
 }  // namespace mf
-
-#define MF_DEFINE_PROCESS(P)                                                                                   \
-  extern "C" {                                                                                                 \
-  int mfp_get_info(mfp_info* o) {                                                                              \
-    if (!o) return mf::fail_msg("mfp_get_info: null pointer");                                                 \
-    memset(o, 0, sizeof(*o));                                                                                  \
-    strncpy(o->name, P::name(), sizeof(o->name) - 1);                                                          \
-    o->nexternal = P::NEXT, o->ninitial = P::NINIT, o->ncomb = P::NCOMB, o->ncolor = P::NCOLOR;                \
-    o->ndiags = P::NDIAGS, o->namps = P::NAMPS, o->nwavefuncs = P::NWF, o->nparams = P::NPAR;                  \
-    o->ncouplings = P::NCOUP, o->ndim = 4 * (P::NEXT - 2) + 2, o->block_threads = P::BLOCK;                    \
-    o->denominator = P::DENOM, o->flops_per_event = P::FLOPS;                                                  \
-    return 0;                                                                                                  \
-  }                                                                                                            \
-  const char* mfp_param_name(int i) { return (i >= 0 && i < P::NPAR) ? P::param_name(i) : ""; }                \
-  const char* mfp_coupling_name(int i) { return (i >= 0 && i < P::NCOUP) ? P::coupling_name(i) : ""; }         \
-  int mfp_coupling_def(int i, double* re, double* im, int* power) {                                            \
-    if (i < 0 || i >= P::NCOUP) return mf::fail_msg("mfp_coupling_def: index out of range");                   \
-    *re = P::coup_re(i), *im = P::coup_im(i), *power = P::coup_power(i);                                       \
-    return 0;                                                                                                  \
-  }                                                                                                            \
-  int mfp_helicity(int ic, int leg) {                                                                          \
-    return (ic >= 0 && ic < P::NCOMB && leg >= 0 && leg < P::NEXT) ? P::hel(ic, leg) : 0;                      \
-  }                                                                                                            \
-  int mfp_smatrix(const double* d_p, int layout, int64_t nevt, const double* par, const double* d_coup,        \
-                  int64_t cs, double sqh, double* d_out, void* st) {                                           \
-    return mf::launch_smatrix<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, -1, (cudaStream_t)st);        \
-  }                                                                                                            \
-  int mfp_matrix_hel(const double* d_p, int layout, int64_t nevt, int ic, const double* par,                   \
-                     const double* d_coup, int64_t cs, double sqh, double* d_out, void* st) {                  \
-    if (ic < 0 || ic >= P::NCOMB) return mf::fail_msg("mfp_matrix_hel: helicity row out of range");            \
-    return mf::launch_smatrix<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, ic, (cudaStream_t)st);        \
-  }                                                                                                            \
-  int mfp_smatrix_host(const double* h_p, int layout, int64_t nevt, const double* par, const double* h_coup,   \
-                       int64_t cs, double sqh, double* h_out) {                                                \
-    return mf::smatrix_host<P>(h_p, layout, nevt, par, h_coup, cs, sqh, h_out);                                \
-  }                                                                                                            \
-  int mfp_integrand_blocks(void) { return mf::integrand_blocks<P>(); }                                         \
-  int mfp_integrand(const mfp_integrand_args* a, void* st) {                                                   \
-    if (!a) return mf::fail_msg("mfp_integrand: null args");                                                   \
-    return mf::launch_integrand<P>(a, (cudaStream_t)st);                                                       \
-  }                                                                                                            \
-  const char* mfp_last_error(void) { return mf::g_err; }                                                       \
-  }

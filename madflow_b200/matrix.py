@@ -41,6 +41,14 @@ class Matrix:
     def __str__(self):
         return self._name
 
+    def set_variant(self, variant):
+        """Select the kernel flavour ('default', 'thread', 'hp'); see DESIGN.md "Kernel mapping"."""
+        self._lib.set_variant(variant)
+
+    @property
+    def variant(self):
+        return self._lib.variant
+
     def clean(self):
         pass
 

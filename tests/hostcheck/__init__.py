@@ -51,8 +51,8 @@ def process(ir):
     return ctypes.CDLL(out)
 
 
-def smatrix(lib, ir, p, par, coup, sqh, only_comb=-1):
-    """p (nevt,n,4); coup (ncoup,) or (ncoup,nevt) complex."""
+def smatrix(lib, ir, p, par, coup, sqh, only_comb=-1, hp=False):
+    """p (nevt,n,4); coup (ncoup,) or (ncoup,nevt) complex.  hp=True runs the helicity-parallel flavour."""
     p = np.ascontiguousarray(p, dtype=np.float64)
     nevt = p.shape[0]
     coup = np.ascontiguousarray(np.asarray(coup, dtype=np.complex128))
@@ -60,7 +60,8 @@ def smatrix(lib, ir, p, par, coup, sqh, only_comb=-1):
     cflat = coup.view(np.float64)
     out = np.empty(nevt)
     par = np.ascontiguousarray(par, dtype=np.float64)
-    rc = lib.hostcheck_smatrix(_dp(p), ctypes.c_longlong(nevt), _dp(par), _dp(cflat), ctypes.c_longlong(stride),
+    fn = lib.hostcheck_smatrix_hp if hp else lib.hostcheck_smatrix
+    rc = fn(_dp(p), ctypes.c_longlong(nevt), _dp(par), _dp(cflat), ctypes.c_longlong(stride),
                                ctypes.c_double(sqh), ctypes.c_int(only_comb), _dp(out))
     assert rc == 0
     return out

@@ -1,6 +1,8 @@
 // TEST INFRASTRUCTURE: runs a generated process's Proc::matrix() on the CPU.
 // The device functions are __host__ __device__, so the very code the GPU kernel executes can be
 // checked against the oracle in the build container (no GPU there).  Never linked into the product.
+#include <vector>
+
 #include MF_PROC_SOURCE
 
 extern "C" int hostcheck_smatrix(const double* p, long long nevt, const double* par, const double* coup,
@@ -19,5 +21,49 @@ extern "C" int hostcheck_smatrix(const double* p, long long nevt, const double* 
     else
       out[ev] = mf::smatrix_event<Proc>(m, par, c, sqh);
   }
+  return 0;
+}
+
+// The helicity-parallel flavour: its phases are separated by block barriers only, so running every
+// "thread" of a phase in turn on the CPU reproduces the kernel's data flow exactly.
+extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const double* par, const double* coup,
+                                    long long coup_stride, double sqh, int only_comb, double* out) {
+  constexpr int E = Proc::HP_E, NH = Proc::NCOMB, T = E * NH;
+  std::vector<cxd> wf((size_t)Proc::HP_WFSIZE * E);
+  std::vector<double> mom(E * Proc::NEXT * 4);
+  std::vector<cxd> cp(E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
+  int only_h = -1;
+  if (only_comb >= 0) {
+    only_h = 0;
+    for (int j = 0; j < Proc::NEXT; ++j) only_h |= ((Proc::hel(only_comb, j) + 1) >> 1) << j;
+  }
+  for (long long ev0 = 0; ev0 < nevt; ev0 += E) {
+    const int nev = (int)((nevt - ev0) < E ? (nevt - ev0) : E);
+    for (int e = 0; e < E; ++e) {
+      const long long ev = ev0 + (e < nev ? e : 0);
+      for (int r = 0; r < Proc::NEXT * 4; ++r) mom[e * Proc::NEXT * 4 + r] = p[ev * Proc::NEXT * 4 + r];
+      for (int j = 0; j < Proc::NCOUP; ++j) {
+        const long long o = coup_stride ? ((long long)j * nevt + ev) : j;
+        cp[e * Proc::NCOUP + j] = mk(coup[2 * o], coup[2 * o + 1]);
+      }
+    }
+    for (int it = 0; it < Proc::NEXT * E * 2; ++it) mf::hp_externals<Proc>(it, E, mom.data(), par, sqh, wf.data());
+    for (int L = 2; L <= Proc::HP_MAXLEVEL; ++L) {
+      const int begin = Proc::level_begin(L), cnt = Proc::level_begin(L + 1) - begin, nv = 1 << L;
+      for (int w = 0; w < cnt * E * nv; ++w) {
+        const int ci = w / (E * nv), r = w - ci * (E * nv), e = r / nv, v = r - e * nv;
+        mf::hp_current<Proc>(begin + ci, e, v, E, par, cp.data() + e * Proc::NCOUP, wf.data());
+      }
+    }
+    for (int e = 0; e < nev; ++e) {
+      double acc = 0.0;
+      for (int h = 0; h < NH; ++h) {
+        const double me = Proc::hp_amps(wf.data(), E, e, h, cp.data() + e * Proc::NCOUP);
+        if (only_h < 0 || h == only_h) acc += me;
+      }
+      out[ev0 + e] = only_h >= 0 ? acc : acc / Proc::DENOM;
+    }
+  }
+  (void)T;
   return 0;
 }
