@@ -176,7 +176,8 @@ class ProcessLib:
 _process_cache = {}
 
 
-def process_lib(name):
-    if name not in _process_cache:
-        _process_cache[name] = ProcessLib(os.path.join(LIBDIR, f"libmfp_{name}.so"))
-    return _process_cache[name]
+def process_lib(name, path=None):
+    path = path or os.path.join(LIBDIR, f"libmfp_{name}.so")
+    if path not in _process_cache:
+        _process_cache[path] = ProcessLib(path)
+    return _process_cache[path]

@@ -312,9 +312,10 @@ def emit_process_source(ir, block=None, minblocks=None):
     hel_flat = ", ".join(str(int(h)) for row in ir["helicities"] for h in row)
     cdefs = []
     for cname in ir["couplings"]:
-        if cname not in COUPLING_DEFS:
+        law = ir.get("coupling_defs", {}).get(cname) or COUPLING_DEFS.get(cname)
+        if law is None:
             raise ValueError(f"coupling {cname}: alpha_s dependence unknown to the CUDA backend")
-        cdefs.append(COUPLING_DEFS[cname])
+        cdefs.append(tuple(law))
 
     def switch(vals, fmt):
         body = " ".join(f"case {i}: return {fmt(v)};" for i, v in enumerate(vals))
@@ -390,6 +391,19 @@ MF_DEFINE_PROCESS(Proc)
     return src
 
 
+def compile_source(src_path, out, verbose=False, extra_flags=()):
+    """nvcc one generated process source into a shared library (sm_100a)."""
+    cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-I", CSRC, "-o", out, src_path]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src_path}:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return out
+
+
 def lib_path(ir_or_name):
     name = ir_or_name if isinstance(ir_or_name, str) else ir_or_name["name"]
     return os.path.join(LIBDIR, f"libmfp_{name}.so")
@@ -409,15 +423,7 @@ def build_process(ir, out=None, verbose=False, extra_flags=()):
         fh.write(text)
     with open(os.path.join(GENDIR, f"proc_{ir['name']}.json"), "w") as fh:
         fh.write(process_ir.dumps(ir))
-    cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-I", CSRC, "-o", out, src_path]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed for {ir['name']}:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
-    return out
+    return compile_source(src_path, out, verbose, extra_flags)
 
 
 def _newest_header_mtime():

@@ -21,8 +21,8 @@ from .parameters import Model
 class Matrix:
     """Drop-in for the generated `Matrix_<process_string>` (matrix_method_python.inc:60-104)."""
 
-    def __init__(self, name, ir=None):
-        self._lib = rt.process_lib(name)
+    def __init__(self, name, ir=None, lib_path=None):
+        self._lib = rt.process_lib(name, lib_path)
         info = self._lib.info
         self._name = self._lib.name
         self.nexternal = float(info.nexternal)

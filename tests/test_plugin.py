@@ -1,0 +1,187 @@
+"""The MG5_aMC `pyout` plugin with the CUDA backend, exercised with stand-ins of the MG5 objects
+(MG5_aMC is not installed here; SURVEY.md Appendix G lists the calls the exporter makes).  CPU only."""
+import fractions
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+# the HELAS call lines of the reference's frozen generated code, tests/mockup_debug_me.py:516-528
+MOCKUP_CALLS = """w0 = vxxxxx(all_ps[:,0],ZERO,hel[0],float_me(-1))
+w1 = vxxxxx(all_ps[:,1],ZERO,hel[1],float_me(-1))
+w2 = oxxxxx(all_ps[:,2],mdl_MT,hel[2],float_me(+1))
+w3 = ixxxxx(all_ps[:,3],mdl_MT,hel[3],float_me(-1))
+w4= VVV1P0_1(w0,w1,GC_10,ZERO,ZERO)
+# Amplitude(s) for diagram number 1
+amp0= FFV1_0(w3,w2,w4,GC_11)
+w4= FFV1_1(w2,w0,GC_11,mdl_MT,mdl_WT)
+# Amplitude(s) for diagram number 2
+amp1= FFV1_0(w3,w4,w1,GC_11)
+w4= FFV1_2(w3,w0,GC_11,mdl_MT,mdl_WT)
+# Amplitude(s) for diagram number 3
+amp2= FFV1_0(w4,w2,w1,GC_11)""".split("\n")
+
+
+class FakeProcess(dict):
+    def shell_string(self):
+        return "1_gg_ttx"
+
+    def nice_string(self):
+        return "Process: g g > t t~ WEIGHTED<=2 @1"
+
+    def get_initial_ids(self):
+        return [21, 21]
+
+
+class FakeColorMatrix:
+    def __bool__(self):
+        return True
+
+    def get_line_denominators(self):
+        return [3, 3]
+
+    def get_line_numerators(self, index, denominator):
+        return [[16, -2], [-2, 16]][index]
+
+
+class FakeMatrixElement:
+    """What MG5's HelasMatrixElement answers for g g > t t~ (values: mockup_debug_me.py:415-543)."""
+
+    def get(self, key):
+        return {"processes": [FakeProcess(legs=[], model=None)], "diagrams": [1, 2, 3],
+                "color_basis": {0: 1, 1: 1}, "color_matrix": FakeColorMatrix()}[key]
+
+    def get_nexternal_ninitial(self):
+        return (4, 2)
+
+    def get_helicity_combinations(self):
+        return 16
+
+    def get_helicity_matrix(self):
+        return [[a, b, c, d] for a in (-1, 1) for b in (-1, 1) for c in (-1, 1) for d in (1, -1)]
+
+    def get_denominator_factor(self):
+        return 256
+
+    def get_number_of_amplitudes(self):
+        return 3
+
+    def get_number_of_wavefunctions(self):
+        return 5
+
+    def get_mirror_processes(self):
+        return []
+
+    def get_color_amplitudes(self):
+        one = fractions.Fraction(1)
+        # ((fermion factor, fraction, is_imaginary, Nc power), amplitude number)
+        return [[((1, one, True, 0), 1), ((-1, one, False, 0), 2)],
+                [((-1, one, True, 0), 1), ((-1, one, False, 0), 3)]]
+
+
+def test_plugin_registration_surface():
+    plugin = importlib.import_module("madgraph_plugin")
+    assert set(plugin.new_output) == {"pyout"}
+    assert plugin.new_cluster == {} and plugin.new_interface is None
+    assert plugin.minimal_mg5amcnlo_version == (2, 5, 0)
+    exp = plugin.new_output["pyout"]
+    assert (exp.check, exp.exporter, exp.output, exp.grouped_mode, exp.sa_symmetry) == (True, 'v4', 'dir', False, False)
+    for method in ("pass_information_from_cmd", "generate_subprocess_directory", "convert_model", "finalize"):
+        assert callable(getattr(exp, method))
+
+
+def test_helas_call_lines_to_ir_reproduces_the_pinned_process():
+    from madflow_b200 import process_ir
+    from madgraph_plugin import PyOut_exporter
+
+    ir = PyOut_exporter.matrix_element_to_ir(FakeMatrixElement(), MOCKUP_CALLS)
+    pin = process_ir.gg_ttx_pinned()
+    assert process_ir.validate(ir)
+    strip = lambda calls: [{k: v for k, v in c.items() if k != "coup_sign"} for c in calls]
+    assert strip(ir["calls"]) == pin["calls"]
+    assert [list(t) for t in ir["jamp"]] == [list(t) for t in pin["jamp"]]
+    for key in ("name", "nexternal", "ninitial", "ndiags", "ncomb", "nwavefuncs", "helicities", "denominator",
+                "params", "couplings", "color_num", "color_denom", "initial_states", "mirror_initial_states"):
+        assert ir[key] == pin[key], key
+
+
+def test_helas_call_parser_rejects_garbage():
+    from madgraph_plugin.PyOut_helas_call_writer import parse_helas_calls
+
+    with pytest.raises(ValueError):
+        parse_helas_calls(["w1 = something strange"])
+    calls = parse_helas_calls(["w5= FFV1_1(w2,w0,-GC_11,mdl_MT,mdl_WT)", "w0 = vxxxxx(all_ps[:,0],ZERO, 4,float_me(-1))"])
+    assert calls[0]["coup"] == "GC_11" and calls[0]["coup_sign"] == -1
+    assert calls[1] == {"op": "vxxxxx", "out": 0, "leg": 0, "mass": "ZERO", "nsf": -1}
+
+
+def test_coupling_power_law():
+    from madgraph_plugin.PyOut_exporter import coupling_power_law, jamp_coefficient
+
+    assert coupling_power_law("-G") == (-1.0, 0.0, 1)
+    assert coupling_power_law("complex(0,1)*G") == (0.0, 1.0, 1)
+    assert coupling_power_law("complex(0,1)*G**2") == (0.0, 1.0, 2)
+    assert coupling_power_law("cmath.sqrt(G)") is None
+    assert jamp_coefficient(1, fractions.Fraction(1, 3), True, 1) == (0.0, 1.0)
+    assert jamp_coefficient(-1, fractions.Fraction(1, 3), False, 0) == (-1.0 / 3.0, 0.0)
+
+
+def test_write_process_files(tmp_path):
+    """The exporter's products for one subprocess: IR, CUDA source, generated Python module."""
+    from madflow_b200 import process_ir
+    from madgraph_plugin import PyOut_exporter
+
+    ir = PyOut_exporter.matrix_element_to_ir(FakeMatrixElement(), MOCKUP_CALLS)
+    lines = ("    mdl_MT = param_card['MASS'].get(6).value\n    mdl_WT = param_card['DECAY'].get(6).value\n"
+             "    GC_10 = lambda G: complex_me(-G)\n    GC_11 = lambda G: complex_me(complex(0,1)*G)\n")
+    path = PyOut_exporter.write_process_files(ir, str(tmp_path), lines, build=False)
+    assert os.path.exists(tmp_path / "1_gg_ttx.json") and os.path.exists(tmp_path / "1_gg_ttx.cu")
+    src = open(tmp_path / "1_gg_ttx.cu").read()
+    assert "MF_DEFINE_PROCESS(Proc)" in src and "mf::VVV1P0_1(w0, w1, coup[0]" in src
+    assert process_ir.loads(open(tmp_path / "1_gg_ttx.json").read())["calls"] == ir["calls"]
+    # the generated module: get_model_param works from a param_card without MG5
+    (tmp_path / "param_card.dat").write_text("Block MASS\n  6 1.730000e+02 # MT\nDECAY 6 1.491500e+00 # WT\n")
+    sys.path.insert(0, str(tmp_path))
+    try:
+        mod = importlib.import_module("matrix_1_gg_ttx")
+        text = open(path).read()
+        assert "class Matrix_1_gg_ttx(Matrix)" in text and "def get_model_param(model, param_card_path)" in text
+        import torch
+
+        if torch.cuda.is_available():
+            model = mod.get_model_param(None, str(tmp_path / "param_card.dat"))
+            assert [float(m) for m in model.get_masses()] == [173.0]
+    finally:
+        sys.path.remove(str(tmp_path))
+        sys.modules.pop("matrix_1_gg_ttx", None)
+
+
+def test_param_card_reader(tmp_path):
+    from madflow_b200.param_card import ParamCard
+
+    (tmp_path / "card.dat").write_text("Block SMINPUTS\n 1 1.325070e+02 # aEWM1\n 3 1.180000e-01 # aS\n"
+                                       "Block MASS\n 6 1.730000e+02\nDECAY 6 1.491500e+00\n")
+    card = ParamCard(str(tmp_path / "card.dat"))
+    assert card["SMINPUTS"].get(3).value == 0.118 and card["MASS"].get(6).value == 173.0
+    assert card["DECAY"].get(6).value == 1.4915
+
+
+def test_aloha_cpp_to_cuda_retargeting():
+    from madgraph_plugin.PyOut_create_aloha import cpp_to_cuda
+
+    cpp = """void VVV1P0_1(std::complex<double> V2[], std::complex<double> V3[], std::complex<double> COUP, double M1, double W1, std::complex<double> V1[])
+{
+  static std::complex<double> cI = std::complex<double>(0.,1.);
+  std::complex<double> TMP1;
+  V1[0] = +V2[0]+V3[0];
+  TMP1 = (V3[2]*V2[2]);
+  V1[2] = COUP * TMP1 * cI;
+}"""
+    cu = cpp_to_cuda(cpp)
+    assert cu.startswith("__device__ __forceinline__ void VVV1P0_1(const cxtype V2[], const cxtype V3[], cxtype COUP")
+    assert "cxtype V1[])" in cu and "const cxtype V1[]" not in cu
+    assert "const cxtype cI(0., 1.);" in cu and "static" not in cu and "std::complex" not in cu
