@@ -110,7 +110,7 @@ def _jamp_update(j, re, im, amp):
     return f"J{j} += mk({re!r}, {im!r}) * {amp};"
 
 
-def _emit_colour(ir):
+def _emit_colour(ir, J=lambda i: f"J{i}"):
     """Colour quadratic form Re sum_ij J_i cf_ij conj(J_j)/denom_j (matrix_method_python.inc:137) with the
     integer matrix as compile-time constants; symmetric form when all row denominators are equal."""
     lines = []
@@ -125,10 +125,10 @@ def _emit_colour(ir):
                 if cf[i][j] != 0:
                     terms.append((j, 2 * cf[i][j]))
             # row i: J_i . (cf_ii J_i + sum_{j>i} 2 cf_ij J_j)
-            lines.append(f"    {{ double tr = {float(cf[i][i])!r} * J{i}.re, ti = {float(cf[i][i])!r} * J{i}.im;")
+            lines.append(f"    {{ double tr = {float(cf[i][i])!r} * {J(i)}.re, ti = {float(cf[i][i])!r} * {J(i)}.im;")
             for j, v in terms:
-                lines.append(f"      tr += {float(v)!r} * J{j}.re; ti += {float(v)!r} * J{j}.im;")
-            lines.append(f"      me += J{i}.re * tr + J{i}.im * ti; }}")
+                lines.append(f"      tr += {float(v)!r} * {J(j)}.re; ti += {float(v)!r} * {J(j)}.im;")
+            lines.append(f"      me += {J(i)}.re * tr + {J(i)}.im * ti; }}")
         lines.append(f"    return me / {float(den[0])!r};")
     else:
         lines.append("    double me = 0.0;")
@@ -136,8 +136,8 @@ def _emit_colour(ir):
             lines.append("    { cxd z = mk(0.0, 0.0);")
             for i in range(ncolor):
                 if cf[i][j] != 0:
-                    lines.append(f"      z += {float(cf[i][j])!r} * J{i};")
-            lines.append(f"      me += (z.re * J{j}.re + z.im * J{j}.im) / {float(den[j])!r}; }}")
+                    lines.append(f"      z += {float(cf[i][j])!r} * {J(i)};")
+            lines.append(f"      me += (z.re * {J(j)}.re + z.im * {J(j)}.im) / {float(den[j])!r}; }}")
         lines.append("    return me;")
     return "\n".join(lines)
 
@@ -255,34 +255,29 @@ def emit_hp(ir):
     L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
     tables = "\n".join(L)
 
-    A = []
-    ncolor = len(ir["jamp"])
-    A.append("    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(ncolor)) + ";")
-    A.append("    cxd a[6], b[6], c[6], d[6];")
+    HP_AMP_TYPES = {"FFV1_0": 0, "VVV1_0": 1, "VVVV1_0": 2, "VVVV3_0": 3, "VVVV4_0": 4}
     by_amp = {}
     for j, terms in enumerate(ir["jamp"]):
         for k, re, im in terms:
             by_amp.setdefault(k, []).append((j, float(re), float(im)))
-    names = "abcd"
-    for am in amps:
+    used = [am for am in amps if by_amp.get(am["call"]["amp"])]
+    arows = []
+    for am in used:
         c = am["call"]
-        uses = by_amp.get(c["amp"], [])
-        if not uses:
-            continue
-        A.append("    {")
-        for q, w in enumerate(am["in"]):
-            W = wfs[w]
-            A.append(f"      mf::HpRef{{wf + {W['off']} * E + e * {2 + 4 * W['nv']}, {W['nv']}, "
-                     f"mf::hp_pext<{W['mask']}u>(h)}}.load({names[q]});")
-        op = c["op"]
-        fn = f"VVVV_0<{op[4]}>" if op.startswith("VVVV") else op
-        args = ", ".join(names[: len(am["in"])])
-        A.append(f"      const cxd amp = mf::{fn}({args}, {_coup_expr(ir, c)});")
-        for j, re, im in uses:
-            A.append("      " + _jamp_update(j, re, im, "amp"))
-        A.append("    }")
-    A.append(_emit_colour(ir))
-    return tables, "\n".join(A), dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items))
+        ins = am["in"] + [0] * (4 - len(am["in"]))
+        arows.append(f"{{{HP_AMP_TYPES[c['op']]}, {len(am['in'])}, {ir['couplings'].index(c['coup'])}, "
+                     f"{1 if c.get('coup_sign', 1) < 0 else 0}, {{{ins[0]}, {ins[1]}, {ins[2]}, {ins[3]}}}}}")
+    tables += "\n" + both("mf::HpAmp", "amps", max(len(arows), 1), ",\n  ".join(arows) if arows else "{0}")
+
+    A = ["    switch (ai) {"]
+    for pos, am in enumerate(used):
+        upd = " ".join(_jamp_update(j, re, im, "amp").replace(f"J{j} ", f"J[{j}] ") for j, re, im in by_amp[am["call"]["amp"]])
+        A.append(f"      case {pos}: {upd} break;")
+    A.append("      default: break;")
+    A.append("    }")
+    C = _emit_colour(ir, J=lambda i: f"J[{i}]")
+    return tables, "\n".join(A), C, dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items),
+                                         namps=len(used))
 
 
 def use_hp_default(ir):
@@ -321,7 +316,7 @@ def emit_process_source(ir, block=None, minblocks=None):
         body = " ".join(f"case {i}: return {fmt(v)};" for i, v in enumerate(vals))
         return f"switch (i) {{ {body} default: return {fmt(0)}; }}"
 
-    hp_tables, hp_amps, hp = emit_hp(ir)
+    hp_tables, hp_jamp, hp_colour, hp = emit_hp(ir)
     hp_e = hp_events_per_block(ir)
     use_hp = "true" if use_hp_default(ir) else "false"
     hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = 2, hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
@@ -369,14 +364,18 @@ struct Proc {{
   // helicity-parallel variant (process_kernels_hp.cuh)
   static constexpr bool USE_HP = {use_hp};
   static constexpr int HP_E = {hp_e}, HP_MINBLOCKS = {hp_minblocks}, HP_WFSIZE = {hp_wfsize}, HP_MAXLEVEL = {hp_maxlevel};
-  static constexpr int HP_NWF = {hp_nwf}, HP_NITEMS = {hp_nitems};
+  static constexpr int HP_NWF = {hp_nwf}, HP_NITEMS = {hp_nitems}, HP_NAMPS = {hp['namps']};
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
   MF_DEV static mf::HpItem item(int i) {{ return MF_TAB(items)[i]; }}
   MF_DEV static int level_begin(int L) {{ return MF_TAB(level_begin)[L]; }}
-  // amplitudes, JAMPs and colour sum of thread (event e, helicity bits h); currents in shared memory
-  MF_DEV static double hp_amps(const cxd* wf, int E, int e, int h, const cxd* coup) {{
-{hp_amps}
+  MF_DEV static mf::HpAmp amp(int i) {{ return MF_TAB(amps)[i]; }}
+  // JAMP updates of amplitude `ai` (block-uniform switch, JAMP registers addressed statically)
+  MF_DEV static void jamp_accumulate(int ai, cxd amp, cxd (&J)[NCOLOR]) {{
+{hp_jamp}
+  }}
+  MF_DEV static double colour_sum(const cxd (&J)[NCOLOR]) {{
+{hp_colour}
   }}
 
   // Matrix_{_cname(ir)}.matrix for helicity row `icomb`

@@ -11,10 +11,10 @@
 //   phase 2   off-shell currents level by level (level = number of legs); the work items of a
 //             level are (current, event, helicity variant), spread over all threads of the block;
 //             table driven (HpItem), one copy of each ALOHA routine in the instruction stream
-//   phase 3   amplitudes + JAMP sums: thread (e, h) walks the generated straight-line list of the
-//             process's amplitudes, reading each input current's variant for ITS helicity h
-//             (a warp's 32 helicities touch <= 8 variants of a current: one shared-memory
-//             wavefront per load), JAMPs stay in registers
+//   phase 3   amplitudes + JAMP sums: thread (e, h) loops over the amplitude table, reading each
+//             input current's variant for ITS helicity h (a warp's 32 helicities touch <= 8
+//             variants of a current: one shared-memory wavefront per load); the JAMP updates are
+//             a generated switch over the amplitude index, so the JAMPs stay in registers
 //   phase 4   colour contraction per thread, then the sum over helicities is a warp-shuffle +
 //             shared-memory reduction per event.
 //
@@ -44,6 +44,13 @@ struct HpExt {
   unsigned char type, leg;
   signed char nsf, mass_idx;   // mass_idx < 0: massless
   unsigned short out;
+};
+
+enum HpAmpType : unsigned char { HP_FFV1_0 = 0, HP_VVV1_0 = 1, HP_VVVV1_0 = 2, HP_VVVV3_0 = 3, HP_VVVV4_0 = 4 };
+
+struct HpAmp {
+  unsigned char type, nin, coup, coup_neg;
+  unsigned short in[4];
 };
 
 struct HpItem {
@@ -122,31 +129,65 @@ MF_DEV void hp_current(int idx, int e, int v, int E, const double* par, const cx
   for (int k = 0; k < 4; ++k) o[2 + k * d.nv + v] = r[2 + k];
 }
 
-// compile-time bit extraction: the bits of h selected by MASK, packed
-template <unsigned MASK>
-MF_DEV int hp_pext(int h) {
-  int out = 0, pos = 0;
+// phase 3 for thread (event e, helicity bits h): loop over the amplitude table.  The loop body is a
+// handful of routines selected by a block-uniform switch, and the JAMP updates of amplitude `ai` are a
+// generated `switch (ai)` whose cases address the JAMP registers statically -- the whole phase is a few
+// tens of KB of instructions and stays in the instruction cache (a fully unrolled amplitude list is
+// ~300 KB for g g > t t~ g g and stalls on instruction fetch: profiles/r01_ttxgg_hp_v1.summary.txt).
+// vtab[w*NCOMB + h] is the helicity variant of wavefunction w that belongs to helicity combination h.
+template <class P>
+MF_DEV void hp_load_amp(const cxd* wf, const unsigned char* vtab, int E, int e, int h, int w, cxd out[6]) {
+  const HpWf d = P::wf(w);
+  const cxd* s = wf + (size_t)d.off * E + (size_t)e * (2 + 4 * d.nv);
+  const int v = vtab[w * P::NCOMB + h];
+  out[0] = s[0], out[1] = s[1];
 #pragma unroll
-  for (int b = 0; b < 16; ++b)
-    if (MASK & (1u << b)) {
+  for (int k = 0; k < 4; ++k) out[2 + k] = s[2 + k * d.nv + v];
+}
+
+template <class P>
+MF_DEV double hp_amplitudes(const cxd* wf, const unsigned char* vtab, int E, int e, int h, const cxd* coup) {
+  cxd J[P::NCOLOR];
+#pragma unroll
+  for (int j = 0; j < P::NCOLOR; ++j) J[j] = mk(0.0, 0.0);
+#pragma unroll 1
+  for (int ai = 0; ai < P::HP_NAMPS; ++ai) {
+    const HpAmp it = P::amp(ai);
+    cxd a[6], b[6], c[6], d[6];
+    hp_load_amp<P>(wf, vtab, E, e, h, it.in[0], a);
+    hp_load_amp<P>(wf, vtab, E, e, h, it.in[1], b);
+    hp_load_amp<P>(wf, vtab, E, e, h, it.in[2], c);
+    cxd cp = coup[it.coup];
+    if (it.coup_neg) cp = -cp;
+    cxd amp;
+    switch (it.type) {
+      case HP_FFV1_0: amp = FFV1_0(a, b, c, cp); break;
+      case HP_VVV1_0: amp = VVV1_0(a, b, c, cp); break;
+      default:
+        hp_load_amp<P>(wf, vtab, E, e, h, it.in[3], d);
+        if (it.type == HP_VVVV1_0) amp = VVVV_0<1>(a, b, c, d, cp);
+        else if (it.type == HP_VVVV3_0) amp = VVVV_0<3>(a, b, c, d, cp);
+        else amp = VVVV_0<4>(a, b, c, d, cp);
+        break;
+    }
+    P::jamp_accumulate(ai, amp, J);
+  }
+  return P::colour_sum(J);
+}
+
+// vtab: helicity variant of every wavefunction for every helicity combination (block-wide, once)
+template <class P>
+MF_DEV void hp_fill_vtab(int idx, unsigned char* vtab) {
+  const int w = idx / P::NCOMB, h = idx - w * P::NCOMB;
+  const unsigned legs = P::wf(w).legs;
+  int out = 0, pos = 0;
+  for (int b = 0; b < P::NEXT; ++b)
+    if (legs & (1u << b)) {
       out |= ((h >> b) & 1) << pos;
       ++pos;
     }
-  return out;
+  vtab[idx] = (unsigned char)out;
 }
-
-// a wavefunction as the amplitude phase sees it: pointers into shared memory
-struct HpRef {
-  const cxd* s;   // block of this event: s[0], s[1] momentum; components at s[2 + k*nv + v]
-  int nv, v;
-  MF_DEV cxd mom(int k) const { return s[k]; }
-  MF_DEV cxd c(int k) const { return s[2 + (k - 2) * nv + v]; }   // k = 2..5 as in HELAS
-  MF_DEV void load(cxd w[6]) const {
-    w[0] = s[0], w[1] = s[1];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[2 + k] = s[2 + k * nv + v];
-  }
-};
 
 // ------------------------------------------------------------------------------------------------
 // The E-event matrix-element evaluation used by both kernels.  `mom` [E][NEXT][4], `coup` [E][NCOUP]
@@ -155,7 +196,8 @@ struct HpRef {
 template <class P>
 __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events */, const double* mom,
                                                    const cxd* coup, const double* par, double sqh, cxd* wf,
-                                                   double* red /* [T/32] */, int only_h) {
+                                                   const unsigned char* vtab, double* red /* [T/32] */,
+                                                   int only_h) {
   constexpr int E = P::HP_E, NH = P::NCOMB, T = E * NH;
   const int tid = threadIdx.x;
   for (int it = tid; it < P::NEXT * E * 2; it += T) hp_externals<P>(it, E, mom, par, sqh, wf);
@@ -175,7 +217,7 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
     __syncthreads();
   }
   const int e = tid / NH, h = tid - e * NH;
-  double me = P::hp_amps(wf, E, e, h, coup + e * P::NCOUP);
+  double me = hp_amplitudes<P>(wf, vtab, E, e, h, coup + e * P::NCOUP);
   if (only_h >= 0) me = (h == only_h) ? me : 0.0;
   if (e >= nev) me = 0.0;
   // sum over helicities of one event
@@ -201,6 +243,7 @@ struct HpSmatrixSmem {
   double mom[E * P::NEXT * 4];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
   double red[T / 32 + 1];
+  unsigned char vtab[P::HP_NWF * P::NCOMB];
   // followed by cxd wf[HP_WFSIZE * E]
 };
 
@@ -211,6 +254,7 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
   HpSmatrixSmem<P>& s = *reinterpret_cast<HpSmatrixSmem<P>*>(smem_raw);
   cxd* wf = reinterpret_cast<cxd*>(smem_raw + ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16);
   const int tid = threadIdx.x;
+  for (int i = tid; i < P::HP_NWF * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
   const long long ngroups = (a.nevt + E - 1) / E;
   for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const long long ev0 = g * E;
@@ -232,7 +276,7 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
       only_h = 0;
       for (int j = 0; j < P::NEXT; ++j) only_h |= ((P::hel(a.only_comb, j) + 1) >> 1) << j;
     }
-    const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, wf, s.red, only_h);
+    const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, wf, s.vtab, s.red, only_h);
     const int e = tid / NH, h = tid - e * NH;
     if (h == 0 && e < nev) a.out[ev0 + e] = me;
     __syncthreads();
@@ -256,6 +300,7 @@ struct HpIntegrandSmem {
   double red3[3][32];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
   double red[T / 32 + 1];
+  unsigned char vtab[P::HP_NWF * P::NCOMB];
 };
 
 template <class P>
@@ -269,6 +314,7 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) integrand_
 
   for (int i = tid; i < NDIM * VEGAS_EDGES; i += T) s.grid[i] = a.u.d_grid[i];
   for (int i = tid; i < NDIM * VEGAS_BINS; i += T) s.hist[i] = 0.0;
+  for (int i = tid; i < P::HP_NWF * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
   __syncthreads();
 
   double s1 = 0.0, s2 = 0.0, cnt = 0.0;
@@ -362,7 +408,7 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) integrand_
         for (int i = tid; i < (E - nev) * P::NCOUP; i += T) s.coup[nev * P::NCOUP + i] = s.coup[i % P::NCOUP];
       }
       __syncthreads();
-      const double me = hp_smatrix_block<P>(nev, &s.qmom[first][0], s.coup, a.u.par, a.u.sqh, wf, s.red, -1);
+      const double me = hp_smatrix_block<P>(nev, &s.qmom[first][0], s.coup, a.u.par, a.u.sqh, wf, s.vtab, s.red, -1);
       const int e = tid / NH, h = tid - e * NH;
       if (h == 0 && e < nev) {
         const int slot = first + e;

@@ -32,6 +32,8 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
   std::vector<cxd> wf((size_t)Proc::HP_WFSIZE * E);
   std::vector<double> mom(E * Proc::NEXT * 4);
   std::vector<cxd> cp(E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
+  std::vector<unsigned char> vtab(Proc::HP_NWF * NH);
+  for (int i = 0; i < Proc::HP_NWF * NH; ++i) mf::hp_fill_vtab<Proc>(i, vtab.data());
   int only_h = -1;
   if (only_comb >= 0) {
     only_h = 0;
@@ -58,7 +60,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
     for (int e = 0; e < nev; ++e) {
       double acc = 0.0;
       for (int h = 0; h < NH; ++h) {
-        const double me = Proc::hp_amps(wf.data(), E, e, h, cp.data() + e * Proc::NCOUP);
+        const double me = mf::hp_amplitudes<Proc>(wf.data(), vtab.data(), E, e, h, cp.data() + e * Proc::NCOUP);
         if (only_h < 0 || h == only_h) acc += me;
       }
       out[ev0 + e] = only_h >= 0 ? acc : acc / Proc::DENOM;
