@@ -170,6 +170,7 @@ def emit_matrix_body(ir):
 
 # ------------------------------------------------------------------------------------------------
 # helicity-parallel variant (csrc/process_kernels_hp.cuh)
+HP_UNROLL_MAX_AMPS = 32   # amplitude lists up to this length are emitted as straight-line code
 HP_TYPES = {"vxxxxx": 0, "oxxxxx": 1, "ixxxxx": 2, "FFV1_1": 3, "FFV1_2": 4, "FFV1P0_3": 5, "VVV1P0_1": 6,
             "VVVV1P0_1": 7, "VVVV3P0_1": 8, "VVVV4P0_1": 9}
 
@@ -276,8 +277,26 @@ def emit_hp(ir):
     A.append("      default: break;")
     A.append("    }")
     C = _emit_colour(ir, J=lambda i: f"J[{i}]")
-    return tables, "\n".join(A), C, dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items),
-                                         namps=len(used))
+    # straight-line flavour of the same phase for short amplitude lists
+    U = ["    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(len(ir["jamp"]))) + ";",
+         "    cxd a[6], b[6], c[6], d[6];"]
+    if len(used) <= HP_UNROLL_MAX_AMPS:
+        for am in used:
+            c = am["call"]
+            for q, w in enumerate(am["in"]):
+                U.append(f"    mf::hp_load_amp<Proc>(wf, vtab, E, e, h, {w}, {'abcd'[q]});")
+            op = c["op"]
+            fn = f"VVVV_0<{op[4]}>" if op.startswith("VVVV") else op
+            args = ", ".join("abcd"[: len(am["in"])])
+            U.append(f"    {{ const cxd amp = mf::{fn}({args}, {_coup_expr(ir, c)});")
+            for j, re, im in by_amp[c["amp"]]:
+                U.append("      " + _jamp_update(j, re, im, "amp"))
+            U.append("    }")
+        U.append(_emit_colour(ir))
+    else:
+        U.append("    return 0.0;  // not used: the amplitude list of this process runs as a loop")
+    return tables, "\n".join(A), C, "\n".join(U), dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items),
+                                         namps=len(used), unroll=len(used) <= HP_UNROLL_MAX_AMPS)
 
 
 def use_hp_default(ir):
@@ -316,7 +335,8 @@ def emit_process_source(ir, block=None, minblocks=None):
         body = " ".join(f"case {i}: return {fmt(v)};" for i, v in enumerate(vals))
         return f"switch (i) {{ {body} default: return {fmt(0)}; }}"
 
-    hp_tables, hp_jamp, hp_colour, hp = emit_hp(ir)
+    hp_tables, hp_jamp, hp_colour, hp_unrolled, hp = emit_hp(ir)
+    hp_unroll = 'true' if hp['unroll'] else 'false'
     hp_e = hp_events_per_block(ir)
     use_hp = "true" if use_hp_default(ir) else "false"
     hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = 2, hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
@@ -377,12 +397,18 @@ struct Proc {{
   MF_DEV static double colour_sum(const cxd (&J)[NCOLOR]) {{
 {hp_colour}
   }}
+  static constexpr bool HP_UNROLL = {hp_unroll};
+  MF_DEV static double hp_amps_unrolled(const cxd* wf, const unsigned char* vtab, int E, int e, int h, const cxd* coup);
 
   // Matrix_{_cname(ir)}.matrix for helicity row `icomb`
   MF_DEV static double matrix(const double (*p)[4], int icomb, const double* par, const cxd* coup, double sqh) {{
 {emit_matrix_body(ir)}
   }}
 }};
+
+MF_DEV double Proc::hp_amps_unrolled(const cxd* wf, const unsigned char* vtab, int E, int e, int h, const cxd* coup) {{
+{hp_unrolled}
+}}
 }}  // namespace
 
 MF_DEFINE_PROCESS(Proc)

@@ -147,6 +147,9 @@ MF_DEV void hp_load_amp(const cxd* wf, const unsigned char* vtab, int E, int e, 
 
 template <class P>
 MF_DEV double hp_amplitudes(const cxd* wf, const unsigned char* vtab, int E, int e, int h, const cxd* coup) {
+  // short amplitude lists are emitted as straight-line code (it fits the instruction cache and has no
+  // loop overhead); long ones run the table-driven loop below
+  if (P::HP_UNROLL) return P::hp_amps_unrolled(wf, vtab, E, e, h, coup);
   cxd J[P::NCOLOR];
 #pragma unroll
   for (int j = 0; j < P::NCOLOR; ++j) J[j] = mk(0.0, 0.0);
