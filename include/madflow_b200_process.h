@@ -95,10 +95,17 @@ typedef struct mfp_integrand_args {
                              * [sum t, sum t^2, #events that reached the matrix element, 0] + hist */
   int32_t nblocks;          /* grid size, from mfp_integrand_blocks()                             */
   int32_t accumulate_hist;  /* 0 when the grid is frozen                                          */
+  /* scratch in HBM for the accepted events of this call (three-stage pipeline of the
+   * helicity-parallel flavour); size from mfp_integrand_workspace(); may be NULL/0 otherwise   */
+  void* d_workspace;
+  int64_t workspace_bytes;
 } mfp_integrand_args;
 
 /* recommended persistent grid size for the current device (multiple of the SM count)          */
 int mfp_integrand_blocks(void);
+/* bytes of device scratch mfp_integrand needs for a call generating `nevents` events (0 for the
+ * one-event-per-thread flavour, whose single kernel keeps everything on chip)                   */
+int64_t mfp_integrand_workspace(int64_t nevents);
 /* One pass of the integrand of scripts/madflow_exec.py:422-470 (--no_pdf) over `nevents` events:
  * Philox -> VEGAS map -> x1,x2 -> RAMBO -> cuts -> boost -> alpha_s -> smatrix -> weight ->
  * block partial sums of xjac*f, (xjac*f)^2 and the per-dimension histogram of (xjac*f)^2.      */

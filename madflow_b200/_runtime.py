@@ -55,6 +55,7 @@ class mfp_integrand_args(ctypes.Structure):
         ("par", ctypes.c_double * MFP_MAX_PARAMS), ("alpha_mode", ctypes.c_int32), ("alpha_s", ctypes.c_double),
         ("mz2", ctypes.c_double), ("b0", ctypes.c_double), ("sqh", ctypes.c_double),
         ("d_partial", ctypes.c_void_p), ("nblocks", ctypes.c_int32), ("accumulate_hist", ctypes.c_int32),
+        ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
     ]
 
 
@@ -167,6 +168,10 @@ class ProcessLib:
     def integrand_blocks(self):
         _require_cuda()
         return int(self.lib.mfp_integrand_blocks())
+
+    def integrand_workspace(self, nevents):
+        self.lib.mfp_integrand_workspace.restype = ctypes.c_int64
+        return int(self.lib.mfp_integrand_workspace(ctypes.c_int64(int(nevents))))
 
     def integrand(self, args):
         _require_cuda()

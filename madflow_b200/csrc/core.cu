@@ -8,6 +8,7 @@
 #include "phasespace.cuh"
 #include "philox.cuh"
 #include "vegas.cuh"
+#include "pipeline_kernels.cuh"
 
 using namespace mf;
 
@@ -216,42 +217,6 @@ __global__ void vegas_sample_kernel(const double* grid, int ndim, unsigned long 
   }
 }
 
-constexpr int ACC_BLOCK = 256;
-__global__ void __launch_bounds__(ACC_BLOCK) vegas_accumulate_kernel(const double* f, const double* xjac,
-                                                                     const unsigned char* bins, long long nevt,
-                                                                     int ndim, int with_hist, double* partial) {
-  extern __shared__ double shist[];  // ndim*50, then 3*8 for the reduction
-  double* red = shist + ndim * VEGAS_BINS;
-  for (int i = threadIdx.x; i < ndim * VEGAS_BINS; i += blockDim.x) shist[i] = 0.0;
-  __syncthreads();
-  double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
-    const double t = f[e] * xjac[e];
-    const double t2 = t * t;
-    s1 += t;
-    s2 += t2;
-    cnt += (t != 0.0) ? 1.0 : 0.0;
-    if (with_hist && t2 != 0.0)
-      for (int d = 0; d < ndim; ++d) atomicAdd(&shist[d * VEGAS_BINS + bins[(long long)d * nevt + e]], t2);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_down_sync(0xffffffffu, s1, o);
-    s2 += __shfl_down_sync(0xffffffffu, s2, o);
-    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) red[warp] = s1, red[8 + warp] = s2, red[16 + warp] = cnt;
-  __syncthreads();
-  double* out = partial + (long long)blockIdx.x * (VEGAS_HEADER + ndim * VEGAS_BINS);
-  if (threadIdx.x == 0) {
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int w = 0; w < ACC_BLOCK / 32; ++w) a += red[w], b += red[8 + w], c += red[16 + w];
-    out[0] = a, out[1] = b, out[2] = c, out[3] = 0.0;
-  }
-  for (int i = threadIdx.x; i < ndim * VEGAS_BINS; i += blockDim.x) out[VEGAS_HEADER + i] = shist[i];
-}
-
 __global__ void vegas_reduce_kernel(const double* partial, int nblocks, int len, int add, double* sums) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
     double acc = add ? sums[i] : 0.0;
@@ -436,9 +401,9 @@ int mf_vegas_accumulate(const double* d_f, const double* d_xjac, const uint8_t* 
   if (ndim < 1 || ndim > MF_MAX_DIM) return fail_msg("mf_vegas_accumulate: 1 <= ndim <= 32");
   if (nblocks < 1) return fail_msg("mf_vegas_accumulate: nblocks < 1");
   const size_t smem = (ndim * VEGAS_BINS + 24) * sizeof(double);
-  vegas_accumulate_kernel<<<nblocks, ACC_BLOCK, smem, (cudaStream_t)stream>>>(d_f, d_xjac, d_bins, nevt, ndim,
-                                                                              with_hist, d_partial);
-  return check_launch("vegas_accumulate_kernel");
+  accumulate_kernel<<<nblocks, ACC_BLOCK, smem, (cudaStream_t)stream>>>(d_f, d_xjac, d_bins, nevt, ndim, with_hist,
+                                                                        d_partial);
+  return check_launch("accumulate_kernel");
 }
 
 int mf_vegas_reduce(const double* d_partial, int nblocks, int ndim, int add, double* d_sums, void* stream) {

@@ -47,6 +47,12 @@ struct SmatrixArgs {
   double sqh;
   double* out;
   int only_comb;  // >= 0: evaluate this helicity row only and do not average (test hook)
+  // segmented input (integrand pipeline): events live in `nseg` segments of `seg_size` slots of which
+  // the first seg_count[s] are valid; couplings then come from alpha_s[slot]
+  const double* alpha_s;
+  const int* seg_count;
+  long long seg_size;
+  int nseg;
 };
 
 template <class P>
@@ -271,6 +277,7 @@ int launch_smatrix(const double* d_p, int layout, long long nevt, const double* 
   SmatrixArgs a;
   a.p = d_p, a.layout = layout, a.nevt = nevt, a.coup = d_coup, a.coup_stride = coup_stride, a.sqh = sqh;
   a.out = d_out, a.only_comb = only_comb;
+  a.alpha_s = nullptr, a.seg_count = nullptr, a.seg_size = 0, a.nseg = 0;
   for (int i = 0; i < MFP_MAX_PARAMS; ++i) a.par[i] = i < P::NPAR ? par[i] : 0.0;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -24,6 +24,7 @@
 // starting at  P::wf_off(w)*E + e*(2 + 4*nv).  Variant bits follow the ascending leg order of S;
 // bit = 1 means helicity +1.
 #pragma once
+#include "pipeline_kernels.cuh"
 #include "process_kernels.cuh"
 
 namespace mf {
@@ -258,198 +259,52 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
   cxd* wf = reinterpret_cast<cxd*>(smem_raw + ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16);
   const int tid = threadIdx.x;
   for (int i = tid; i < P::HP_NWF * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
-  const long long ngroups = (a.nevt + E - 1) / E;
-  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const long long ev0 = g * E;
-    const int nev = (int)((a.nevt - ev0) < E ? (a.nevt - ev0) : E);
-    for (int i = tid; i < E * P::NEXT * 4; i += T) {
-      const int e = i / (P::NEXT * 4), r = i - e * (P::NEXT * 4);
-      const long long ev = ev0 + (e < nev ? e : 0);  // pad with a valid event
-      s.mom[i] = a.layout == MFP_LAYOUT_AOS ? a.p[ev * (P::NEXT * 4) + r] : a.p[(long long)r * a.nevt + ev];
-    }
-    for (int i = tid; i < E * P::NCOUP; i += T) {
-      const int e = i / P::NCOUP, c = i - e * P::NCOUP;
-      const long long ev = ev0 + (e < nev ? e : 0);
-      const double2 v = reinterpret_cast<const double2*>(a.coup)[a.coup_stride ? (long long)c * a.nevt + ev : c];
-      s.coup[i] = mk(v.x, v.y);
-    }
-    __syncthreads();
-    int only_h = -1;
-    if (a.only_comb >= 0) {
-      only_h = 0;
-      for (int j = 0; j < P::NEXT; ++j) only_h |= ((P::hel(a.only_comb, j) + 1) >> 1) << j;
-    }
-    const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, wf, s.vtab, s.red, only_h);
-    const int e = tid / NH, h = tid - e * NH;
-    if (h == 0 && e < nev) a.out[ev0 + e] = me;
-    __syncthreads();
+  int only_h = -1;
+  if (a.only_comb >= 0) {
+    only_h = 0;
+    for (int j = 0; j < P::NEXT; ++j) only_h |= ((P::hel(a.only_comb, j) + 1) >> 1) << j;
   }
-}
-
-// fused integrand, hp flavour: phase-space generation one event per thread, accepted events
-// queued in shared memory, matrix elements E events at a time
-template <class P>
-struct HpIntegrandSmem {
-  static constexpr int NDIM = 4 * (P::NEXT - 2) + 2;
-  static constexpr int E = P::HP_E, T = E * P::NCOMB;
-  static constexpr int QCAP = T + E;
-  double grid[NDIM * VEGAS_EDGES];
-  double hist[NDIM * VEGAS_BINS];
-  double qmom[QCAP][P::NEXT * 4];   // event-major: the ME phase copies whole events
-  double qw[QCAP];
-  double qas[QCAP];
-  unsigned char qbin[QCAP][NDIM];
-  int warp_count[32];
-  double red3[3][32];
-  cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
-  double red[T / 32 + 1];
-  unsigned char vtab[P::HP_NWF * P::NCOMB];
-};
-
-template <class P>
-__global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) integrand_kernel_hp(const IntegrandArgs a) {
-  using S = HpIntegrandSmem<P>;
-  constexpr int NDIM = S::NDIM, E = P::HP_E, NH = P::NCOMB, T = E * NH, NWARP = T / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  S& s = *reinterpret_cast<S*>(smem_raw);
-  cxd* wf = reinterpret_cast<cxd*>(smem_raw + ((sizeof(S) + 15) / 16) * 16);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int i = tid; i < NDIM * VEGAS_EDGES; i += T) s.grid[i] = a.u.d_grid[i];
-  for (int i = tid; i < NDIM * VEGAS_BINS; i += T) s.hist[i] = 0.0;
-  for (int i = tid; i < P::HP_NWF * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
-  __syncthreads();
-
-  double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-  int qcount = 0;
-  const long long ntiles = (a.u.nevents + T - 1) / T;
-  const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  for (long long k = 0; k <= my_tiles; ++k) {
-    const bool flush = (k == my_tiles);
-    if (!flush) {
-      const long long tile = blockIdx.x + k * gridDim.x;
-      const long long local = tile * T + tid;
-      bool ok = false;
-      double m[P::NEXT][4];
-      double wgt = 0.0, as = 0.0;
-      unsigned char bins[NDIM];
-      if (local < a.u.nevents) {
-        const unsigned long long ev = a.u.first_event + (unsigned long long)local;
-        double xr[NDIM];
-        double w = 1.0;
-#pragma unroll
-        for (int j = 0; j < (NDIM + 1) / 2; ++j) {
-          double u0, u1;
-          philox_pair(a.u.seed, a.u.iteration, ev, j, u0, u1);
-          int b;
-          xr[2 * j] = vegas_map(&s.grid[(2 * j) * VEGAS_EDGES], vegas_confine(u0), b, w);
-          bins[2 * j] = (unsigned char)b;
-          if (2 * j + 1 < NDIM) {
-            xr[2 * j + 1] = vegas_map(&s.grid[(2 * j + 1) * VEGAS_EDGES], vegas_confine(u1), b, w);
-            bins[2 * j + 1] = (unsigned char)b;
-          }
-        }
-        double x1, x2;
-        ramboflow<P::NEXT>(xr, a.u.com_sqrts, a.u.masses, a.massive != 0, a.shat_min, a.ps, m, wgt, x1, x2);
-        ok = pass_cuts<P::NEXT>(a.cuts, m);
-        ok = ok && (wgt == wgt) && (wgt != 0.0);
-        if (ok) {
-          if (a.u.lab_frame) boost_to_lab<P::NEXT>(m, x1, x2);
-          double q2 = 0.0;
-          if (a.u.alpha_mode != 0) {
-            double smt = 0.0;
-#pragma unroll
-            for (int i = 2; i < P::NEXT; ++i) smt += cut_value(CUT_MT, m[i]);
-            q2 = (smt / 2.0) * (smt / 2.0);
-          }
-          as = alpha_s_of(a.u, q2);
-          wgt *= w * a.u.inv_total_events;
-        }
+  // plain mode: one "segment" holding all nevt events, blocks stride over its groups of E events;
+  // segmented mode: block b owns segments b, b + gridDim.x, ... and walks their valid events
+  const bool segmented = a.seg_count != nullptr;
+  const int nseg = segmented ? a.nseg : 1;
+  for (int sg = segmented ? blockIdx.x : 0; sg < nseg; sg += segmented ? gridDim.x : 1) {
+    const long long base = segmented ? (long long)sg * a.seg_size : 0;
+    const long long cnt = segmented ? a.seg_count[sg] : a.nevt;
+    const long long ngroups = (cnt + E - 1) / E;
+    for (long long g = segmented ? 0 : blockIdx.x; g < ngroups; g += segmented ? 1 : gridDim.x) {
+      const long long ev0 = base + g * E;
+      const int nev = (int)((base + cnt - ev0) < E ? (base + cnt - ev0) : E);
+      for (int i = tid; i < E * P::NEXT * 4; i += T) {
+        const int e = i / (P::NEXT * 4), r = i - e * (P::NEXT * 4);
+        const long long ev = ev0 + (e < nev ? e : 0);  // pad a partial group with a valid event
+        s.mom[i] = a.layout == MFP_LAYOUT_AOS ? a.p[ev * (P::NEXT * 4) + r] : a.p[(long long)r * a.nevt + ev];
       }
-      const unsigned ballot = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) s.warp_count[warp] = __popc(ballot);
-      __syncthreads();
-      int base = qcount, total = 0;
-#pragma unroll
-      for (int wv = 0; wv < NWARP; ++wv) {
-        const int c = s.warp_count[wv];
-        if (wv < warp) base += c;
-        total += c;
-      }
-      if (ok) {
-        const int slot = base + __popc(ballot & ((1u << lane) - 1u));
-#pragma unroll
-        for (int i = 0; i < P::NEXT; ++i)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) s.qmom[slot][i * 4 + c] = m[i][c];
-        s.qw[slot] = wgt;
-        s.qas[slot] = as;
-#pragma unroll
-        for (int d = 0; d < NDIM; ++d) s.qbin[slot][d] = bins[d];
-      }
-      qcount += total;
-      __syncthreads();
-    }
-    // matrix elements, E queued events at a time (all of them when flushing)
-    while (qcount >= E || (flush && qcount > 0)) {
-      const int nev = qcount < E ? qcount : E;
-      const int first = qcount - nev;
-      // couplings of these events
-      for (int i = tid; i < nev * P::NCOUP; i += T) {
+      for (int i = tid; i < E * P::NCOUP; i += T) {
         const int e = i / P::NCOUP, c = i - e * P::NCOUP;
-        const double G = 2.0 * sqrt(M_PI * s.qas[first + e]);
-        double g = 1.0;
-        for (int q = 0; q < P::coup_power(c); ++q) g *= G;
-        s.coup[i] = mk(P::coup_re(c) * g, P::coup_im(c) * g);
-      }
-      // pad missing events of a partial group with copies of the first one (results discarded)
-      if (nev < E) {
-        for (int i = tid; i < (E - nev) * P::NEXT * 4; i += T) {
-          const int e = nev + i / (P::NEXT * 4), r = i % (P::NEXT * 4);
-          s.qmom[first + e][r] = s.qmom[first][r];
+        const long long ev = ev0 + (e < nev ? e : 0);
+        if (a.alpha_s) {  // couplings from alpha_s: G = 2 sqrt(pi alpha_s) (parameters.py:13-15)
+          const double G = 2.0 * sqrt(M_PI * a.alpha_s[ev]);
+          double gp = 1.0;
+          for (int q = 0; q < P::coup_power(c); ++q) gp *= G;
+          s.coup[i] = mk(P::coup_re(c) * gp, P::coup_im(c) * gp);
+        } else {
+          const double2 v = reinterpret_cast<const double2*>(a.coup)[a.coup_stride ? (long long)c * a.nevt + ev : c];
+          s.coup[i] = mk(v.x, v.y);
         }
-        for (int i = tid; i < (E - nev) * P::NCOUP; i += T) s.coup[nev * P::NCOUP + i] = s.coup[i % P::NCOUP];
       }
       __syncthreads();
-      const double me = hp_smatrix_block<P>(nev, &s.qmom[first][0], s.coup, a.u.par, a.u.sqh, wf, s.vtab, s.red, -1);
+      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, wf, s.vtab, s.red, only_h);
       const int e = tid / NH, h = tid - e * NH;
-      if (h == 0 && e < nev) {
-        const int slot = first + e;
-        const double t = me * s.qw[slot];
-        const double t2 = t * t;
-        s1 += t, s2 += t2, cnt += 1.0;
-        if (a.u.accumulate_hist) {
-#pragma unroll 1
-          for (int d = 0; d < NDIM; ++d) atomicAdd(&s.hist[d * VEGAS_BINS + s.qbin[slot][d]], t2);
-        }
-      }
-      qcount -= nev;
+      if (h == 0 && e < nev) a.out[ev0 + e] = me;
       __syncthreads();
     }
   }
-
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_down_sync(0xffffffffu, s1, o);
-    s2 += __shfl_down_sync(0xffffffffu, s2, o);
-    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-  }
-  if (lane == 0) s.red3[0][warp] = s1, s.red3[1][warp] = s2, s.red3[2][warp] = cnt;
-  __syncthreads();
-  double* out = a.u.d_partial + (long long)blockIdx.x * (VEGAS_HEADER + NDIM * VEGAS_BINS);
-  if (tid == 0) {
-    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    for (int wv = 0; wv < NWARP; ++wv) t1 += s.red3[0][wv], t2 += s.red3[1][wv], t3 += s.red3[2][wv];
-    out[0] = t1, out[1] = t2, out[2] = t3, out[3] = 0.0;
-  }
-  for (int i = tid; i < NDIM * VEGAS_BINS; i += T) out[VEGAS_HEADER + i] = s.hist[i];
 }
 
 // ------------------------------------------------------------------------------------------------
 template <class P>
 size_t hp_smatrix_smem() { return ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16 + sizeof(cxd) * P::HP_WFSIZE * P::HP_E; }
-template <class P>
-size_t hp_integrand_smem() { return ((sizeof(HpIntegrandSmem<P>) + 15) / 16) * 16 + sizeof(cxd) * P::HP_WFSIZE * P::HP_E; }
 
 template <class P>
 int launch_smatrix_hp(const double* d_p, int layout, long long nevt, const double* par, const double* d_coup,
@@ -460,6 +315,7 @@ int launch_smatrix_hp(const double* d_p, int layout, long long nevt, const doubl
   SmatrixArgs a;
   a.p = d_p, a.layout = layout, a.nevt = nevt, a.coup = d_coup, a.coup_stride = coup_stride, a.sqh = sqh;
   a.out = d_out, a.only_comb = only_comb;
+  a.alpha_s = nullptr, a.seg_count = nullptr, a.seg_size = 0, a.nseg = 0;
   for (int i = 0; i < MFP_MAX_PARAMS; ++i) a.par[i] = i < P::NPAR ? par[i] : 0.0;
   const size_t smem = hp_smatrix_smem<P>();
   cudaError_t e = cudaFuncSetAttribute(smatrix_kernel_hp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -483,23 +339,59 @@ int integrand_blocks_hp() {
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = hp_integrand_smem<P>();
-  cudaFuncSetAttribute(integrand_kernel_hp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, integrand_kernel_hp<P>, P::HP_E * P::NCOMB, smem);
+  const size_t smem = hp_smatrix_smem<P>();
+  cudaFuncSetAttribute(smatrix_kernel_hp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smatrix_kernel_hp<P>, P::HP_E * P::NCOMB, smem);
   if (per_sm < 1) per_sm = 1;
   return sms * per_sm;
 }
 
+// segments of the event buffer: a few per matrix-element block so that the blocks stay balanced
+template <class P>
+int hp_segments(int nblocks) { return nblocks * 4; }
+
+template <class P>
+long long integrand_workspace_hp(long long nevents) {
+  constexpr int NDIM = 4 * (P::NEXT - 2) + 2;
+  return (long long)event_buffer_layout(nevents, hp_segments<P>(integrand_blocks_hp<P>()), P::NEXT, NDIM, nullptr, nullptr);
+}
+
+// One pass of the integrand = three launches on the caller's stream (see pipeline_kernels.cuh)
 template <class P>
 int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
-  IntegrandArgs a;
-  if (int rc = prepare_integrand_args<P>(u, a)) return rc;
-  const size_t smem = hp_integrand_smem<P>();
-  cudaError_t e = cudaFuncSetAttribute(integrand_kernel_hp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail("integrand_kernel_hp smem attribute", e);
-  integrand_kernel_hp<P><<<u->nblocks, P::HP_E * P::NCOMB, smem, st>>>(a);
+  constexpr int NDIM = 4 * (P::NEXT - 2) + 2;
+  IntegrandArgs ia;
+  if (int rc = prepare_integrand_args<P>(u, ia)) return rc;
+  const int nseg = hp_segments<P>(u->nblocks);
+  GenArgs g;
+  g.u = ia.u, g.massive = ia.massive, g.shat_min = ia.shat_min, g.ps = ia.ps, g.cuts = ia.cuts;
+  const size_t need = event_buffer_layout(u->nevents, nseg, P::NEXT, NDIM, u->d_workspace, &g.buf);
+  if (!u->d_workspace || (size_t)u->workspace_bytes < need)
+    return fail_msg("mfp_integrand: workspace missing or smaller than mfp_integrand_workspace(nevents)");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ggrid = nseg < sms * 8 ? nseg : sms * 8;
+  ps_generate_kernel<P::NEXT><<<ggrid, GEN_BLOCK, 0, st>>>(g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("ps_generate_kernel launch", e);
+
+  SmatrixArgs a;
+  a.p = g.buf.mom, a.layout = MFP_LAYOUT_AOS, a.nevt = g.buf.cap, a.coup = nullptr, a.coup_stride = 0;
+  a.sqh = u->sqh, a.out = g.buf.me, a.only_comb = -1;
+  a.alpha_s = g.buf.as, a.seg_count = g.buf.count, a.seg_size = g.buf.seg, a.nseg = nseg;
+  for (int i = 0; i < MFP_MAX_PARAMS; ++i) a.par[i] = i < P::NPAR ? u->par[i] : 0.0;
+  const size_t smem = hp_smatrix_smem<P>();
+  e = cudaFuncSetAttribute(smatrix_kernel_hp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail("smatrix_kernel_hp smem attribute", e);
+  smatrix_kernel_hp<P><<<u->nblocks, P::HP_E * P::NCOMB, smem, st>>>(a);
   e = cudaGetLastError();
-  if (e != cudaSuccess) return fail("integrand_kernel_hp launch", e);
+  if (e != cudaSuccess) return fail("smatrix_kernel_hp launch", e);
+
+  accumulate_kernel<<<u->nblocks, ACC_BLOCK, (NDIM * VEGAS_BINS + 24) * sizeof(double), st>>>(
+      g.buf.me, g.buf.w, g.buf.bins, g.buf.cap, NDIM, u->accumulate_hist, u->d_partial);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("accumulate_kernel launch", e);
   return 0;
 }
 
@@ -561,6 +453,9 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
   }                                                                                                            \
   int mfp_integrand_blocks(void) {                                                                             \
     return mf::use_hp<P>() ? mf::integrand_blocks_hp<P>() : mf::integrand_blocks<P>();                         \
+  }                                                                                                            \
+  int64_t mfp_integrand_workspace(int64_t nevents) {                                                           \
+    return mf::use_hp<P>() ? mf::integrand_workspace_hp<P>(nevents) : 0;                                       \
   }                                                                                                            \
   int mfp_integrand(const mfp_integrand_args* a, void* st) {                                                   \
     if (!a) return mf::fail_msg("mfp_integrand: null args");                                                   \

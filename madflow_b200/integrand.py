@@ -48,6 +48,7 @@ class FusedIntegrand:
         if pt_cut is not None:  # madflow_exec.py:392-395
             self.cuts += [("pt", i, float(pt_cut), None) for i in range(2, n)]
         self.lab_frame = bool(lab_frame)
+        self.max_events_per_launch = 1 << 23   # bounds the HBM scratch of the pipeline flavour (~2 GB)
         self.running = bool(running)
         if alpha_s is None:
             alpha_s = 0.118
@@ -62,6 +63,15 @@ class FusedIntegrand:
 
     def nblocks(self):
         return self._lib.integrand_blocks()
+
+    def _workspace(self, nevents):
+        need = self._lib.integrand_workspace(nevents)
+        if need == 0:
+            return None
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need:
+            self._ws = ws = torch.empty(need, dtype=torch.uint8, device=config.device())
+        return ws
 
     def _args(self):
         a = rt.mfp_integrand_args()
@@ -89,6 +99,9 @@ class FusedIntegrand:
         a.d_partial = partial.data_ptr()
         a.nblocks = int(nblocks)
         a.accumulate_hist = int(bool(train))
+        ws = self._workspace(nevents)
+        a.d_workspace = ws.data_ptr() if ws is not None else None
+        a.workspace_bytes = ws.numel() if ws is not None else 0
         self._lib.integrand(a)
 
     # -- the same integrand from the separate API calls (reference structure, madflow_exec.py:422-470)

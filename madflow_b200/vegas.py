@@ -167,7 +167,8 @@ class VegasFlow:
             raise ValueError(f"the integrand needs {self.integrand.n_dim} dimensions, VegasFlow has {self.n_dim}")
         _, rank, world = _dist()
         first, count = shard_events(self.n_events, rank, world)
-        limit = self.events_limit or (count if fused else 10_000_000)
+        limit = self.events_limit or (min(count, getattr(self.integrand, "max_events_per_launch", count)) if fused
+                                      else 10_000_000)
         self._sums.zero_()
         done = 0
         while done < count:
