@@ -170,7 +170,9 @@ def emit_matrix_body(ir):
 
 # ------------------------------------------------------------------------------------------------
 # helicity-parallel variant (csrc/process_kernels_hp.cuh)
+THREAD_MAX_CALLS = 64     # call lists up to this length also get the one-event-per-thread kernels
 HP_UNROLL_MAX_AMPS = 32   # amplitude lists up to this length are emitted as straight-line code
+HP_SCRATCH_CXD = 1024     # shared-memory scratch for pair objects, complex numbers per event (16 KB)
 HP_TYPES = {"vxxxxx": 0, "oxxxxx": 1, "ixxxxx": 2, "FFV1_1": 3, "FFV1_2": 4, "FFV1P0_3": 5, "VVV1P0_1": 6,
             "VVVV1P0_1": 7, "VVVV3P0_1": 8, "VVVV4P0_1": 9}
 
@@ -217,7 +219,14 @@ def _vmap(out_legs, in_legs):
     return word
 
 
+def hp_group():
+    """Amplitudes per unrolled group of the amplitude phase (csrc: MF_HP_GROUP)."""
+    return int(os.environ.get("MADFLOW_B200_HP_GROUP", 12))
+
+
 def hp_events_per_block(ir):
+    if os.environ.get("MADFLOW_B200_HP_E"):
+        return int(os.environ["MADFLOW_B200_HP_E"])
     return max(1, 128 // ir["ncomb"])
 
 
@@ -248,32 +257,127 @@ def emit_hp(ir):
         c = it["call"]
         ins = it["in"] + [0] * (3 - len(it["in"]))
         vm = [_vmap(wfs[it["out"]]["legs"], wfs[i]["legs"]) for i in it["in"]] + [0] * (3 - len(it["in"]))
+        ioff = [wfs[i]["off"] for i in ins]
+        inv = [wfs[i]["nv"] for i in ins]
+        W = wfs[it["out"]]
         rows.append(f"{{{HP_TYPES[c['op']]}, {len(it['in'])}, {pidx(c['mass'])}, {pidx(c['width'])}, "
-                    f"{ir['couplings'].index(c['coup'])}, {1 if c.get('coup_sign', 1) < 0 else 0}, {it['out']}, "
-                    f"{{{ins[0]}, {ins[1]}, {ins[2]}}}, {{{vm[0]}ull, {vm[1]}ull, {vm[2]}ull}}}}")
+                    f"{ir['couplings'].index(c['coup'])}, {1 if c.get('coup_sign', 1) < 0 else 0}, {W['off']}, {W['nv']}, "
+                    f"{{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
+                    f"{{{vm[0]}ull, {vm[1]}ull, {vm[2]}ull}}}}")
     L.append(both("mf::HpItem", "items", max(len(rows), 1), ",\n  ".join(rows) if rows else "{0}"))
     begins = [sum(1 for it in items if wfs[it["out"]]["level"] < lev) for lev in range(0, maxlevel + 2)]
     L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
     tables = "\n".join(L)
 
-    HP_AMP_TYPES = {"FFV1_0": 0, "VVV1_0": 1, "VVVV1_0": 2, "VVVV3_0": 3, "VVVV4_0": 4}
     by_amp = {}
     for j, terms in enumerate(ir["jamp"]):
         for k, re, im in terms:
             by_amp.setdefault(k, []).append((j, float(re), float(im)))
     used = [am for am in amps if by_amp.get(am["call"]["amp"])]
-    arows = []
+
+    # pair objects: amp = x . Q(rest of the vertex), x = the input with the most legs
+    QUARTIC = {"1": ((+1, (1, 4), (2, 3)), (-1, (1, 3), (2, 4))),
+               "3": ((+1, (1, 4), (2, 3)), (-1, (1, 2), (3, 4))),
+               "4": ((+1, (1, 3), (2, 4)), (-1, (1, 2), (3, 4)))}
+    pairs, pair_index, amp_rows = [], {}, []
     for am in used:
         c = am["call"]
-        ins = am["in"] + [0] * (4 - len(am["in"]))
-        arows.append(f"{{{HP_AMP_TYPES[c['op']]}, {len(am['in'])}, {ir['couplings'].index(c['coup'])}, "
-                     f"{1 if c.get('coup_sign', 1) < 0 else 0}, {{{ins[0]}, {ins[1]}, {ins[2]}, {ins[3]}}}}}")
-    tables += "\n" + both("mf::HpAmp", "amps", max(len(arows), 1), ",\n  ".join(arows) if arows else "{0}")
+        ins = am["in"]
+        sizes = [wfs[w]["level"] for w in ins]
+        jx = sizes.index(max(sizes))
+        op = c["op"]
+        term = (0, 0)
+        if op == "FFV1_0":
+            I, O, G = ins
+            ptype, rest = [("ROW", (O, G)), ("COL", (I, G)), ("CUR", (I, O))][jx]
+        elif op == "VVV1_0":
+            ptype, rest = "VVV", (ins[(jx + 1) % 3], ins[(jx + 2) % 3])
+        else:
+            ptype = "VVVV"
+            others = [q for q in range(4) if q != jx]
+            rest = tuple(ins[q] for q in others)
+            pos = {q + 1: others.index(q) for q in others}   # vertex position -> index into `rest`
+            enc = []
+            for sign, pa, pb in QUARTIC[op[4]]:
+                if jx + 1 in pa:
+                    vec, dot = [q for q in pa if q != jx + 1][0], pb
+                else:
+                    vec, dot = [q for q in pb if q != jx + 1][0], pa
+                enc.append((0x40 if sign < 0 else 0) | pos[vec] << 4 | pos[dot[0]] << 2 | pos[dot[1]])
+            term = tuple(enc)
+        coup, neg = ir["couplings"].index(c["coup"]), 1 if c.get("coup_sign", 1) < 0 else 0
+        key = (ptype, rest, term, coup, neg)
+        if key not in pair_index:
+            legs = tuple(sorted(set().union(*[wfs[w]["legs"] for w in rest])))
+            pair_index[key] = len(pairs)
+            pairs.append(dict(type=ptype, rest=rest, term=term, coup=coup, neg=neg, legs=legs, nv=1 << len(legs)))
+        amp_rows.append(dict(am=am, x=ins[jx], pair=pair_index[key]))
+    # batches: pair objects in order of first use, packed into the scratch area
+    scratch = int(os.environ.get("MADFLOW_B200_HP_SCRATCH", HP_SCRATCH_CXD))
+    order = sorted(range(len(amp_rows)), key=lambda k: amp_rows[k]["pair"])
+    batches, cur_pairs, cur_amps, fill = [], [], [], 0
+    for k in order:
+        pi = amp_rows[k]["pair"]
+        if pi not in cur_pairs:
+            need = 4 * pairs[pi]["nv"]
+            assert need <= scratch
+            if fill + need > scratch:
+                batches.append((cur_pairs, cur_amps))
+                cur_pairs, cur_amps, fill = [], [], 0
+            pairs[pi]["off"] = fill
+            fill += need
+            cur_pairs.append(pi)
+        cur_amps.append(k)
+    if cur_amps:
+        batches.append((cur_pairs, cur_amps))
+    PT = {"ROW": 0, "COL": 1, "CUR": 2, "VVV": 3, "VVVV": 4}
+    prow = []
+    for pr in pairs:
+        rest = list(pr["rest"]) + [0] * (3 - len(pr["rest"]))
+        vm = [_vmap(pr["legs"], wfs[w]["legs"]) for w in pr["rest"]] + [0] * (3 - len(pr["rest"]))
+        mask = sum(1 << l for l in pr["legs"])
+        ioff = [wfs[w]["off"] for w in rest]
+        inv = [wfs[w]["nv"] for w in rest]
+        prow.append(f"{{{PT[pr['type']]}, {len(pr['rest'])}, {pr['coup']}, {pr['neg']}, {{{pr['term'][0]}, {pr['term'][1]}}}, "
+                    f"{pr['nv']}, {pr.get('off', 0)}, {{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
+                    f"{{{vm[0]}ull, {vm[1]}ull, {vm[2]}ull}}}}")
+    E = hp_events_per_block(ir)
+    NH = ir["ncomb"]
+    GROUP = hp_group()
+    irow, arow, brow, groups = [], [], [], []
 
-    A = ["    switch (ai) {"]
-    for pos, am in enumerate(used):
-        upd = " ".join(_jamp_update(j, re, im, "amp").replace(f"J{j} ", f"J[{j}] ") for j, re, im in by_amp[am["call"]["amp"]])
-        A.append(f"      case {pos}: {upd} break;")
+    def amp_entry(k):
+        r = amp_rows[k]
+        xw, pr = wfs[r["x"]], pairs[r["pair"]]
+        qmask = sum(1 << l for l in pr["legs"])
+        return (f"{{{xw['off'] + 2}, {pr['off']}, {xw['nv']}, {pr['nv']}, {xw['mask'] * NH}, {qmask * NH}}}")
+
+    for cur_pairs, cur_amps in batches:
+        ib, gb = len(irow), len(groups)
+        for pi in sorted(cur_pairs, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
+            for v in range(pairs[pi]["nv"]):
+                irow.append(f"{{{pi}, {v}}}")
+        for g0 in range(0, len(cur_amps), GROUP):
+            chunk = cur_amps[g0:g0 + GROUP]
+            groups.append(chunk)
+            for k in chunk:
+                arow.append(amp_entry(k))
+            for _ in range(GROUP - len(chunk)):   # pad with a repeat; its result is not accumulated
+                arow.append(amp_entry(chunk[0]))
+        brow.append(f"{{{ib}, {len(irow)}, {gb}, {len(groups)}}}")
+    tables += "\n" + both("mf::HpPair", "pairs", max(len(prow), 1), ",\n  ".join(prow) if prow else "{0}")
+    tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0}")
+    tables += "\n" + both("mf::HpAmp", "amps", max(len(arow), 1), ", ".join(arow) if arow else "{0, 0, 0, 0, 0, 0}")
+    tables += "\n" + both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}")
+
+    A = ["    switch (g) {"]
+    for gi, chunk in enumerate(groups):
+        upd = []
+        for slot, k in enumerate(chunk):
+            am = amp_rows[k]["am"]
+            for j, re, im in by_amp[am["call"]["amp"]]:
+                upd.append(_jamp_update(j, re, im, f"amp[{slot}]").replace(f"J{j} ", f"J[{j}] "))
+        A.append(f"      case {gi}: " + " ".join(upd) + " break;")
     A.append("      default: break;")
     A.append("    }")
     C = _emit_colour(ir, J=lambda i: f"J[{i}]")
@@ -284,7 +388,7 @@ def emit_hp(ir):
         for am in used:
             c = am["call"]
             for q, w in enumerate(am["in"]):
-                U.append(f"    mf::hp_load_amp<Proc>(wf, vtab, E, e, h, {w}, {'abcd'[q]});")
+                U.append(f"    mf::hp_load_amp<Proc>(wf_e, vtab, h, {w}, {'abcd'[q]});")
             op = c["op"]
             fn = f"VVVV_0<{op[4]}>" if op.startswith("VVVV") else op
             args = ", ".join("abcd"[: len(am["in"])])
@@ -296,7 +400,8 @@ def emit_hp(ir):
     else:
         U.append("    return 0.0;  // not used: the amplitude list of this process runs as a loop")
     return tables, "\n".join(A), C, "\n".join(U), dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items),
-                                         namps=len(used), unroll=len(used) <= HP_UNROLL_MAX_AMPS)
+                                         namps=len(used), unroll=len(used) <= HP_UNROLL_MAX_AMPS,
+                                         nbatch=len(batches), npairs=len(pairs), nitems_pair=len(irow))
 
 
 def use_hp_default(ir):
@@ -337,13 +442,17 @@ def emit_process_source(ir, block=None, minblocks=None):
 
     hp_tables, hp_jamp, hp_colour, hp_unrolled, hp = emit_hp(ir)
     hp_unroll = 'true' if hp['unroll'] else 'false'
+    hp_group_n = hp_group()
+    hp_scratch = 0 if hp['unroll'] else int(os.environ.get("MADFLOW_B200_HP_SCRATCH", HP_SCRATCH_CXD))
     hp_e = hp_events_per_block(ir)
     use_hp = "true" if use_hp_default(ir) else "false"
-    hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = 2, hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
+    has_thread = "true" if (len(ir["calls"]) <= THREAD_MAX_CALLS or os.environ.get("MADFLOW_B200_BUILD_THREAD") == "1") else "false"
+    hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = int(os.environ.get("MADFLOW_B200_HP_MINBLOCKS", 2)), hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
     pnames = ", ".join(f'"{p}"' for p in ir["params"]) or '""'
     cnames = ", ".join(f'"{c}"' for c in ir["couplings"]) or '""'
     src = f"""// GENERATED by madflow_b200.codegen -- do not edit.  Process: {ir.get('process', ir['name'])}
 // One fused FP64 kernel per process: HELAS wavefunctions -> ALOHA vertices -> JAMP -> colour matrix.
+#define MF_HP_GROUP {hp_group_n}
 #include "process_kernels_hp.cuh"
 
 namespace {{
@@ -383,22 +492,29 @@ struct Proc {{
 
   // helicity-parallel variant (process_kernels_hp.cuh)
   static constexpr bool USE_HP = {use_hp};
+  // the one-event-per-thread kernels are only compiled while a helicity's wavefunctions can stay in
+  // registers; beyond that they spill to DRAM (profiles/r01_ttxgg_thread_per_event.summary.txt)
+  static constexpr bool HAS_THREAD = {has_thread};
   static constexpr int HP_E = {hp_e}, HP_MINBLOCKS = {hp_minblocks}, HP_WFSIZE = {hp_wfsize}, HP_MAXLEVEL = {hp_maxlevel};
   static constexpr int HP_NWF = {hp_nwf}, HP_NITEMS = {hp_nitems}, HP_NAMPS = {hp['namps']};
+  static constexpr int HP_NBATCH = {hp['nbatch']}, HP_NPAIRS = {hp['npairs']}, HP_SCRATCH = {hp_scratch};
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
   MF_DEV static mf::HpItem item(int i) {{ return MF_TAB(items)[i]; }}
   MF_DEV static int level_begin(int L) {{ return MF_TAB(level_begin)[L]; }}
   MF_DEV static mf::HpAmp amp(int i) {{ return MF_TAB(amps)[i]; }}
-  // JAMP updates of amplitude `ai` (block-uniform switch, JAMP registers addressed statically)
-  MF_DEV static void jamp_accumulate(int ai, cxd amp, cxd (&J)[NCOLOR]) {{
+  MF_DEV static mf::HpPair pair(int i) {{ return MF_TAB(pairs)[i]; }}
+  MF_DEV static mf::HpPairItem pair_item(int i) {{ return MF_TAB(pair_items)[i]; }}
+  MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
+  // JAMP updates of amplitude group `g` (block-uniform switch, JAMP registers addressed statically)
+  MF_DEV static void jamp_accumulate(int g, const cxd (&amp)[mf::HP_GROUP], cxd (&J)[NCOLOR]) {{
 {hp_jamp}
   }}
   MF_DEV static double colour_sum(const cxd (&J)[NCOLOR]) {{
 {hp_colour}
   }}
   static constexpr bool HP_UNROLL = {hp_unroll};
-  MF_DEV static double hp_amps_unrolled(const cxd* wf, const unsigned char* vtab, int E, int e, int h, const cxd* coup);
+  MF_DEV static double hp_amps_unrolled(const cxd* wf_e, const unsigned char* vtab, int h, const cxd* coup);
 
   // Matrix_{_cname(ir)}.matrix for helicity row `icomb`
   MF_DEV static double matrix(const double (*p)[4], int icomb, const double* par, const cxd* coup, double sqh) {{
@@ -406,7 +522,7 @@ struct Proc {{
   }}
 }};
 
-MF_DEV double Proc::hp_amps_unrolled(const cxd* wf, const unsigned char* vtab, int E, int e, int h, const cxd* coup) {{
+MF_DEV double Proc::hp_amps_unrolled(const cxd* wf_e, const unsigned char* vtab, int h, const cxd* coup) {{
 {hp_unrolled}
 }}
 }}  // namespace

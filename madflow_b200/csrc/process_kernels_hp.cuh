@@ -18,11 +18,11 @@
 //   phase 4   colour contraction per thread, then the sum over helicities is a warp-shuffle +
 //             shared-memory reduction per event.
 //
-// Shared-memory layout of wavefunction w (sizes in cxd = 16 bytes), for the E events of the block:
-//   [e][ 0..1 ]                momentum slots w0, w1  (helicity independent)
-//   [e][ 2 + k*nv + v ]        component k = 0..3 (HELAS slots 2..5), helicity variant v < nv = 2^|S|
-// starting at  P::wf_off(w)*E + e*(2 + 4*nv).  Variant bits follow the ascending leg order of S;
-// bit = 1 means helicity +1.
+// Shared memory: every event of the block owns HP_WFSIZE cxd (= 16 bytes) of wavefunctions and
+// HP_SCRATCH cxd of pair objects.  Wavefunction w lives at offset P::wf(w).off of its event's area:
+//   [ 0..1 ]              momentum slots w0, w1  (helicity independent)
+//   [ 2 + k*nv + v ]      component k = 0..3 (HELAS slots 2..5), helicity variant v < nv = 2^|S|
+// Variant bits follow the ascending leg order of S; bit = 1 means helicity +1.
 #pragma once
 #include "pipeline_kernels.cuh"
 #include "process_kernels.cuh"
@@ -47,31 +47,57 @@ struct HpExt {
   unsigned short out;
 };
 
-enum HpAmpType : unsigned char { HP_FFV1_0 = 0, HP_VVV1_0 = 1, HP_VVVV1_0 = 2, HP_VVVV3_0 = 3, HP_VVVV4_0 = 4 };
+// Amplitude phase.  Every amplitude is written as  amp = sum_k x[2+k] * Q[k]  where x is its input
+// with the most legs and Q ("pair object") is the rest of the vertex contracted once per helicity
+// variant of ITS legs, with -i*COUP and the metric signs folded in:
+//   FFV1_0(I,O,G):  x=I: Q = Obar Gslash (row)   x=O: Q = Gslash I (column)   x=G: Q = current(I,O)
+//   VVV1_0(1,2,3):  Q = three-gluon vertex contracted with the two other legs (cyclic order)
+//   VVVVk_0:        Q = contact term contracted with the three other legs
+// The reference evaluates the whole vertex for each of the 2^n helicity combinations
+// (matrix_method_python.inc:99-102); here the vertex costs 2^|legs(Q)| evaluations and each of the
+// 2^n combinations only a 4-term complex dot product.
+enum HpPairType : unsigned char { HP_Q_ROW = 0, HP_Q_COL = 1, HP_Q_CUR = 2, HP_Q_VVV = 3, HP_Q_VVVV = 4 };
 
-struct HpAmp {
+struct HpPair {
   unsigned char type, nin, coup, coup_neg;
-  unsigned short in[4];
+  unsigned char term[2];       // HP_Q_VVVV: sign<<6 | vector<<4 | dotA<<2 | dotB  (indices into the inputs)
+  unsigned short nv;           // helicity variants of the object
+  unsigned short off;          // offset in the event's scratch area (cxd)
+  unsigned short in_off[3];    // inputs: offset of the wavefunction block in the event's area
+  unsigned short in_nv[3];
+  unsigned long long vmap[3];  // 4 bits per output variant: the input's variant index
+};
+
+struct HpPairItem {
+  unsigned short pair, v;      // work item of a pair phase: (object, helicity variant)
+};
+
+// one amplitude (cxd units, relative to the event's wavefunction / scratch area):
+//   x component k for helicity h:  wf_e[x + k*xnv + vtab[xvt + h]]
+//   Q component k:                 scratch_e[q + k*qnv + vtab[qvt + h]]
+struct HpAmp {
+  unsigned short x, q;         // x: offset of component 0 (block offset + 2) in the event's wavefunction area
+  unsigned short xnv, qnv;     // component strides = helicity variants
+  unsigned short xvt, qvt;     // row of vtab (leg mask * NCOMB)
+};
+
+#ifndef MF_HP_GROUP
+#define MF_HP_GROUP 8
+#endif
+constexpr int HP_GROUP = MF_HP_GROUP;   // amplitudes per unrolled group of the amplitude phase
+
+struct HpBatch {
+  unsigned short item_begin, item_end, group_begin, group_end;
 };
 
 struct HpItem {
   unsigned char type, nin;
   signed char mass_idx, width_idx;   // < 0: ZERO
   unsigned char coup, coup_neg;
-  unsigned short out;
-  unsigned short in[3];
+  unsigned short out_off, out_nv;    // output wavefunction block (offset in the event's area, variants)
+  unsigned short in_off[3], in_nv[3];
   unsigned long long vmap[3];        // 4 bits per output variant: the input's variant index
 };
-
-// number of cxd needed for the wavefunctions of E events
-template <class P>
-MF_HD constexpr int hp_wf_cxd(int E) { return P::HP_WFSIZE * E; }
-
-template <class P>
-MF_DEV cxd* hp_wf(cxd* wf, int E, int w, int e) {
-  const HpWf d = P::wf(w);
-  return wf + (size_t)d.off * E + (size_t)e * (2 + 4 * d.nv);
-}
 
 // phase 1: work item `it` in [0, NEXT*E*2)
 template <class P>
@@ -87,29 +113,27 @@ MF_DEV void hp_externals(int it, int E, const double* mom /*[E][NEXT][4]*/, cons
   if (x.type == HP_VXXXXX) vxxxxx(p, mass, hel, x.nsf, sqh, w);
   else if (x.type == HP_OXXXXX) oxxxxx(p, mass, hel, x.nsf, w);
   else ixxxxx(p, mass, hel, x.nsf, w);
-  cxd* o = hp_wf<P>(wf, E, x.out, e);
+  cxd* o = wf + e * P::HP_WFSIZE + P::wf(x.out).off;
   if (bit == 0) o[0] = w[0], o[1] = w[1];
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[2 + k * 2 + bit] = w[2 + k];
 }
 
-template <class P>
-MF_DEV void hp_load(const cxd* wf, int E, int w, int e, int v, cxd out[6]) {
-  const HpWf d = P::wf(w);
-  const cxd* s = wf + (size_t)d.off * E + (size_t)e * (2 + 4 * d.nv);
-  out[0] = s[0], out[1] = s[1];
+// the 6 slots of one helicity variant of a wavefunction block
+MF_DEV void hp_load(const cxd* blk, int nv, int v, cxd out[6]) {
+  out[0] = blk[0], out[1] = blk[1];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) out[2 + k] = s[2 + k * d.nv + v];
+  for (int k = 0; k < 4; ++k) out[2 + k] = blk[2 + k * nv + v];
 }
 
-// phase 2: work item (item index `idx`, event e, output variant v)
+// phase 2: work item (item index `idx`, output variant v) of the event whose area is wf_e
 template <class P>
-MF_DEV void hp_current(int idx, int e, int v, int E, const double* par, const cxd* coup_e, cxd* wf) {
+MF_DEV void hp_current(int idx, int v, const double* par, const cxd* coup_e, cxd* wf_e) {
   const HpItem it = P::item(idx);
   cxd a[6], b[6], c[6], r[6];
-  hp_load<P>(wf, E, it.in[0], e, (int)((it.vmap[0] >> (4 * v)) & 15ull), a);
-  hp_load<P>(wf, E, it.in[1], e, (int)((it.vmap[1] >> (4 * v)) & 15ull), b);
-  if (it.nin > 2) hp_load<P>(wf, E, it.in[2], e, (int)((it.vmap[2] >> (4 * v)) & 15ull), c);
+  hp_load(wf_e + it.in_off[0], it.in_nv[0], (int)((it.vmap[0] >> (4 * v)) & 15ull), a);
+  hp_load(wf_e + it.in_off[1], it.in_nv[1], (int)((it.vmap[1] >> (4 * v)) & 15ull), b);
+  if (it.nin > 2) hp_load(wf_e + it.in_off[2], it.in_nv[2], (int)((it.vmap[2] >> (4 * v)) & 15ull), c);
   cxd cp = coup_e[it.coup];
   if (it.coup_neg) cp = -cp;
   const double M = it.mass_idx < 0 ? 0.0 : par[it.mass_idx];
@@ -123,74 +147,117 @@ MF_DEV void hp_current(int idx, int e, int v, int E, const double* par, const cx
     case HP_VVVV3P0_1: VVVVP0_1<3>(a, b, c, cp, M, W, r); break;
     default: VVVVP0_1<4>(a, b, c, cp, M, W, r); break;
   }
-  const HpWf d = P::wf(it.out);
-  cxd* o = wf + (size_t)d.off * E + (size_t)e * (2 + 4 * d.nv);
+  cxd* o = wf_e + it.out_off;
+  const int nv = it.out_nv;
   if (v == 0) o[0] = r[0], o[1] = r[1];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) o[2 + k * d.nv + v] = r[2 + k];
+  for (int k = 0; k < 4; ++k) o[2 + k * nv + v] = r[2 + k];
 }
 
-// phase 3 for thread (event e, helicity bits h): loop over the amplitude table.  The loop body is a
-// handful of routines selected by a block-uniform switch, and the JAMP updates of amplitude `ai` are a
-// generated `switch (ai)` whose cases address the JAMP registers statically -- the whole phase is a few
-// tens of KB of instructions and stays in the instruction cache (a fully unrolled amplitude list is
-// ~300 KB for g g > t t~ g g and stalls on instruction fetch: profiles/r01_ttxgg_hp_v1.summary.txt).
-// vtab[w*NCOMB + h] is the helicity variant of wavefunction w that belongs to helicity combination h.
-template <class P>
-MF_DEV void hp_load_amp(const cxd* wf, const unsigned char* vtab, int E, int e, int h, int w, cxd out[6]) {
-  const HpWf d = P::wf(w);
-  const cxd* s = wf + (size_t)d.off * E + (size_t)e * (2 + 4 * d.nv);
-  const int v = vtab[w * P::NCOMB + h];
-  out[0] = s[0], out[1] = s[1];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) out[2 + k] = s[2 + k * d.nv + v];
-}
-
-template <class P>
-MF_DEV double hp_amplitudes(const cxd* wf, const unsigned char* vtab, int E, int e, int h, const cxd* coup) {
-  // short amplitude lists are emitted as straight-line code (it fits the instruction cache and has no
-  // loop overhead); long ones run the table-driven loop below
-  if (P::HP_UNROLL) return P::hp_amps_unrolled(wf, vtab, E, e, h, coup);
-  cxd J[P::NCOLOR];
-#pragma unroll
-  for (int j = 0; j < P::NCOLOR; ++j) J[j] = mk(0.0, 0.0);
-#pragma unroll 1
-  for (int ai = 0; ai < P::HP_NAMPS; ++ai) {
-    const HpAmp it = P::amp(ai);
-    cxd a[6], b[6], c[6], d[6];
-    hp_load_amp<P>(wf, vtab, E, e, h, it.in[0], a);
-    hp_load_amp<P>(wf, vtab, E, e, h, it.in[1], b);
-    hp_load_amp<P>(wf, vtab, E, e, h, it.in[2], c);
-    cxd cp = coup[it.coup];
-    if (it.coup_neg) cp = -cp;
-    cxd amp;
-    switch (it.type) {
-      case HP_FFV1_0: amp = FFV1_0(a, b, c, cp); break;
-      case HP_VVV1_0: amp = VVV1_0(a, b, c, cp); break;
-      default:
-        hp_load_amp<P>(wf, vtab, E, e, h, it.in[3], d);
-        if (it.type == HP_VVVV1_0) amp = VVVV_0<1>(a, b, c, d, cp);
-        else if (it.type == HP_VVVV3_0) amp = VVVV_0<3>(a, b, c, d, cp);
-        else amp = VVVV_0<4>(a, b, c, d, cp);
-        break;
-    }
-    P::jamp_accumulate(ai, amp, J);
-  }
-  return P::colour_sum(J);
-}
-
-// vtab: helicity variant of every wavefunction for every helicity combination (block-wide, once)
+// vtab[mask * NCOMB + h]: the helicity variant, of an object over the leg set `mask`, that belongs to
+// helicity combination h (= the bits of h at the positions in mask, packed).  Filled once per block.
 template <class P>
 MF_DEV void hp_fill_vtab(int idx, unsigned char* vtab) {
-  const int w = idx / P::NCOMB, h = idx - w * P::NCOMB;
-  const unsigned legs = P::wf(w).legs;
+  const int mask = idx / P::NCOMB, h = idx - mask * P::NCOMB;
   int out = 0, pos = 0;
   for (int b = 0; b < P::NEXT; ++b)
-    if (legs & (1u << b)) {
+    if (mask & (1 << b)) {
       out |= ((h >> b) & 1) << pos;
       ++pos;
     }
   vtab[idx] = (unsigned char)out;
+}
+
+// wavefunction w as helicity combination h sees it (used by the straight-line flavour)
+template <class P>
+MF_DEV void hp_load_amp(const cxd* wf_e, const unsigned char* vtab, int h, int w, cxd out[6]) {
+  const HpWf d = P::wf(w);
+  hp_load(wf_e + d.off, d.nv, vtab[d.legs * P::NCOMB + h], out);
+}
+
+// pair phase: work item (object pi, event e, variant v) -> Q[4] into the scratch area
+template <class P>
+MF_DEV void hp_pair(int pi, int v, const cxd* coup_e, const cxd* wf_e, cxd* scratch_e) {
+  const HpPair pr = P::pair(pi);
+  cxd a[6], b[6], c[6];
+  hp_load(wf_e + pr.in_off[0], pr.in_nv[0], (int)((pr.vmap[0] >> (4 * v)) & 15ull), a);
+  hp_load(wf_e + pr.in_off[1], pr.in_nv[1], (int)((pr.vmap[1] >> (4 * v)) & 15ull), b);
+  cxd cp = coup_e[pr.coup];
+  if (pr.coup_neg) cp = -cp;
+  const cxd f = mul_mi(cp);  // -i * COUP
+  cxd Q[4];
+  switch (pr.type) {
+    case HP_Q_ROW: {  // a = O (F2), b = G
+      cxd X[4];
+      slash_row(a, b, X);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) Q[k] = f * X[k];
+    } break;
+    case HP_Q_COL: {  // a = I (F1), b = G
+      cxd Y[4];
+      slash_col(a, b, Y);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) Q[k] = f * Y[k];
+    } break;
+    case HP_Q_CUR: {  // a = I (F1), b = O (F2): J^mu with FFV1_0 = -i COUP (J.V)
+      const cxd t0 = a[2] * b[4], t1 = a[3] * b[5], t2 = a[4] * b[2], t3 = a[5] * b[3];
+      const cxd u0 = a[2] * b[5], u1 = a[3] * b[4], u2 = a[4] * b[3], u3 = a[5] * b[2];
+      Q[0] = f * (t0 + t1 + t2 + t3);
+      Q[1] = f * (u0 + u1 - u2 - u3);            // -J1
+      Q[2] = f * mul_i(u0 - u1 - u2 + u3);       // -J2
+      Q[3] = f * (t0 - t1 - t2 + t3);            // -J3
+    } break;
+    case HP_Q_VVV: {  // a = V2, b = V3 of VVV1_0(V1,V2,V3); P1 = -(P2+P3)
+      const Mom P2 = mom_of(a, 1.0), P3 = mom_of(b, 1.0);
+      const Mom d12 = Mom{-2.0 * P2.e - P3.e, -2.0 * P2.x - P3.x, -2.0 * P2.y - P3.y, -2.0 * P2.z - P3.z};  // P1-P2
+      const Mom d31 = Mom{2.0 * P3.e + P2.e, 2.0 * P3.x + P2.x, 2.0 * P3.y + P2.y, 2.0 * P3.z + P2.z};      // P3-P1
+      const cxd s3 = pdot(d12, b), s2 = pdot(d31, a), s23 = vdot(a, b);
+      const double q[4] = {P2.e - P3.e, P2.x - P3.x, P2.y - P3.y, P2.z - P3.z};
+      const cxd K0 = a[2] * s3 + b[2] * s2 + q[0] * s23;
+      const cxd K1 = a[3] * s3 + b[3] * s2 + q[1] * s23;
+      const cxd K2 = a[4] * s3 + b[4] * s2 + q[2] * s23;
+      const cxd K3 = a[5] * s3 + b[5] * s2 + q[3] * s23;
+      Q[0] = f * K0, Q[1] = -(f * K1), Q[2] = -(f * K2), Q[3] = -(f * K3);
+    } break;
+    default: {  // HP_Q_VVVV: K = sum_t sign_t * in[vec_t] * (in[dotA_t] . in[dotB_t])
+      hp_load(wf_e + pr.in_off[2], pr.in_nv[2], (int)((pr.vmap[2] >> (4 * v)) & 15ull), c);
+      // the three Minkowski products once; each term picks one of them and one vector (block-uniform)
+      const cxd d01 = vdot(a, b), d02 = vdot(a, c), d12 = vdot(b, c);
+      cxd K[4] = {mk(0, 0), mk(0, 0), mk(0, 0), mk(0, 0)};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const unsigned char d = pr.term[t];
+        const int vi = (d >> 4) & 3, da = (d >> 2) & 3, db = d & 3;
+        const int key = da + db;  // {0,1} -> 1, {0,2} -> 2, {1,2} -> 3
+        cxd dot = key == 1 ? d01 : (key == 2 ? d02 : d12);
+        if (d & 0x40) dot = -dot;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const cxd V = vi == 0 ? a[2 + k] : (vi == 1 ? b[2 + k] : c[2 + k]);
+          K[k] += V * dot;
+        }
+      }
+      Q[0] = f * K[0], Q[1] = -(f * K[1]), Q[2] = -(f * K[2]), Q[3] = -(f * K[3]);
+    } break;
+  }
+  cxd* o = scratch_e + pr.off;
+  const int nv = pr.nv;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k * nv + v] = Q[k];
+}
+
+// amplitude ai for helicity h of the event whose areas are wf_e / scratch_e: four complex products
+template <class P>
+MF_DEV cxd hp_amp_dot(int ai, int h, const cxd* wf_e, const cxd* scratch_e, const unsigned char* vtab) {
+  const HpAmp am = P::amp(ai);
+  const int xnv = am.xnv, qnv = am.qnv;
+  const cxd* x = wf_e + am.x + vtab[am.xvt + h];
+  const cxd* q = scratch_e + am.q + vtab[am.qvt + h];
+  cxd amp = x[0] * q[0];
+  amp = fma_c(x[xnv], q[qnv], amp);
+  amp = fma_c(x[2 * xnv], q[2 * qnv], amp);
+  amp = fma_c(x[3 * xnv], q[3 * qnv], amp);
+  return amp;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -200,8 +267,8 @@ MF_DEV void hp_fill_vtab(int idx, unsigned char* vtab) {
 template <class P>
 __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events */, const double* mom,
                                                    const cxd* coup, const double* par, double sqh, cxd* wf,
-                                                   const unsigned char* vtab, double* red /* [T/32] */,
-                                                   int only_h) {
+                                                   cxd* scratch, const unsigned char* vtab,
+                                                   double* red /* [T/32] */, int only_h) {
   constexpr int E = P::HP_E, NH = P::NCOMB, T = E * NH;
   const int tid = threadIdx.x;
   for (int it = tid; it < P::NEXT * E * 2; it += T) hp_externals<P>(it, E, mom, par, sqh, wf);
@@ -216,12 +283,44 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
       const int ci = w / (E * nv);
       const int r = w - ci * (E * nv);
       const int e = r / nv, v = r - e * nv;
-      hp_current<P>(begin + ci, e, v, E, par, coup + e * P::NCOUP, wf);
+      hp_current<P>(begin + ci, v, par, coup + e * P::NCOUP, wf + e * P::HP_WFSIZE);
     }
     __syncthreads();
   }
   const int e = tid / NH, h = tid - e * NH;
-  double me = hp_amplitudes<P>(wf, vtab, E, e, h, coup + e * P::NCOUP);
+  double me;
+  if (P::HP_UNROLL) {
+    // short amplitude lists: straight-line code, whole vertices per helicity combination
+    me = P::hp_amps_unrolled(wf + e * P::HP_WFSIZE, vtab, h, coup + e * P::NCOUP);
+  } else {
+    const cxd* wf_e = wf + e * P::HP_WFSIZE;
+    const cxd* scratch_e = scratch + e * P::HP_SCRATCH;
+    cxd J[P::NCOLOR];
+#pragma unroll
+    for (int j = 0; j < P::NCOLOR; ++j) J[j] = mk(0.0, 0.0);
+#pragma unroll 1
+    for (int bi = 0; bi < P::HP_NBATCH; ++bi) {
+      const HpBatch bt = P::batch(bi);
+      const int total = (bt.item_end - bt.item_begin) * E;
+#pragma unroll 1
+      for (int w = tid; w < total; w += T) {
+        const int ii = w / E, ee = w - ii * E;
+        const HpPairItem pit = P::pair_item(bt.item_begin + ii);
+        hp_pair<P>(pit.pair, pit.v, coup + ee * P::NCOUP, wf + ee * P::HP_WFSIZE, scratch + ee * P::HP_SCRATCH);
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int g = bt.group_begin; g < bt.group_end; ++g) {
+        // HP_GROUP independent dot products in flight, then their JAMP updates (one block-uniform switch)
+        cxd amp[HP_GROUP];
+#pragma unroll
+        for (int k = 0; k < HP_GROUP; ++k) amp[k] = hp_amp_dot<P>(g * HP_GROUP + k, h, wf_e, scratch_e, vtab);
+        P::jamp_accumulate(g, amp, J);
+      }
+      __syncthreads();  // the next batch overwrites the scratch area
+    }
+    me = P::colour_sum(J);
+  }
   if (only_h >= 0) me = (h == only_h) ? me : 0.0;
   if (e >= nev) me = 0.0;
   // sum over helicities of one event
@@ -247,8 +346,8 @@ struct HpSmatrixSmem {
   double mom[E * P::NEXT * 4];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
   double red[T / 32 + 1];
-  unsigned char vtab[P::HP_NWF * P::NCOMB];
-  // followed by cxd wf[HP_WFSIZE * E]
+  unsigned char vtab[(1 << P::NEXT) * P::NCOMB];
+  // followed by cxd wf[HP_WFSIZE * E], cxd scratch[HP_SCRATCH * E]
 };
 
 template <class P>
@@ -258,7 +357,8 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
   HpSmatrixSmem<P>& s = *reinterpret_cast<HpSmatrixSmem<P>*>(smem_raw);
   cxd* wf = reinterpret_cast<cxd*>(smem_raw + ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16);
   const int tid = threadIdx.x;
-  for (int i = tid; i < P::HP_NWF * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
+  cxd* scratch = wf + (size_t)P::HP_WFSIZE * E;
+  for (int i = tid; i < (1 << P::NEXT) * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
   int only_h = -1;
   if (a.only_comb >= 0) {
     only_h = 0;
@@ -294,7 +394,7 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
         }
       }
       __syncthreads();
-      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, wf, s.vtab, s.red, only_h);
+      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, wf, scratch, s.vtab, s.red, only_h);
       const int e = tid / NH, h = tid - e * NH;
       if (h == 0 && e < nev) a.out[ev0 + e] = me;
       __syncthreads();
@@ -304,7 +404,9 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
 
 // ------------------------------------------------------------------------------------------------
 template <class P>
-size_t hp_smatrix_smem() { return ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16 + sizeof(cxd) * P::HP_WFSIZE * P::HP_E; }
+size_t hp_smatrix_smem() {
+  return ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16 + sizeof(cxd) * (P::HP_WFSIZE + P::HP_SCRATCH) * P::HP_E;
+}
 
 template <class P>
 int launch_smatrix_hp(const double* d_p, int layout, long long nevt, const double* par, const double* d_coup,
@@ -398,13 +500,15 @@ int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
 // kernel flavour: 0 = the process's default (P::USE_HP), 1 = one event per thread, 2 = helicity-parallel
 static int g_variant = 0;
 template <class P>
-bool use_hp() { return g_variant == 0 ? P::USE_HP : g_variant == 2; }
+bool use_hp() { return !P::HAS_THREAD || (g_variant == 0 ? P::USE_HP : g_variant == 2); }
 
 template <class P>
 int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double* par, const double* d_coup,
                      long long cs, double sqh, double* d_out, int only_comb, cudaStream_t st) {
-  return use_hp<P>() ? launch_smatrix_hp<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, only_comb, st)
-                     : launch_smatrix<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, only_comb, st);
+  if constexpr (P::HAS_THREAD) {
+    if (!use_hp<P>()) return launch_smatrix<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, only_comb, st);
+  }
+  return launch_smatrix_hp<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, only_comb, st);
 }
 
 }  // namespace mf
@@ -434,6 +538,8 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
   }                                                                                                            \
   int mfp_set_variant(int v) {                                                                                 \
     if (v < 0 || v > 2) return mf::fail_msg("mfp_set_variant: 0 default, 1 thread-per-event, 2 helicity-parallel"); \
+    if (v == 1 && !P::HAS_THREAD)                                                                              \
+      return mf::fail_msg("mfp_set_variant: the one-event-per-thread flavour is not compiled for this process"); \
     mf::g_variant = v;                                                                                         \
     return 0;                                                                                                  \
   }                                                                                                            \
@@ -452,15 +558,20 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
     return mf::smatrix_host<P>(mf::dispatch_smatrix<P>, h_p, layout, nevt, par, h_coup, cs, sqh, h_out);       \
   }                                                                                                            \
   int mfp_integrand_blocks(void) {                                                                             \
-    return mf::use_hp<P>() ? mf::integrand_blocks_hp<P>() : mf::integrand_blocks<P>();                         \
+    if constexpr (P::HAS_THREAD) {                                                                             \
+      if (!mf::use_hp<P>()) return mf::integrand_blocks<P>();                                                  \
+    }                                                                                                          \
+    return mf::integrand_blocks_hp<P>();                                                                       \
   }                                                                                                            \
   int64_t mfp_integrand_workspace(int64_t nevents) {                                                           \
     return mf::use_hp<P>() ? mf::integrand_workspace_hp<P>(nevents) : 0;                                       \
   }                                                                                                            \
   int mfp_integrand(const mfp_integrand_args* a, void* st) {                                                   \
     if (!a) return mf::fail_msg("mfp_integrand: null args");                                                   \
-    return mf::use_hp<P>() ? mf::launch_integrand_hp<P>(a, (cudaStream_t)st)                                   \
-                           : mf::launch_integrand<P>(a, (cudaStream_t)st);                                     \
+    if constexpr (P::HAS_THREAD) {                                                                             \
+      if (!mf::use_hp<P>()) return mf::launch_integrand<P>(a, (cudaStream_t)st);                               \
+    }                                                                                                          \
+    return mf::launch_integrand_hp<P>(a, (cudaStream_t)st);                                                    \
   }                                                                                                            \
   const char* mfp_last_error(void) { return mf::g_err; }                                                       \
   }

@@ -32,8 +32,9 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
   std::vector<cxd> wf((size_t)Proc::HP_WFSIZE * E);
   std::vector<double> mom(E * Proc::NEXT * 4);
   std::vector<cxd> cp(E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
-  std::vector<unsigned char> vtab(Proc::HP_NWF * NH);
-  for (int i = 0; i < Proc::HP_NWF * NH; ++i) mf::hp_fill_vtab<Proc>(i, vtab.data());
+  std::vector<unsigned char> vtab((1 << Proc::NEXT) * NH);
+  for (int i = 0; i < (1 << Proc::NEXT) * NH; ++i) mf::hp_fill_vtab<Proc>(i, vtab.data());
+  std::vector<cxd> scratch((size_t)(Proc::HP_SCRATCH > 0 ? Proc::HP_SCRATCH : 1) * E);
   int only_h = -1;
   if (only_comb >= 0) {
     only_h = 0;
@@ -54,15 +55,45 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
       const int begin = Proc::level_begin(L), cnt = Proc::level_begin(L + 1) - begin, nv = 1 << L;
       for (int w = 0; w < cnt * E * nv; ++w) {
         const int ci = w / (E * nv), r = w - ci * (E * nv), e = r / nv, v = r - e * nv;
-        mf::hp_current<Proc>(begin + ci, e, v, E, par, cp.data() + e * Proc::NCOUP, wf.data());
+        mf::hp_current<Proc>(begin + ci, v, par, cp.data() + e * Proc::NCOUP, wf.data() + e * Proc::HP_WFSIZE);
+      }
+    }
+    std::vector<double> me_h((size_t)E * NH, 0.0);
+    if (Proc::HP_UNROLL) {
+      for (int e = 0; e < nev; ++e)
+        for (int h = 0; h < NH; ++h)
+          me_h[e * NH + h] = Proc::hp_amps_unrolled(wf.data() + e * Proc::HP_WFSIZE, vtab.data(), h, cp.data() + e * Proc::NCOUP);
+    } else {
+      std::vector<cxd> J((size_t)T * Proc::NCOLOR, mk(0.0, 0.0));
+      for (int bi = 0; bi < Proc::HP_NBATCH; ++bi) {
+        const mf::HpBatch bt = Proc::batch(bi);
+        for (int w = 0; w < (bt.item_end - bt.item_begin) * E; ++w) {
+          const int ii = w / E, ee = w - ii * E;
+          const mf::HpPairItem pit = Proc::pair_item(bt.item_begin + ii);
+          mf::hp_pair<Proc>(pit.pair, pit.v, cp.data() + ee * Proc::NCOUP, wf.data() + ee * Proc::HP_WFSIZE,
+                            scratch.data() + ee * (Proc::HP_SCRATCH > 0 ? Proc::HP_SCRATCH : 1));
+        }
+        for (int t = 0; t < T; ++t) {
+          const int e = t / NH, h = t - e * NH;
+          cxd(&Jt)[Proc::NCOLOR] = *reinterpret_cast<cxd(*)[Proc::NCOLOR]>(&J[(size_t)t * Proc::NCOLOR]);
+          for (int g = bt.group_begin; g < bt.group_end; ++g) {
+            cxd amp[mf::HP_GROUP];
+            for (int k = 0; k < mf::HP_GROUP; ++k)
+              amp[k] = mf::hp_amp_dot<Proc>(g * mf::HP_GROUP + k, h, wf.data() + e * Proc::HP_WFSIZE,
+                                            scratch.data() + e * (Proc::HP_SCRATCH > 0 ? Proc::HP_SCRATCH : 1), vtab.data());
+            Proc::jamp_accumulate(g, amp, Jt);
+          }
+        }
+      }
+      for (int t = 0; t < T; ++t) {
+        cxd(&Jt)[Proc::NCOLOR] = *reinterpret_cast<cxd(*)[Proc::NCOLOR]>(&J[(size_t)t * Proc::NCOLOR]);
+        me_h[t] = Proc::colour_sum(Jt);
       }
     }
     for (int e = 0; e < nev; ++e) {
       double acc = 0.0;
-      for (int h = 0; h < NH; ++h) {
-        const double me = mf::hp_amplitudes<Proc>(wf.data(), vtab.data(), E, e, h, cp.data() + e * Proc::NCOUP);
-        if (only_h < 0 || h == only_h) acc += me;
-      }
+      for (int h = 0; h < NH; ++h)
+        if (only_h < 0 || h == only_h) acc += me_h[e * NH + h];
       out[ev0 + e] = only_h >= 0 ? acc : acc / Proc::DENOM;
     }
   }
