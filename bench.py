@@ -309,11 +309,17 @@ def main():
                         "sample": f"{n} generated events of the same workload ({nme} reach the matrix element), "
                                   f"{dt:.1f} s wall; oracle/ numpy restatement, one process per core"}
 
-    peaks = {}
+    peaks, executed = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    try:  # executed FP64 instruction counts of the dominant kernel, from the committed ncu captures
+        executed = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json"))).get(proc, {})
+    except OSError:
+        pass
+    exec_flops = executed.get("flops_per_me_event")
+    exec_tflops = exec_flops * me_per_launch / (kernel_ms * 1e-3) / 1e12 if exec_flops else None
     final, err, chi2 = mfv.combine_iterations(results)
     bytes_per_event = 0.0  # the fused kernel reads no per-event input from HBM
     line = {
@@ -337,6 +343,13 @@ def main():
                            f"{fp64_burst:.1f} TFLOP/s; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2; "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "hbm_gbs_measured": peaks.get("hbm_gbs"), "hbm_bytes_per_event": bytes_per_event,
+            "note": "achieved = F_alg (the reference's operation count over all helicities, SURVEY 8d) x events / time; "
+                    "the kernel executes fewer operations (wavefunctions and vertices are evaluated once per helicity "
+                    "variant of their own legs), so this fraction can exceed 1; the executed figures below are the "
+                    "hardware-side view",
+            "executed_flops_per_event": exec_flops, "executed_tflops": exec_tflops,
+            "executed_frac": exec_tflops / fp64_sustained if exec_tflops else None,
+            "executed_source": executed.get("source"),
         },
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
