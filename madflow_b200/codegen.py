@@ -172,7 +172,7 @@ def emit_matrix_body(ir):
 # helicity-parallel variant (csrc/process_kernels_hp.cuh)
 THREAD_MAX_CALLS = 64     # call lists up to this length also get the one-event-per-thread kernels
 HP_UNROLL_MAX_AMPS = 32   # amplitude lists up to this length are emitted as straight-line code
-HP_SCRATCH_CXD = 1024     # shared-memory scratch for pair objects, complex numbers per event (16 KB)
+HP_SCRATCH_CXD = 512      # shared-memory scratch for the pair objects of a batch, complex numbers per event (8 KB)
 HP_TYPES = {"vxxxxx": 0, "oxxxxx": 1, "ixxxxx": 2, "FFV1_1": 3, "FFV1_2": 4, "FFV1P0_3": 5, "VVV1P0_1": 6,
             "VVVV1P0_1": 7, "VVVV3P0_1": 8, "VVVV4P0_1": 9}
 
@@ -219,9 +219,22 @@ def _vmap(out_legs, in_legs):
     return word
 
 
-def hp_group():
-    """Amplitudes per unrolled group of the amplitude phase (csrc: MF_HP_GROUP)."""
-    return int(os.environ.get("MADFLOW_B200_HP_GROUP", 12))
+def hp_batch_amps():
+    """Rows of the amplitude buffer = amplitudes per batch of the tensor-core amplitude phase."""
+    return int(os.environ.get("MADFLOW_B200_HP_NB", 16))
+
+
+def hp_scratch():
+    """Shared-memory scratch for the pair objects of one batch, complex numbers per event."""
+    return int(os.environ.get("MADFLOW_B200_HP_SCRATCH", HP_SCRATCH_CXD))
+
+
+def hp_colour_groups(ir):
+    """Threads per (event, helicity combination): the JAMPs of one helicity are spread over this many
+    threads (colour groups) to keep them in registers at a higher occupancy."""
+    if os.environ.get("MADFLOW_B200_HP_NCG"):
+        return int(os.environ["MADFLOW_B200_HP_NCG"])
+    return 1
 
 
 def hp_events_per_block(ir):
@@ -241,8 +254,9 @@ def emit_hp(ir):
     def pidx(name):
         return -1 if name == "ZERO" else ir["params"].index(name)
 
-    def both(ctype, name, count, body):
-        return (f"__device__ __constant__ {ctype} d_{name}[{count}] = {{{body}}};\n"
+    def both(ctype, name, count, body, const=True):
+        space = "__device__ __constant__" if const else "__device__ const"
+        return (f"{space} {ctype} d_{name}[{count}] = {{{body}}};\n"
                 f"static const {ctype} h_{name}[{count}] = {{{body}}};")
 
     L = []
@@ -312,75 +326,97 @@ def emit_hp(ir):
             pair_index[key] = len(pairs)
             pairs.append(dict(type=ptype, rest=rest, term=term, coup=coup, neg=neg, legs=legs, nv=1 << len(legs)))
         amp_rows.append(dict(am=am, x=ins[jx], pair=pair_index[key]))
-    # batches: pair objects in order of first use, packed into the scratch area
-    scratch = int(os.environ.get("MADFLOW_B200_HP_SCRATCH", HP_SCRATCH_CXD))
-    order = sorted(range(len(amp_rows)), key=lambda k: amp_rows[k]["pair"])
+    # batches: pair objects in order of first use, packed into the scratch area; a batch closes at a
+    # pair boundary when the scratch area or the amplitude buffer (HP_NB rows) would overflow
+    scratch = hp_scratch()
+    NB = hp_batch_amps()
+    NCG = hp_colour_groups(ir)
+    by_pair = {}
+    for k, r in enumerate(amp_rows):
+        by_pair.setdefault(r["pair"], []).append(k)
+    PT = {"ROW": 0, "COL": 1, "CUR": 2, "VVV": 3, "VVVV": 4}
     batches, cur_pairs, cur_amps, fill = [], [], [], 0
-    for k in order:
-        pi = amp_rows[k]["pair"]
-        if pi not in cur_pairs:
-            need = 4 * pairs[pi]["nv"]
-            assert need <= scratch
-            if fill + need > scratch:
-                batches.append((cur_pairs, cur_amps))
-                cur_pairs, cur_amps, fill = [], [], 0
-            pairs[pi]["off"] = fill
-            fill += need
-            cur_pairs.append(pi)
-        cur_amps.append(k)
+    # pair objects of one kind together: the warps of a batch then run the same routine for about the same time
+    for pi in sorted(by_pair, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
+        need = 4 * pairs[pi]["nv"]
+        assert need <= scratch and len(by_pair[pi]) <= NB
+        if fill + need > scratch or len(cur_amps) + len(by_pair[pi]) > NB:
+            batches.append((cur_pairs, cur_amps))
+            cur_pairs, cur_amps, fill = [], [], 0
+        pairs[pi]["off"] = fill
+        fill += need
+        cur_pairs.append(pi)
+        cur_amps += by_pair[pi]
     if cur_amps:
         batches.append((cur_pairs, cur_amps))
-    PT = {"ROW": 0, "COL": 1, "CUR": 2, "VVV": 3, "VVVV": 4}
     prow = []
     for pr in pairs:
         rest = list(pr["rest"]) + [0] * (3 - len(pr["rest"]))
         vm = [_vmap(pr["legs"], wfs[w]["legs"]) for w in pr["rest"]] + [0] * (3 - len(pr["rest"]))
-        mask = sum(1 << l for l in pr["legs"])
         ioff = [wfs[w]["off"] for w in rest]
         inv = [wfs[w]["nv"] for w in rest]
         prow.append(f"{{{PT[pr['type']]}, {len(pr['rest'])}, {pr['coup']}, {pr['neg']}, {{{pr['term'][0]}, {pr['term'][1]}}}, "
                     f"{pr['nv']}, {pr.get('off', 0)}, {{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
                     f"{{{vm[0]}ull, {vm[1]}ull, {vm[2]}ull}}}}")
-    E = hp_events_per_block(ir)
     NH = ir["ncomb"]
-    GROUP = hp_group()
-    irow, arow, brow, groups = [], [], [], []
 
-    def amp_entry(k):
-        r = amp_rows[k]
-        xw, pr = wfs[r["x"]], pairs[r["pair"]]
-        qmask = sum(1 << l for l in pr["legs"])
-        return (f"{{{xw['off'] + 2}, {pr['off']}, {xw['nv']}, {pr['nv']}, {xw['mask'] * NH}, {qmask * NH}}}")
+    def spread(legs, v):
+        """helicity-combination bits of variant v of an object over `legs` (ascending)"""
+        return sum(((v >> q) & 1) << l for q, l in enumerate(legs))
 
-    for cur_pairs, cur_amps in batches:
-        ib, gb = len(irow), len(groups)
+    # tensor-core tiles: amplitude(variant of Q, variant of x) = sum_k Q_k x_k is an (nvq x 4)(4 x nvx)
+    # complex product; one work item = 8 variants of Q (rows) x 8 variants of x (columns)
+    irow, trow, brow = [], [], []
+    ncolor = len(ir["jamp"])
+    NJ = -(-ncolor // NCG)
+    jamp_cases = [[] for _ in range(NCG)]
+    for bi, (cur_pairs, cur_amps) in enumerate(batches):
+        ib, tb = len(irow), len(trow)
         for pi in sorted(cur_pairs, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
             for v in range(pairs[pi]["nv"]):
                 irow.append(f"{{{pi}, {v}}}")
-        for g0 in range(0, len(cur_amps), GROUP):
-            chunk = cur_amps[g0:g0 + GROUP]
-            groups.append(chunk)
-            for k in chunk:
-                arow.append(amp_entry(k))
-            for _ in range(GROUP - len(chunk)):   # pad with a repeat; its result is not accumulated
-                arow.append(amp_entry(chunk[0]))
-        brow.append(f"{{{ib}, {len(irow)}, {gb}, {len(groups)}}}")
+        upd = [[] for _ in range(NCG)]
+        for slot, k in enumerate(cur_amps):
+            r = amp_rows[k]
+            xw, pr = wfs[r["x"]], pairs[r["pair"]]
+            assert not set(xw["legs"]) & set(pr["legs"]) and len(xw["legs"]) + len(pr["legs"]) == n
+            for q0 in range(0, pr["nv"], 8):
+                for x0 in range(0, xw["nv"], 8):
+                    qv, xv = min(8, pr["nv"] - q0), min(8, xw["nv"] - x0)
+                    rowh = [spread(pr["legs"], q0 + i) if i < qv else 0 for i in range(8)]
+                    colh = [spread(xw["legs"], x0 + i) if i < xv else 0 for i in range(8)]
+                    trow.append(f"{{{pr['off']}, {xw['off'] + 2}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
+                                f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
+            am = r["am"]
+            per_cg = [[] for _ in range(NCG)]
+            for j, re, im in by_amp[am["call"]["amp"]]:
+                cg, jl = divmod(j, NJ)
+                per_cg[cg].append(_jamp_update(jl, re, im, "a").replace(f"J{jl} ", f"J[{jl}] "))
+            for cg in range(NCG):
+                if per_cg[cg]:
+                    upd[cg].append(f"{{ const cxd a = ab[{slot * NH}]; " + " ".join(per_cg[cg]) + " }")
+        for cg in range(NCG):
+            jamp_cases[cg].append(f"      case {bi}: {{ " + "\n        ".join(upd[cg]) + " } break;")
+        brow.append(f"{{{ib}, {len(irow)}, {tb}, {len(trow)}}}")
     tables += "\n" + both("mf::HpPair", "pairs", max(len(prow), 1), ",\n  ".join(prow) if prow else "{0}")
     tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0}")
-    tables += "\n" + both("mf::HpAmp", "amps", max(len(arow), 1), ", ".join(arow) if arow else "{0, 0, 0, 0, 0, 0}")
+    tables += "\n" + both("mf::HpTile", "tiles", max(len(trow), 1), ",\n  ".join(trow) if trow else "{0}", const=len(trow) * 32 <= 24576)
     tables += "\n" + both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}")
 
-    A = ["    switch (g) {"]
-    for gi, chunk in enumerate(groups):
-        upd = []
-        for slot, k in enumerate(chunk):
-            am = amp_rows[k]["am"]
-            for j, re, im in by_amp[am["call"]["amp"]]:
-                upd.append(_jamp_update(j, re, im, f"amp[{slot}]").replace(f"J{j} ", f"J[{j}] "))
-        A.append(f"      case {gi}: " + " ".join(upd) + " break;")
-    A.append("      default: break;")
+    A = ["    switch (cg) {"]
+    for cg in range(NCG):
+        A.append(f"    case {cg}:")
+        A.append("      switch (b) {")
+        A += jamp_cases[cg]
+        A.append("      default: break;")
+        A.append("      }")
+        A.append("      break;")
+    A.append("    default: break;")
     A.append("    }")
-    C = _emit_colour(ir, J=lambda i: f"J[{i}]")
+    if NCG == 1:
+        C = _emit_colour(ir, J=lambda i: f"J[{i}]")
+    else:
+        C = _emit_colour_groups(ir, NCG, NJ, NH)
     # straight-line flavour of the same phase for short amplitude lists
     U = ["    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(len(ir["jamp"]))) + ";",
          "    cxd a[6], b[6], c[6], d[6];"]
@@ -398,10 +434,49 @@ def emit_hp(ir):
             U.append("    }")
         U.append(_emit_colour(ir))
     else:
-        U.append("    return 0.0;  // not used: the amplitude list of this process runs as a loop")
+        U.append("    return 0.0;  // not used: the amplitudes of this process run on the tensor cores")
+    unroll = len(used) <= HP_UNROLL_MAX_AMPS
     return tables, "\n".join(A), C, "\n".join(U), dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items),
-                                         namps=len(used), unroll=len(used) <= HP_UNROLL_MAX_AMPS,
-                                         nbatch=len(batches), npairs=len(pairs), nitems_pair=len(irow))
+                                         namps=len(used), unroll=unroll, nbatch=len(batches), npairs=len(pairs),
+                                         nitems_pair=len(irow), ntiles=len(trow), ncg=1 if unroll else NCG,
+                                         nb=max(len(b[1]) for b in batches) if batches else 1,
+                                         scratch=max(max((pairs[pi]["off"] + 4 * pairs[pi]["nv"] for pi in b[0]), default=0) for b in batches) if batches else 0)
+
+
+def _emit_colour_groups(ir, ncg, nj, nh):
+    """Colour quadratic form with the JAMPs of one helicity spread over `ncg` threads (colour group g owns
+    colours [g*nj, (g+1)*nj)): every unordered pair (a, b) is evaluated by exactly one thread -- the owner of
+    a when both are in one group, else alternating between the two owners -- which reads the other
+    group's JAMP from shared memory (jb[c * NH])."""
+    ncolor = len(ir["jamp"])
+    cf, den = ir["color_num"], ir["color_denom"]
+    assert len(set(den)) == 1 and all(cf[i][j] == cf[j][i] for i in range(ncolor) for j in range(ncolor)), \
+        "colour groups need a symmetric colour matrix with one denominator"
+    L = ["    double me = 0.0;", "    switch (cg) {"]
+    for g in range(ncg):
+        L.append(f"    case {g}: {{")
+        own = range(g * nj, min((g + 1) * nj, ncolor))
+        for a in own:
+            terms = []
+            for b in range(ncolor):
+                if b == a or cf[a][b] == 0:
+                    continue
+                gb = b // nj
+                if gb == g:
+                    if b > a:
+                        terms.append((b, True))
+                elif (a + b) % 2 == (0 if g < gb else 1):
+                    terms.append((b, False))
+            L.append(f"      {{ double tr = {float(cf[a][a])!r} * J[{a - g * nj}].re, ti = {float(cf[a][a])!r} * J[{a - g * nj}].im;")
+            for b, mine in terms:
+                src = f"J[{b - g * nj}]" if mine else f"jb[{b * nh}]"
+                L.append(f"        {{ const cxd o = {src}; tr += {float(2 * cf[a][b])!r} * o.re; ti += {float(2 * cf[a][b])!r} * o.im; }}")
+            L.append(f"        me += J[{a - g * nj}].re * tr + J[{a - g * nj}].im * ti; }}")
+        L.append("    } break;")
+    L.append("    default: break;")
+    L.append("    }")
+    L.append(f"    return me / {float(den[0])!r};")
+    return "\n".join(L)
 
 
 def use_hp_default(ir):
@@ -442,8 +517,10 @@ def emit_process_source(ir, block=None, minblocks=None):
 
     hp_tables, hp_jamp, hp_colour, hp_unrolled, hp = emit_hp(ir)
     hp_unroll = 'true' if hp['unroll'] else 'false'
-    hp_group_n = hp_group()
-    hp_scratch = 0 if hp['unroll'] else int(os.environ.get("MADFLOW_B200_HP_SCRATCH", HP_SCRATCH_CXD))
+    hp_scratch_n = 0 if hp['unroll'] else hp['scratch']
+    hp_nb = 0 if hp['unroll'] else hp['nb']
+    hp_ncg = hp['ncg']
+    hp_nj = -(-ncolor // hp_ncg)
     hp_e = hp_events_per_block(ir)
     use_hp = "true" if use_hp_default(ir) else "false"
     has_thread = "true" if (len(ir["calls"]) <= THREAD_MAX_CALLS or os.environ.get("MADFLOW_B200_BUILD_THREAD") == "1") else "false"
@@ -452,7 +529,6 @@ def emit_process_source(ir, block=None, minblocks=None):
     cnames = ", ".join(f'"{c}"' for c in ir["couplings"]) or '""'
     src = f"""// GENERATED by madflow_b200.codegen -- do not edit.  Process: {ir.get('process', ir['name'])}
 // One fused FP64 kernel per process: HELAS wavefunctions -> ALOHA vertices -> JAMP -> colour matrix.
-#define MF_HP_GROUP {hp_group_n}
 #include "process_kernels_hp.cuh"
 
 namespace {{
@@ -497,20 +573,31 @@ struct Proc {{
   static constexpr bool HAS_THREAD = {has_thread};
   static constexpr int HP_E = {hp_e}, HP_MINBLOCKS = {hp_minblocks}, HP_WFSIZE = {hp_wfsize}, HP_MAXLEVEL = {hp_maxlevel};
   static constexpr int HP_NWF = {hp_nwf}, HP_NITEMS = {hp_nitems}, HP_NAMPS = {hp['namps']};
-  static constexpr int HP_NBATCH = {hp['nbatch']}, HP_NPAIRS = {hp['npairs']}, HP_SCRATCH = {hp_scratch};
+  static constexpr int HP_NBATCH = {hp['nbatch']}, HP_NPAIRS = {hp['npairs']}, HP_SCRATCH = {hp_scratch_n};
+  // tensor-core amplitude phase: HP_NB rows of NCOMB amplitudes per event and batch; the JAMPs of one
+  // helicity combination are spread over HP_NCG threads, HP_NJ colours each
+  static constexpr int HP_NB = {hp_nb}, HP_NCG = {hp_ncg}, HP_NJ = {hp_nj}, HP_NTILES = {hp['ntiles']};
+  static constexpr int HP_THREADS = HP_E * NCOMB * HP_NCG;                 // threads per block
+  static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 4)) // hp_e)};  // tile descriptors per warp and trip
+  // shared-memory cxd per event: wavefunctions | pair objects | amplitude buffer (the last two double as the
+  // JAMP exchange area of the colour groups)
+  static constexpr int HP_XCHG = HP_NCG > 1 ? NCOLOR * NCOMB : 0;
+  static constexpr int HP_EVSTRIDE = HP_WFSIZE + (HP_SCRATCH + HP_NB * NCOMB > HP_XCHG ? HP_SCRATCH + HP_NB * NCOMB : HP_XCHG);
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
   MF_DEV static mf::HpItem item(int i) {{ return MF_TAB(items)[i]; }}
   MF_DEV static int level_begin(int L) {{ return MF_TAB(level_begin)[L]; }}
-  MF_DEV static mf::HpAmp amp(int i) {{ return MF_TAB(amps)[i]; }}
+  MF_DEV static const mf::HpTile* tile(int i) {{ return &MF_TAB(tiles)[i]; }}
   MF_DEV static mf::HpPair pair(int i) {{ return MF_TAB(pairs)[i]; }}
   MF_DEV static mf::HpPairItem pair_item(int i) {{ return MF_TAB(pair_items)[i]; }}
   MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
-  // JAMP updates of amplitude group `g` (block-uniform switch, JAMP registers addressed statically)
-  MF_DEV static void jamp_accumulate(int g, const cxd (&amp)[mf::HP_GROUP], cxd (&J)[NCOLOR]) {{
+  // JAMP updates of batch `b` for colour group `cg` (warp-uniform switches): ab = the event's amplitude
+  // buffer at this thread's helicity combination, row r at ab[r * NCOMB]; JAMP registers addressed statically
+  MF_DEV static void jamp_batch(int b, int cg, const cxd* ab, cxd (&J)[HP_NJ]) {{
 {hp_jamp}
   }}
-  MF_DEV static double colour_sum(const cxd (&J)[NCOLOR]) {{
+  // colour quadratic form; with HP_NCG > 1 the other groups' JAMPs are read from jb[colour * NCOMB]
+  MF_DEV static double colour_sum(int cg, const cxd (&J)[HP_NJ], const cxd* jb) {{
 {hp_colour}
   }}
   static constexpr bool HP_UNROLL = {hp_unroll};

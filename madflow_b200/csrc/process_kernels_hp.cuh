@@ -11,18 +11,26 @@
 //   phase 2   off-shell currents level by level (level = number of legs); the work items of a
 //             level are (current, event, helicity variant), spread over all threads of the block;
 //             table driven (HpItem), one copy of each ALOHA routine in the instruction stream
-//   phase 3   amplitudes + JAMP sums: thread (e, h) loops over the amplitude table, reading each
-//             input current's variant for ITS helicity h (a warp's 32 helicities touch <= 8
-//             variants of a current: one shared-memory wavefront per load); the JAMP updates are
-//             a generated switch over the amplitude index, so the JAMPs stay in registers
-//   phase 4   colour contraction per thread, then the sum over helicities is a warp-shuffle +
-//             shared-memory reduction per event.
+//   phase 3   amplitudes, batch by batch: (a) the pair objects of the batch (see HpPair), (b) the
+//             amplitudes of ALL helicity combinations on the FP64 tensor cores: amplitude[vq][vx] =
+//             sum_k Q_k[vq] x_k[vx] is a (variants of Q x 4)(4 x variants of x) complex matrix
+//             product, evaluated in 8x8 tiles by four mma.sync.m8n8k4.f64 per tile and written to
+//             the amplitude buffer [row][helicity combination], (c) the JAMP sums: thread
+//             (e, h, colour group) adds the buffer rows into its JAMP registers through generated
+//             code (static offsets, coefficients +-1, +-i folded into the adds)
+//   phase 4   colour contraction per thread (colour groups exchange JAMPs through shared memory),
+//             then the sum over helicities and colour groups is a warp-shuffle + shared-memory
+//             reduction per event.
 //
-// Shared memory: every event of the block owns HP_WFSIZE cxd (= 16 bytes) of wavefunctions and
-// HP_SCRATCH cxd of pair objects.  Wavefunction w lives at offset P::wf(w).off of its event's area:
+// Shared memory: every event of the block owns HP_EVSTRIDE cxd (= 16 bytes): HP_WFSIZE of
+// wavefunctions, HP_SCRATCH of pair objects, HP_NB * NCOMB of amplitudes.  Wavefunction w lives at
+// offset P::wf(w).off of its event's area:
 //   [ 0..1 ]              momentum slots w0, w1  (helicity independent)
-//   [ 2 + k*nv + v ]      component k = 0..3 (HELAS slots 2..5), helicity variant v < nv = 2^|S|
-// Variant bits follow the ascending leg order of S; bit = 1 means helicity +1.
+//   [ 2 + hp_slot(k,nv,v) ]  component k = 0..3 (HELAS slots 2..5), helicity variant v < nv = 2^|S|
+// Variant bits follow the ascending leg order of S; bit = 1 means helicity +1.  hp_slot = k*nv + (v ^ 2k):
+// the XOR makes BOTH access patterns bank-conflict free for 16-byte elements -- 8 consecutive variants
+// of one component (current / pair-object phases) and the tensor-core fragment (2 variants x 4 components
+// per quarter warp).
 #pragma once
 #include "pipeline_kernels.cuh"
 #include "process_kernels.cuh"
@@ -72,22 +80,20 @@ struct HpPairItem {
   unsigned short pair, v;      // work item of a pair phase: (object, helicity variant)
 };
 
-// one amplitude (cxd units, relative to the event's wavefunction / scratch area):
-//   x component k for helicity h:  wf_e[x + k*xnv + vtab[xvt + h]]
-//   Q component k:                 scratch_e[q + k*qnv + vtab[qvt + h]]
-struct HpAmp {
-  unsigned short x, q;         // x: offset of component 0 (block offset + 2) in the event's wavefunction area
-  unsigned short xnv, qnv;     // component strides = helicity variants
-  unsigned short xvt, qvt;     // row of vtab (leg mask * NCOMB)
+// One tensor-core work item of the amplitude phase: rows = 8 helicity variants of the pair object Q
+// (from variant q0), columns = 8 variants of the wavefunction x (from x0); element (r, c) is the
+// amplitude of helicity combination rowh[r] | colh[c] and goes to row `slot` of the amplitude buffer.
+struct alignas(16) HpTile {
+  unsigned short q, x;          // component 0 of Q in the event's scratch area / of x in its wavefunction area (cxd)
+  unsigned short qnv, xnv;      // component strides = helicity variants of the objects
+  unsigned char q0, x0;         // first variant of the tile
+  unsigned char qvalid, xvalid; // rows / columns in use (the rest is padding)
+  unsigned short slot, pad;
+  unsigned char rowh[8], colh[8];
 };
 
-#ifndef MF_HP_GROUP
-#define MF_HP_GROUP 8
-#endif
-constexpr int HP_GROUP = MF_HP_GROUP;   // amplitudes per unrolled group of the amplitude phase
-
 struct HpBatch {
-  unsigned short item_begin, item_end, group_begin, group_end;
+  unsigned short item_begin, item_end, tile_begin, tile_end;
 };
 
 struct HpItem {
@@ -99,7 +105,7 @@ struct HpItem {
   unsigned long long vmap[3];        // 4 bits per output variant: the input's variant index
 };
 
-// phase 1: work item `it` in [0, NEXT*E*2)
+// phase 1: work item `it` in [0, NEXT*E*2) = (leg, event, helicity)
 template <class P>
 MF_DEV void hp_externals(int it, int E, const double* mom /*[E][NEXT][4]*/, const double* par, double sqh, cxd* wf) {
   const int leg = it / (2 * E);
@@ -113,17 +119,25 @@ MF_DEV void hp_externals(int it, int E, const double* mom /*[E][NEXT][4]*/, cons
   if (x.type == HP_VXXXXX) vxxxxx(p, mass, hel, x.nsf, sqh, w);
   else if (x.type == HP_OXXXXX) oxxxxx(p, mass, hel, x.nsf, w);
   else ixxxxx(p, mass, hel, x.nsf, w);
-  cxd* o = wf + e * P::HP_WFSIZE + P::wf(x.out).off;
+  cxd* o = wf + e * P::HP_EVSTRIDE + P::wf(x.out).off;
   if (bit == 0) o[0] = w[0], o[1] = w[1];
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[2 + k * 2 + bit] = w[2 + k];
 }
 
+// position of helicity combination h inside a row of the amplitude buffer: folding bits 3..5 onto bits 0..2
+// keeps the JAMP threads' reads (consecutive h) conflict free and spreads the tensor-core tiles' stores
+// (8 lanes = 3 arbitrary helicity bits) over the banks
+MF_DEV int hp_abuf_pos(int h) { return h ^ ((h >> 3) & 7); }
+
+// position of (component k, helicity variant v) inside an object of nv variants (see the header)
+MF_DEV int hp_slot(int k, int nv, int v) { return k * nv + (v ^ ((2 * k) & (nv - 1))); }
+
 // the 6 slots of one helicity variant of a wavefunction block
 MF_DEV void hp_load(const cxd* blk, int nv, int v, cxd out[6]) {
   out[0] = blk[0], out[1] = blk[1];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) out[2 + k] = blk[2 + k * nv + v];
+  for (int k = 0; k < 4; ++k) out[2 + k] = blk[2 + hp_slot(k, nv, v)];
 }
 
 // phase 2: work item (item index `idx`, output variant v) of the event whose area is wf_e
@@ -151,7 +165,7 @@ MF_DEV void hp_current(int idx, int v, const double* par, const cxd* coup_e, cxd
   const int nv = it.out_nv;
   if (v == 0) o[0] = r[0], o[1] = r[1];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) o[2 + k * nv + v] = r[2 + k];
+  for (int k = 0; k < 4; ++k) o[2 + hp_slot(k, nv, v)] = r[2 + k];
 }
 
 // vtab[mask * NCOMB + h]: the helicity variant, of an object over the leg set `mask`, that belongs to
@@ -243,36 +257,153 @@ MF_DEV void hp_pair(int pi, int v, const cxd* coup_e, const cxd* wf_e, cxd* scra
   cxd* o = scratch_e + pr.off;
   const int nv = pr.nv;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) o[k * nv + v] = Q[k];
+  for (int k = 0; k < 4; ++k) o[hp_slot(k, nv, v)] = Q[k];
 }
 
-// amplitude ai for helicity h of the event whose areas are wf_e / scratch_e: four complex products
-template <class P>
-MF_DEV cxd hp_amp_dot(int ai, int h, const cxd* wf_e, const cxd* scratch_e, const unsigned char* vtab) {
-  const HpAmp am = P::amp(ai);
-  const int xnv = am.xnv, qnv = am.qnv;
-  const cxd* x = wf_e + am.x + vtab[am.xvt + h];
-  const cxd* q = scratch_e + am.q + vtab[am.qvt + h];
-  cxd amp = x[0] * q[0];
-  amp = fma_c(x[xnv], q[qnv], amp);
-  amp = fma_c(x[2 * xnv], q[2 * qnv], amp);
-  amp = fma_c(x[3 * xnv], q[3 * qnv], amp);
-  return amp;
+// D += A(8x4) B(4x8) on the FP64 tensor cores.  Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// {d0, d1} = D[lane/4][2*(lane%4) + {0, 1}]  (layout checked on the device by tools/ubench.cu)
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+#endif
 }
+
+// explicit shared-space accesses for the amplitude phase (byte address in the shared window)
+__device__ __forceinline__ cxd lds_cxd(unsigned addr) {
+  cxd v = {0.0, 0.0};
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(addr));
+#endif
+  return v;
+}
+__device__ __forceinline__ void sts_cxd(unsigned addr, double re, double im) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(re), "d"(im) : "memory");
+#endif
+}
+
+// NT tiles of the amplitude phase for the E events of the block, executed by a full warp: the
+// descriptors are read first (warp-uniform), then all fragment loads are issued, then the NT*E*4
+// tensor-core instructions, then the stores -- NT*E independent tiles in flight per warp.
+// `evs` = shared-window byte address of the block's event areas.
+struct HpTileWords {
+  uint4 w0;  // q, x, qnv, xnv | q0, x0, qvalid, xvalid | slot
+  uint4 w1;  // rowh[8] | colh[8]
+};
+__device__ __forceinline__ HpTileWords hp_tile_words(const HpTile* t) {
+  const uint4* tp = reinterpret_cast<const uint4*>(t);
+  return HpTileWords{tp[0], tp[1]};
+}
+
+template <class P, int NT>
+__device__ __forceinline__ void hp_mma_tiles(const HpTileWords (&tile)[NT], int lane, unsigned evs) {
+  constexpr int E = P::HP_E;
+  constexpr unsigned EVB = P::HP_EVSTRIDE * 16u;
+  const int r = lane >> 2, k = lane & 3;
+  unsigned qi[NT], xi[NT], d0[NT], d1[NT];
+  bool s0[NT], s1[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const uint4 w0 = tile[t].w0, w1 = tile[t].w1;
+    const int q = w0.x & 0xffff, x = w0.x >> 16, qnv = w0.y & 0xffff, xnv = w0.y >> 16;
+    const int q0 = w0.z & 0xff, x0 = (w0.z >> 8) & 0xff, qvalid = (w0.z >> 16) & 0xff, xvalid = w0.z >> 24;
+    const int slot = w0.w & 0xffff;
+    qi[t] = evs + 16u * (P::HP_WFSIZE + q + hp_slot(k, qnv, (q0 + r) & (qnv - 1)));
+    xi[t] = evs + 16u * (x + hp_slot(k, xnv, (x0 + r) & (xnv - 1)));
+    const int hq = (((r & 4) ? w1.y : w1.x) >> (8 * (r & 3))) & 0xff;
+    const unsigned hc = (((k & 2) ? w1.w : w1.z) >> (16 * (k & 1))) & 0xffff;
+    d0[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::NCOMB + hp_abuf_pos(hq | (hc & 0xff)));
+    d1[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::NCOMB + hp_abuf_pos(hq | (hc >> 8)));
+    s0[t] = r < qvalid && 2 * k < xvalid, s1[t] = r < qvalid && 2 * k + 1 < xvalid;
+  }
+  cxd qa[NT][E], xb[NT][E];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int e = 0; e < E; ++e) qa[t][e] = lds_cxd(qi[t] + e * EVB), xb[t][e] = lds_cxd(xi[t] + e * EVB);
+  double cr0[NT][E], cr1[NT][E], ci0[NT][E], ci1[NT][E];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      cr0[t][e] = cr1[t][e] = ci0[t][e] = ci1[t][e] = 0.0;
+      dmma_m8n8k4(cr0[t][e], cr1[t][e], qa[t][e].re, xb[t][e].re);
+      dmma_m8n8k4(ci0[t][e], ci1[t][e], qa[t][e].re, xb[t][e].im);
+    }
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      dmma_m8n8k4(cr0[t][e], cr1[t][e], -qa[t][e].im, xb[t][e].im);
+      dmma_m8n8k4(ci0[t][e], ci1[t][e], qa[t][e].im, xb[t][e].re);
+    }
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (s0[t]) sts_cxd(d0[t] + e * EVB, cr0[t][e], ci0[t][e]);
+      if (s1[t]) sts_cxd(d1[t] + e * EVB, cr1[t][e], ci1[t][e]);
+    }
+}
+
+// the same tile on the CPU (tests/hostcheck): plain loops over its rows and columns
+template <class P>
+inline void hp_mma_tile_host(const HpTile* tp, const cxd* wf_e, const cxd* scratch_e, cxd* abuf_e) {
+  for (int r = 0; r < tp->qvalid; ++r)
+    for (int c = 0; c < tp->xvalid; ++c) {
+      cxd amp = mk(0.0, 0.0);
+      for (int k = 0; k < 4; ++k)
+        amp = fma_c(scratch_e[tp->q + hp_slot(k, tp->qnv, tp->q0 + r)], wf_e[tp->x + hp_slot(k, tp->xnv, tp->x0 + c)], amp);
+      abuf_e[tp->slot * P::NCOMB + hp_abuf_pos(tp->rowh[r] | tp->colh[c])] = amp;
+    }
+}
+
+// Optional phase timers (-DMF_HP_PROFILE, tools/profile_phases.py): SM cycles spent by each block in
+// externals / currents / pair objects / amplitudes / JAMP / colour+reduction, summed over blocks.
+#ifdef MF_HP_PROFILE
+__device__ unsigned long long g_hp_prof[8];
+#define MF_PROF_DECL long long prof_t = clock64();
+#define MF_PROF(slot)                                                   \
+  do {                                                                  \
+    if (threadIdx.x == 0) {                                             \
+      const long long now_ = clock64();                                 \
+      atomicAdd(&g_hp_prof[slot], (unsigned long long)(now_ - prof_t)); \
+      prof_t = now_;                                                    \
+    }                                                                   \
+  } while (0)
+#else
+#define MF_PROF_DECL
+#define MF_PROF(slot)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // The E-event matrix-element evaluation used by both kernels.  `mom` [E][NEXT][4], `coup` [E][NCOUP]
-// and `wf` live in shared memory; returns, in thread (e, h = 0), the event's |M|^2 summed over
-// helicities and colours and averaged (other threads return garbage).
+// and the event areas `ev` [E][HP_EVSTRIDE] live in shared memory; returns, in the first thread of
+// every event, the event's |M|^2 summed over helicities and colours and averaged (other threads
+// return garbage).  Thread tid = (e * HP_NCG + colour group) * NCOMB + helicity combination.
 template <class P>
 __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events */, const double* mom,
-                                                   const cxd* coup, const double* par, double sqh, cxd* wf,
-                                                   cxd* scratch, const unsigned char* vtab,
-                                                   double* red /* [T/32] */, int only_h) {
-  constexpr int E = P::HP_E, NH = P::NCOMB, T = E * NH;
+                                                   const cxd* coup, const double* par, double sqh, cxd* ev,
+                                                   const unsigned char* vtab, double* red /* [T/32] */, int only_h) {
+  constexpr int E = P::HP_E, NH = P::NCOMB, NCG = P::HP_NCG, TE = NH * NCG, T = E * TE, EVS = P::HP_EVSTRIDE;
   const int tid = threadIdx.x;
-  for (int it = tid; it < P::NEXT * E * 2; it += T) hp_externals<P>(it, E, mom, par, sqh, wf);
+  MF_PROF_DECL
+  if constexpr (2 * E <= 32 && P::NEXT <= 32) {
+    // leg l runs in warp l % NW, lanes [l / NW * 2E, +2E): the legs sharing a warp are mostly of one
+    // kind, so the vector / spinor routines of different legs run side by side instead of in turn
+    constexpr int NW = T / 32, PER = 32 / (2 * E);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int l0 = 0; l0 < P::NEXT; l0 += NW * PER) {
+      const int leg = l0 + warp + NW * (lane / (2 * E));
+      if (leg < P::NEXT && lane < PER * 2 * E) hp_externals<P>(leg * 2 * E + lane % (2 * E), E, mom, par, sqh, ev);
+    }
+  } else {
+    for (int it = tid; it < P::NEXT * E * 2; it += T) hp_externals<P>(it, E, mom, par, sqh, ev);
+  }
   __syncthreads();
+  MF_PROF(0);
 #pragma unroll 1
   for (int L = 2; L <= P::HP_MAXLEVEL; ++L) {
     const int begin = P::level_begin(L), cnt = P::level_begin(L + 1) - begin;
@@ -283,21 +414,23 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
       const int ci = w / (E * nv);
       const int r = w - ci * (E * nv);
       const int e = r / nv, v = r - e * nv;
-      hp_current<P>(begin + ci, v, par, coup + e * P::NCOUP, wf + e * P::HP_WFSIZE);
+      hp_current<P>(begin + ci, v, par, coup + e * P::NCOUP, ev + e * EVS);
     }
     __syncthreads();
   }
-  const int e = tid / NH, h = tid - e * NH;
+  MF_PROF(1);
+  const int e = tid / TE, rr = tid - e * TE, cg = rr / NH, h = rr - cg * NH;
+  const cxd* wf_e = ev + e * EVS;
   double me;
-  if (P::HP_UNROLL) {
+  if constexpr (P::HP_UNROLL) {
     // short amplitude lists: straight-line code, whole vertices per helicity combination
-    me = P::hp_amps_unrolled(wf + e * P::HP_WFSIZE, vtab, h, coup + e * P::NCOUP);
+    me = P::hp_amps_unrolled(wf_e, vtab, h, coup + e * P::NCOUP);
   } else {
-    const cxd* wf_e = wf + e * P::HP_WFSIZE;
-    const cxd* scratch_e = scratch + e * P::HP_SCRATCH;
-    cxd J[P::NCOLOR];
+    cxd* abuf_h = ev + e * EVS + P::HP_WFSIZE + P::HP_SCRATCH + hp_abuf_pos(h);
+    cxd J[P::HP_NJ];
 #pragma unroll
-    for (int j = 0; j < P::NCOLOR; ++j) J[j] = mk(0.0, 0.0);
+    for (int j = 0; j < P::HP_NJ; ++j) J[j] = mk(0.0, 0.0);
+    const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
     for (int bi = 0; bi < P::HP_NBATCH; ++bi) {
       const HpBatch bt = P::batch(bi);
@@ -306,59 +439,89 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
       for (int w = tid; w < total; w += T) {
         const int ii = w / E, ee = w - ii * E;
         const HpPairItem pit = P::pair_item(bt.item_begin + ii);
-        hp_pair<P>(pit.pair, pit.v, coup + ee * P::NCOUP, wf + ee * P::HP_WFSIZE, scratch + ee * P::HP_SCRATCH);
+        hp_pair<P>(pit.pair, pit.v, coup + ee * P::NCOUP, ev + ee * EVS, ev + ee * EVS + P::HP_WFSIZE);
       }
       __syncthreads();
-#pragma unroll 1
-      for (int g = bt.group_begin; g < bt.group_end; ++g) {
-        // HP_GROUP independent dot products in flight, then their JAMP updates (one block-uniform switch)
-        cxd amp[HP_GROUP];
+      MF_PROF(2);
+      {
+        // every warp takes MT tiles per trip; an index past the end repeats the batch's last tile
+        // (same values stored twice) so that the trips stay straight-line
+        constexpr int NW = T / 32, MT = P::HP_TILES_IN_FLIGHT;
+        const unsigned evs = (unsigned)__cvta_generic_to_shared(ev);
+        const int last = bt.tile_end - 1;
+        // the descriptors of the next trip are fetched while the current trip computes
+        HpTileWords cur[MT], nxt[MT];
+        int w = bt.tile_begin + warp;
 #pragma unroll
-        for (int k = 0; k < HP_GROUP; ++k) amp[k] = hp_amp_dot<P>(g * HP_GROUP + k, h, wf_e, scratch_e, vtab);
-        P::jamp_accumulate(g, amp, J);
+        for (int t = 0; t < MT; ++t) cur[t] = hp_tile_words(P::tile(w + t * NW < last ? w + t * NW : last));
+#pragma unroll 1
+        for (; w < bt.tile_end; w += MT * NW) {
+          const int wn = w + MT * NW;
+#pragma unroll
+          for (int t = 0; t < MT; ++t) nxt[t] = hp_tile_words(P::tile(wn + t * NW < last ? wn + t * NW : last));
+          hp_mma_tiles<P, MT>(cur, lane, evs);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) cur[t] = nxt[t];
+        }
       }
-      __syncthreads();  // the next batch overwrites the scratch area
+      __syncthreads();
+      MF_PROF(3);
+      P::jamp_batch(bi, cg, abuf_h, J);
+      MF_PROF(4);
     }
-    me = P::colour_sum(J);
+    if constexpr (NCG > 1) {
+      // exchange the JAMPs of the colour groups through the (now free) scratch + amplitude buffer area
+      static_assert(P::HP_EVSTRIDE - P::HP_WFSIZE >= P::NCOLOR * NH, "JAMP exchange area too small");
+      cxd* jb = ev + e * EVS + P::HP_WFSIZE + h;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < P::HP_NJ; ++j)
+        if (cg * P::HP_NJ + j < P::NCOLOR) jb[(cg * P::HP_NJ + j) * NH] = J[j];
+      __syncthreads();
+      me = P::colour_sum(cg, J, jb);
+    } else {
+      me = P::colour_sum(0, J, nullptr);
+    }
   }
   if (only_h >= 0) me = (h == only_h) ? me : 0.0;
   if (e >= nev) me = 0.0;
-  // sum over helicities of one event
-  constexpr int W = NH < 32 ? NH : 32;
+  // sum over the helicities (and colour groups) of one event
+  constexpr int W = TE < 32 ? TE : 32;
 #pragma unroll
   for (int o = W / 2; o > 0; o >>= 1) me += __shfl_down_sync(0xffffffffu, me, o, W);
-  if (NH > 32) {
+  if (TE > 32) {
     const int warp = tid >> 5, lane = tid & 31;
     if (lane == 0) red[warp] = me;
     __syncthreads();
-    if (h == 0) {
+    if (rr == 0) {
       me = 0.0;
 #pragma unroll
-      for (int k = 0; k < NH / 32; ++k) me += red[e * (NH / 32) + k];
+      for (int k = 0; k < TE / 32; ++k) me += red[e * (TE / 32) + k];
     }
   }
+  MF_PROF(5);
   return only_h >= 0 ? me : me / P::DENOM;
 }
 
 template <class P>
 struct HpSmatrixSmem {
-  static constexpr int E = P::HP_E, T = E * P::NCOMB;
+  static constexpr int E = P::HP_E, T = E * P::NCOMB * P::HP_NCG;
   double mom[E * P::NEXT * 4];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
   double red[T / 32 + 1];
-  unsigned char vtab[(1 << P::NEXT) * P::NCOMB];
-  // followed by cxd wf[HP_WFSIZE * E], cxd scratch[HP_SCRATCH * E]
+  unsigned char vtab[P::HP_UNROLL ? (1 << P::NEXT) * P::NCOMB : 16];  // straight-line flavour only
+  // followed by the event areas: cxd ev[E][HP_EVSTRIDE] = wavefunctions | pair objects | amplitude buffer
 };
 
 template <class P>
-__global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_kernel_hp(const SmatrixArgs a) {
-  constexpr int E = P::HP_E, NH = P::NCOMB, T = E * NH;
+__global__ void __launch_bounds__(P::HP_E* P::NCOMB* P::HP_NCG, P::HP_MINBLOCKS) smatrix_kernel_hp(const SmatrixArgs a) {
+  constexpr int E = P::HP_E, NH = P::NCOMB, TE = NH * P::HP_NCG, T = E * TE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HpSmatrixSmem<P>& s = *reinterpret_cast<HpSmatrixSmem<P>*>(smem_raw);
-  cxd* wf = reinterpret_cast<cxd*>(smem_raw + ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16);
+  cxd* evarea = reinterpret_cast<cxd*>(smem_raw + ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16);
   const int tid = threadIdx.x;
-  cxd* scratch = wf + (size_t)P::HP_WFSIZE * E;
-  for (int i = tid; i < (1 << P::NEXT) * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
+  if constexpr (P::HP_UNROLL)
+    for (int i = tid; i < (1 << P::NEXT) * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
   int only_h = -1;
   if (a.only_comb >= 0) {
     only_h = 0;
@@ -394,9 +557,9 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
         }
       }
       __syncthreads();
-      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, wf, scratch, s.vtab, s.red, only_h);
-      const int e = tid / NH, h = tid - e * NH;
-      if (h == 0 && e < nev) a.out[ev0 + e] = me;
+      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, evarea, s.vtab, s.red, only_h);
+      const int e = tid / TE;
+      if (tid - e * TE == 0 && e < nev) a.out[ev0 + e] = me;
       __syncthreads();
     }
   }
@@ -405,7 +568,7 @@ __global__ void __launch_bounds__(P::HP_E* P::NCOMB, P::HP_MINBLOCKS) smatrix_ke
 // ------------------------------------------------------------------------------------------------
 template <class P>
 size_t hp_smatrix_smem() {
-  return ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16 + sizeof(cxd) * (P::HP_WFSIZE + P::HP_SCRATCH) * P::HP_E;
+  return ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16 + sizeof(cxd) * (size_t)P::HP_EVSTRIDE * P::HP_E;
 }
 
 template <class P>
@@ -425,12 +588,12 @@ int launch_smatrix_hp(const double* d_p, int layout, long long nevt, const doubl
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smatrix_kernel_hp<P>, P::HP_E * P::NCOMB, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smatrix_kernel_hp<P>, P::HP_THREADS, smem);
   if (per_sm < 1) per_sm = 1;
   long long blocks = (nevt + P::HP_E - 1) / P::HP_E;
   const long long cap = (long long)sms * per_sm;
   if (blocks > cap) blocks = cap;
-  smatrix_kernel_hp<P><<<(unsigned)blocks, P::HP_E * P::NCOMB, smem, st>>>(a);
+  smatrix_kernel_hp<P><<<(unsigned)blocks, P::HP_THREADS, smem, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("smatrix_kernel_hp launch", e);
   return 0;
@@ -443,7 +606,7 @@ int integrand_blocks_hp() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = hp_smatrix_smem<P>();
   cudaFuncSetAttribute(smatrix_kernel_hp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smatrix_kernel_hp<P>, P::HP_E * P::NCOMB, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smatrix_kernel_hp<P>, P::HP_THREADS, smem);
   if (per_sm < 1) per_sm = 1;
   return sms * per_sm;
 }
@@ -486,7 +649,7 @@ int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
   const size_t smem = hp_smatrix_smem<P>();
   e = cudaFuncSetAttribute(smatrix_kernel_hp<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail("smatrix_kernel_hp smem attribute", e);
-  smatrix_kernel_hp<P><<<u->nblocks, P::HP_E * P::NCOMB, smem, st>>>(a);
+  smatrix_kernel_hp<P><<<u->nblocks, P::HP_THREADS, smem, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("smatrix_kernel_hp launch", e);
 
@@ -513,6 +676,21 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
 
 }  // namespace mf
 
+#ifdef MF_HP_PROFILE
+#define MF_DEFINE_PROFILE_HOOK                                                          \
+  int mfp_profile_read(unsigned long long* out8, int reset) {                           \
+    cudaDeviceSynchronize();                                                            \
+    if (out8) cudaMemcpyFromSymbol(out8, mf::g_hp_prof, 8 * sizeof(unsigned long long)); \
+    if (reset) {                                                                        \
+      unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};                               \
+      cudaMemcpyToSymbol(mf::g_hp_prof, z, sizeof(z));                                  \
+    }                                                                                   \
+    return 0;                                                                           \
+  }
+#else
+#define MF_DEFINE_PROFILE_HOOK
+#endif
+
 #define MF_DEFINE_PROCESS(P)                                                                                   \
   extern "C" {                                                                                                 \
   int mfp_get_info(mfp_info* o) {                                                                              \
@@ -522,7 +700,7 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
     o->nexternal = P::NEXT, o->ninitial = P::NINIT, o->ncomb = P::NCOMB, o->ncolor = P::NCOLOR;                \
     o->ndiags = P::NDIAGS, o->namps = P::NAMPS, o->nwavefuncs = P::NWF, o->nparams = P::NPAR;                  \
     o->ncouplings = P::NCOUP, o->ndim = 4 * (P::NEXT - 2) + 2;                                                 \
-    o->block_threads = mf::use_hp<P>() ? P::HP_E * P::NCOMB : P::BLOCK;                                        \
+    o->block_threads = mf::use_hp<P>() ? P::HP_THREADS : P::BLOCK;                                        \
     o->denominator = P::DENOM, o->flops_per_event = P::FLOPS;                                                  \
     return 0;                                                                                                  \
   }                                                                                                            \
@@ -574,4 +752,5 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
     return mf::launch_integrand_hp<P>(a, (cudaStream_t)st);                                                    \
   }                                                                                                            \
   const char* mfp_last_error(void) { return mf::g_err; }                                                       \
+  MF_DEFINE_PROFILE_HOOK                                                                                       \
   }

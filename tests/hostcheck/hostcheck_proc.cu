@@ -28,13 +28,12 @@ extern "C" int hostcheck_smatrix(const double* p, long long nevt, const double* 
 // "thread" of a phase in turn on the CPU reproduces the kernel's data flow exactly.
 extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const double* par, const double* coup,
                                     long long coup_stride, double sqh, int only_comb, double* out) {
-  constexpr int E = Proc::HP_E, NH = Proc::NCOMB, T = E * NH;
-  std::vector<cxd> wf((size_t)Proc::HP_WFSIZE * E);
+  constexpr int E = Proc::HP_E, NH = Proc::NCOMB, NCG = Proc::HP_NCG, EVS = Proc::HP_EVSTRIDE;
+  std::vector<cxd> evarea((size_t)EVS * E);
   std::vector<double> mom(E * Proc::NEXT * 4);
   std::vector<cxd> cp(E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
   std::vector<unsigned char> vtab((1 << Proc::NEXT) * NH);
   for (int i = 0; i < (1 << Proc::NEXT) * NH; ++i) mf::hp_fill_vtab<Proc>(i, vtab.data());
-  std::vector<cxd> scratch((size_t)(Proc::HP_SCRATCH > 0 ? Proc::HP_SCRATCH : 1) * E);
   int only_h = -1;
   if (only_comb >= 0) {
     only_h = 0;
@@ -50,44 +49,53 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
         cp[e * Proc::NCOUP + j] = mk(coup[2 * o], coup[2 * o + 1]);
       }
     }
-    for (int it = 0; it < Proc::NEXT * E * 2; ++it) mf::hp_externals<Proc>(it, E, mom.data(), par, sqh, wf.data());
+    for (int it = 0; it < Proc::NEXT * E * 2; ++it) mf::hp_externals<Proc>(it, E, mom.data(), par, sqh, evarea.data());
     for (int L = 2; L <= Proc::HP_MAXLEVEL; ++L) {
       const int begin = Proc::level_begin(L), cnt = Proc::level_begin(L + 1) - begin, nv = 1 << L;
       for (int w = 0; w < cnt * E * nv; ++w) {
         const int ci = w / (E * nv), r = w - ci * (E * nv), e = r / nv, v = r - e * nv;
-        mf::hp_current<Proc>(begin + ci, v, par, cp.data() + e * Proc::NCOUP, wf.data() + e * Proc::HP_WFSIZE);
+        mf::hp_current<Proc>(begin + ci, v, par, cp.data() + e * Proc::NCOUP, evarea.data() + e * EVS);
       }
     }
     std::vector<double> me_h((size_t)E * NH, 0.0);
     if (Proc::HP_UNROLL) {
       for (int e = 0; e < nev; ++e)
         for (int h = 0; h < NH; ++h)
-          me_h[e * NH + h] = Proc::hp_amps_unrolled(wf.data() + e * Proc::HP_WFSIZE, vtab.data(), h, cp.data() + e * Proc::NCOUP);
+          me_h[e * NH + h] = Proc::hp_amps_unrolled(evarea.data() + e * EVS, vtab.data(), h, cp.data() + e * Proc::NCOUP);
     } else {
-      std::vector<cxd> J((size_t)T * Proc::NCOLOR, mk(0.0, 0.0));
+      // "thread" t = (e * NCG + cg) * NH + h owns HP_NJ JAMPs
+      constexpr int NJ = Proc::HP_NJ, T = E * NCG * NH;
+      std::vector<cxd> J((size_t)T * NJ, mk(0.0, 0.0));
       for (int bi = 0; bi < Proc::HP_NBATCH; ++bi) {
         const mf::HpBatch bt = Proc::batch(bi);
         for (int w = 0; w < (bt.item_end - bt.item_begin) * E; ++w) {
           const int ii = w / E, ee = w - ii * E;
           const mf::HpPairItem pit = Proc::pair_item(bt.item_begin + ii);
-          mf::hp_pair<Proc>(pit.pair, pit.v, cp.data() + ee * Proc::NCOUP, wf.data() + ee * Proc::HP_WFSIZE,
-                            scratch.data() + ee * (Proc::HP_SCRATCH > 0 ? Proc::HP_SCRATCH : 1));
+          mf::hp_pair<Proc>(pit.pair, pit.v, cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS,
+                            evarea.data() + ee * EVS + Proc::HP_WFSIZE);
+        }
+        for (int w = 0; w < (bt.tile_end - bt.tile_begin) * E; ++w) {
+          const int ti = w / E, ee = w - ti * E;
+          cxd* a_e = evarea.data() + ee * EVS;
+          mf::hp_mma_tile_host<Proc>(Proc::tile(bt.tile_begin + ti), a_e, a_e + Proc::HP_WFSIZE,
+                                     a_e + Proc::HP_WFSIZE + Proc::HP_SCRATCH);
         }
         for (int t = 0; t < T; ++t) {
-          const int e = t / NH, h = t - e * NH;
-          cxd(&Jt)[Proc::NCOLOR] = *reinterpret_cast<cxd(*)[Proc::NCOLOR]>(&J[(size_t)t * Proc::NCOLOR]);
-          for (int g = bt.group_begin; g < bt.group_end; ++g) {
-            cxd amp[mf::HP_GROUP];
-            for (int k = 0; k < mf::HP_GROUP; ++k)
-              amp[k] = mf::hp_amp_dot<Proc>(g * mf::HP_GROUP + k, h, wf.data() + e * Proc::HP_WFSIZE,
-                                            scratch.data() + e * (Proc::HP_SCRATCH > 0 ? Proc::HP_SCRATCH : 1), vtab.data());
-            Proc::jamp_accumulate(g, amp, Jt);
-          }
+          const int e = t / (NCG * NH), cg = (t / NH) % NCG, h = t % NH;
+          cxd(&Jt)[NJ] = *reinterpret_cast<cxd(*)[NJ]>(&J[(size_t)t * NJ]);
+          Proc::jamp_batch(bi, cg, evarea.data() + e * EVS + Proc::HP_WFSIZE + Proc::HP_SCRATCH + mf::hp_abuf_pos(h), Jt);
         }
       }
+      if (NCG > 1)
+        for (int t = 0; t < T; ++t) {
+          const int e = t / (NCG * NH), cg = (t / NH) % NCG, h = t % NH;
+          for (int j = 0; j < NJ; ++j)
+            if (cg * NJ + j < Proc::NCOLOR) evarea[(size_t)e * EVS + Proc::HP_WFSIZE + h + (cg * NJ + j) * NH] = J[(size_t)t * NJ + j];
+        }
       for (int t = 0; t < T; ++t) {
-        cxd(&Jt)[Proc::NCOLOR] = *reinterpret_cast<cxd(*)[Proc::NCOLOR]>(&J[(size_t)t * Proc::NCOLOR]);
-        me_h[t] = Proc::colour_sum(Jt);
+        const int e = t / (NCG * NH), cg = (t / NH) % NCG, h = t % NH;
+        cxd(&Jt)[NJ] = *reinterpret_cast<cxd(*)[NJ]>(&J[(size_t)t * NJ]);
+        me_h[e * NH + h] += Proc::colour_sum(cg, Jt, evarea.data() + e * EVS + Proc::HP_WFSIZE + h);
       }
     }
     for (int e = 0; e < nev; ++e) {
@@ -97,6 +105,5 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
       out[ev0 + e] = only_h >= 0 ? acc : acc / Proc::DENOM;
     }
   }
-  (void)T;
   return 0;
 }

@@ -112,3 +112,25 @@ def test_generated_cuda_source_on_host_ttxg(irs):
     coup = np.stack([params[c] for c in ir["couplings"]])
     out = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF)
     np.testing.assert_allclose(out, omatrix.smatrix(ir, p, params), rtol=1e-12)
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+@pytest.mark.parametrize("k", [1, 2])
+def test_helicity_parallel_data_flow_on_host(irs, k):
+    """The helicity-parallel kernels' tables and generated code (currents once per helicity variant,
+    pair objects, amplitude tiles -> amplitude buffer -> JAMP code per colour group, colour groups)
+    executed phase by phase on the CPU against the oracle; also one helicity row on its own."""
+    import hostcheck as hc
+
+    ir = irs[k]
+    lib = hc.process(ir)
+    p = _points(k, n=6, seed=11)
+    a_s = 0.09 + 0.05 * np.random.default_rng(3).random(6)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    ref = omatrix.smatrix(ir, p, params)
+    out = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True)
+    np.testing.assert_allclose(out, ref, rtol=1e-12)
+    row = 5
+    one = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, only_comb=row, hp=True)
+    np.testing.assert_allclose(one, omatrix.matrix(ir, p, ir["helicities"][row], params), rtol=1e-11)
