@@ -170,9 +170,9 @@ def emit_matrix_body(ir):
 
 # ------------------------------------------------------------------------------------------------
 # helicity-parallel variant (csrc/process_kernels_hp.cuh)
+STRAIGHT_LINE_MAX_CALLS = 400   # longer call lists are only emitted in the helicity-parallel (table) form
 THREAD_MAX_CALLS = 64     # call lists up to this length also get the one-event-per-thread kernels
 HP_UNROLL_MAX_AMPS = 32   # amplitude lists up to this length are emitted as straight-line code
-HP_SCRATCH_CXD = 512      # shared-memory scratch for the pair objects of a batch, complex numbers per event (8 KB)
 HP_TYPES = {"vxxxxx": 0, "oxxxxx": 1, "ixxxxx": 2, "FFV1_1": 3, "FFV1_2": 4, "FFV1P0_3": 5, "VVV1P0_1": 6,
             "VVVV1P0_1": 7, "VVVV3P0_1": 8, "VVVV4P0_1": 9}
 
@@ -209,47 +209,57 @@ def hp_analyse(ir):
     return wfs, exts, items, amps, off
 
 
-def _vmap(out_legs, in_legs):
-    word = 0
-    for v in range(1 << len(out_legs)):
-        idx = 0
-        for q, l in enumerate(in_legs):
-            idx |= ((v >> out_legs.index(l)) & 1) << q
-        word |= idx << (4 * v)
-    return word
+def hp_config(ir, key):
+    """Launch shape of the helicity-parallel kernels, MADFLOW_B200_HP_<KEY> overrides (tools/build_variants.py):
+      E          events per block
+      NCG        colour groups = threads per (event, helicity combination); each keeps NCOLOR/NCG JAMPs in registers
+      NB         rows of the amplitude buffer = amplitudes per batch
+      SCRATCH    shared-memory scratch for the pair objects of a batch, complex numbers per event
+      MINBLOCKS  resident blocks per SM the register allocation aims at
+    Defaults from measurements on B200: up to 64 helicity combinations two events per
+    block and all JAMPs in one thread; beyond, one event per block (its wavefunctions fill a third of the
+    shared memory), 8 colour groups and batches of 64 amplitudes."""
+    env = os.environ.get("MADFLOW_B200_HP_" + key)
+    if env:
+        return int(env)
+    if ir["ncomb"] > 64:
+        return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 4096, "MINBLOCKS": 1}[key]
+    return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 16, "SCRATCH": 512, "MINBLOCKS": 2}[key]
 
 
-def hp_batch_amps():
-    """Rows of the amplitude buffer = amplitudes per batch of the tensor-core amplitude phase."""
-    return int(os.environ.get("MADFLOW_B200_HP_NB", 16))
+def hp_passes(ir):
+    """Helicity passes: with more than 64 helicity combinations the amplitude / JAMP / colour phases run
+    once per helicity of the last external leg (64 combinations per pass), so that the JAMPs of a pass
+    fit in registers and their exchange area in shared memory."""
+    if os.environ.get("MADFLOW_B200_HP_NPASS"):
+        return int(os.environ["MADFLOW_B200_HP_NPASS"])
+    return max(1, ir["ncomb"] // 64)
 
 
-def hp_scratch():
-    """Shared-memory scratch for the pair objects of one batch, complex numbers per event."""
-    return int(os.environ.get("MADFLOW_B200_HP_SCRATCH", HP_SCRATCH_CXD))
-
-
-def hp_colour_groups(ir):
-    """Threads per (event, helicity combination): the JAMPs of one helicity are spread over this many
-    threads (colour groups) to keep them in registers at a higher occupancy."""
-    if os.environ.get("MADFLOW_B200_HP_NCG"):
-        return int(os.environ["MADFLOW_B200_HP_NCG"])
-    return 1
-
-
-def hp_events_per_block(ir):
-    if os.environ.get("MADFLOW_B200_HP_E"):
-        return int(os.environ["MADFLOW_B200_HP_E"])
-    return max(1, 128 // ir["ncomb"])
+def hp_colour_mode(ir, ncg):
+    """'thread': each thread owns all JAMPs of its helicity; 'groups': generated code, JAMPs exchanged through
+    shared memory; 'mma' / 'loop': table driven over the block-symmetrised colour matrix, on the FP64 tensor
+    cores / on the CUDA cores (the A/B pair behind DESIGN.md's tensor-core decision)."""
+    mode = os.environ.get("MADFLOW_B200_HP_COLOUR")
+    if mode:
+        return mode
+    if ncg == 1:
+        return "thread"
+    return "mma" if len(ir["jamp"]) >= 48 else "groups"
 
 
 def emit_hp(ir):
-    """Tables + the straight-line amplitude/JAMP/colour code of the helicity-parallel kernels."""
+    """Tables + the generated amplitude/JAMP/colour code of the helicity-parallel kernels."""
     wfs, exts, items, amps, wfsize = hp_analyse(ir)
     n = ir["nexternal"]
     assert ir["ncomb"] == 2**n, "the hp kernels need the full 2^n helicity table"
     maxlevel = max(w["level"] for w in wfs)
-    assert maxlevel <= 4, "variant maps hold up to 16 variants per current"
+    NH = ir["ncomb"]
+    NPASS = hp_passes(ir)
+    assert NPASS in (1, 2)
+    NHP = NH // NPASS
+    LSTAR = n - 1 if NPASS > 1 else None   # the leg whose helicity is fixed within a pass (top variant bit)
+    big = len(amps) > 400                  # tables beyond the 64 KB of constant memory live in global memory
 
     def pidx(name):
         return -1 if name == "ZERO" else ir["params"].index(name)
@@ -258,6 +268,10 @@ def emit_hp(ir):
         space = "__device__ __constant__" if const else "__device__ const"
         return (f"{space} {ctype} d_{name}[{count}] = {{{body}}};\n"
                 f"static const {ctype} h_{name}[{count}] = {{{body}}};")
+
+    def vmask(out_legs, in_legs):
+        """bits of the output's variant index that make up the input's variant index (both ascending)"""
+        return sum(1 << q for q, l in enumerate(out_legs) if l in in_legs)
 
     L = []
     L.append(both("mf::HpWf", "wf", len(wfs), ", ".join(f"{{{w['off']}u, {w['nv']}, {w['mask']}}}" for w in wfs)))
@@ -270,14 +284,14 @@ def emit_hp(ir):
     for it in items:
         c = it["call"]
         ins = it["in"] + [0] * (3 - len(it["in"]))
-        vm = [_vmap(wfs[it["out"]]["legs"], wfs[i]["legs"]) for i in it["in"]] + [0] * (3 - len(it["in"]))
+        vm = [vmask(wfs[it["out"]]["legs"], wfs[i]["legs"]) for i in it["in"]] + [0] * (3 - len(it["in"]))
         ioff = [wfs[i]["off"] for i in ins]
         inv = [wfs[i]["nv"] for i in ins]
         W = wfs[it["out"]]
         rows.append(f"{{{HP_TYPES[c['op']]}, {len(it['in'])}, {pidx(c['mass'])}, {pidx(c['width'])}, "
                     f"{ir['couplings'].index(c['coup'])}, {1 if c.get('coup_sign', 1) < 0 else 0}, {W['off']}, {W['nv']}, "
                     f"{{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
-                    f"{{{vm[0]}ull, {vm[1]}ull, {vm[2]}ull}}}}")
+                    f"{{{vm[0]}, {vm[1]}, {vm[2]}}}}}")
     L.append(both("mf::HpItem", "items", max(len(rows), 1), ",\n  ".join(rows) if rows else "{0}"))
     begins = [sum(1 for it in items if wfs[it["out"]]["level"] < lev) for lev in range(0, maxlevel + 2)]
     L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
@@ -289,7 +303,8 @@ def emit_hp(ir):
             by_amp.setdefault(k, []).append((j, float(re), float(im)))
     used = [am for am in amps if by_amp.get(am["call"]["amp"])]
 
-    # pair objects: amp = x . Q(rest of the vertex), x = the input with the most legs
+    # pair objects: amp = x . Q(rest of the vertex), x = the input with the most legs (with helicity passes:
+    # preferably one that does not hold the pass leg, so that the pass halves the rows and not the columns)
     QUARTIC = {"1": ((+1, (1, 4), (2, 3)), (-1, (1, 3), (2, 4))),
                "3": ((+1, (1, 4), (2, 3)), (-1, (1, 2), (3, 4))),
                "4": ((+1, (1, 3), (2, 4)), (-1, (1, 2), (3, 4)))}
@@ -298,7 +313,9 @@ def emit_hp(ir):
         c = am["call"]
         ins = am["in"]
         sizes = [wfs[w]["level"] for w in ins]
-        jx = sizes.index(max(sizes))
+        cands = [q for q in range(len(ins)) if sizes[q] == max(sizes)]
+        free = [q for q in cands if LSTAR not in wfs[ins[q]]["legs"]]
+        jx = (free or cands)[0]
         op = c["op"]
         term = (0, 0)
         if op == "FFV1_0":
@@ -326,17 +343,18 @@ def emit_hp(ir):
             pair_index[key] = len(pairs)
             pairs.append(dict(type=ptype, rest=rest, term=term, coup=coup, neg=neg, legs=legs, nv=1 << len(legs)))
         amp_rows.append(dict(am=am, x=ins[jx], pair=pair_index[key]))
-    # batches: pair objects in order of first use, packed into the scratch area; a batch closes at a
-    # pair boundary when the scratch area or the amplitude buffer (HP_NB rows) would overflow
-    scratch = hp_scratch()
-    NB = hp_batch_amps()
-    NCG = hp_colour_groups(ir)
+    assert all(pr["nv"] <= 32 for pr in pairs), "pair objects hold up to 32 helicity variants"
+
+    # batches: a batch closes at a pair boundary when the scratch area or the amplitude buffer (HP_NB rows)
+    # would overflow; pair objects of one kind together, so that the warps of a batch run the same routine
+    scratch = hp_config(ir, "SCRATCH")
+    NB = hp_config(ir, "NB")
+    NCG = hp_config(ir, "NCG")
+    PT = {"ROW": 0, "COL": 1, "CUR": 2, "VVV": 3, "VVVV": 4}
     by_pair = {}
     for k, r in enumerate(amp_rows):
         by_pair.setdefault(r["pair"], []).append(k)
-    PT = {"ROW": 0, "COL": 1, "CUR": 2, "VVV": 3, "VVVV": 4}
     batches, cur_pairs, cur_amps, fill = [], [], [], 0
-    # pair objects of one kind together: the warps of a batch then run the same routine for about the same time
     for pi in sorted(by_pair, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
         need = 4 * pairs[pi]["nv"]
         assert need <= scratch and len(by_pair[pi]) <= NB
@@ -352,54 +370,63 @@ def emit_hp(ir):
     prow = []
     for pr in pairs:
         rest = list(pr["rest"]) + [0] * (3 - len(pr["rest"]))
-        vm = [_vmap(pr["legs"], wfs[w]["legs"]) for w in pr["rest"]] + [0] * (3 - len(pr["rest"]))
+        vm = [vmask(pr["legs"], wfs[w]["legs"]) for w in pr["rest"]] + [0] * (3 - len(pr["rest"]))
         ioff = [wfs[w]["off"] for w in rest]
         inv = [wfs[w]["nv"] for w in rest]
         prow.append(f"{{{PT[pr['type']]}, {len(pr['rest'])}, {pr['coup']}, {pr['neg']}, {{{pr['term'][0]}, {pr['term'][1]}}}, "
                     f"{pr['nv']}, {pr.get('off', 0)}, {{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
-                    f"{{{vm[0]}ull, {vm[1]}ull, {vm[2]}ull}}}}")
-    NH = ir["ncomb"]
+                    f"{{{vm[0]}, {vm[1]}, {vm[2]}}}}}")
 
     def spread(legs, v):
-        """helicity-combination bits of variant v of an object over `legs` (ascending)"""
-        return sum(((v >> q) & 1) << l for q, l in enumerate(legs))
+        """helicity-combination bits (within the pass) of variant v of an object over `legs` (ascending)"""
+        return sum(((v >> q) & 1) << l for q, l in enumerate(legs) if l != LSTAR)
+
+    def vrange(legs, nv, p):
+        """variants of an object that pass p needs: the half with the pass leg's helicity = p, or all"""
+        if LSTAR is not None and LSTAR in legs:
+            return range(p * nv // 2, (p + 1) * nv // 2)   # the pass leg is the highest leg = top variant bit
+        return range(nv)
 
     # tensor-core tiles: amplitude(variant of Q, variant of x) = sum_k Q_k x_k is an (nvq x 4)(4 x nvx)
     # complex product; one work item = 8 variants of Q (rows) x 8 variants of x (columns)
     irow, trow, brow = [], [], []
     ncolor = len(ir["jamp"])
     NJ = -(-ncolor // NCG)
+    for p in range(NPASS):
+        for bi, (cur_pairs, cur_amps) in enumerate(batches):
+            ib, tb = len(irow), len(trow)
+            for pi in sorted(cur_pairs, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
+                for v in vrange(pairs[pi]["legs"], pairs[pi]["nv"], p):
+                    irow.append(f"{{{pi}, {v}}}")
+            for slot, k in enumerate(cur_amps):
+                r = amp_rows[k]
+                xw, pr = wfs[r["x"]], pairs[r["pair"]]
+                assert not set(xw["legs"]) & set(pr["legs"]) and len(xw["legs"]) + len(pr["legs"]) == n
+                qr, xr = vrange(pr["legs"], pr["nv"], p), vrange(xw["legs"], xw["nv"], p)
+                for q0 in range(qr.start, qr.stop, 8):
+                    for x0 in range(xr.start, xr.stop, 8):
+                        qv, xv = min(8, qr.stop - q0), min(8, xr.stop - x0)
+                        rowh = [spread(pr["legs"], q0 + i) if i < qv else 0 for i in range(8)]
+                        colh = [spread(xw["legs"], x0 + i) if i < xv else 0 for i in range(8)]
+                        trow.append(f"{{{pr['off']}, {xw['off'] + 2}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
+                                    f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
+            brow.append(f"{{{ib}, {len(irow)}, {tb}, {len(trow)}}}")
     jamp_cases = [[] for _ in range(NCG)]
     for bi, (cur_pairs, cur_amps) in enumerate(batches):
-        ib, tb = len(irow), len(trow)
-        for pi in sorted(cur_pairs, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
-            for v in range(pairs[pi]["nv"]):
-                irow.append(f"{{{pi}, {v}}}")
         upd = [[] for _ in range(NCG)]
         for slot, k in enumerate(cur_amps):
-            r = amp_rows[k]
-            xw, pr = wfs[r["x"]], pairs[r["pair"]]
-            assert not set(xw["legs"]) & set(pr["legs"]) and len(xw["legs"]) + len(pr["legs"]) == n
-            for q0 in range(0, pr["nv"], 8):
-                for x0 in range(0, xw["nv"], 8):
-                    qv, xv = min(8, pr["nv"] - q0), min(8, xw["nv"] - x0)
-                    rowh = [spread(pr["legs"], q0 + i) if i < qv else 0 for i in range(8)]
-                    colh = [spread(xw["legs"], x0 + i) if i < xv else 0 for i in range(8)]
-                    trow.append(f"{{{pr['off']}, {xw['off'] + 2}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
-                                f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
-            am = r["am"]
+            am = amp_rows[k]["am"]
             per_cg = [[] for _ in range(NCG)]
             for j, re, im in by_amp[am["call"]["amp"]]:
                 cg, jl = divmod(j, NJ)
                 per_cg[cg].append(_jamp_update(jl, re, im, "a").replace(f"J{jl} ", f"J[{jl}] "))
             for cg in range(NCG):
                 if per_cg[cg]:
-                    upd[cg].append(f"{{ const cxd a = ab[{slot * NH}]; " + " ".join(per_cg[cg]) + " }")
+                    upd[cg].append(f"{{ const cxd a = ab[{slot * NHP}]; " + " ".join(per_cg[cg]) + " }")
         for cg in range(NCG):
             jamp_cases[cg].append(f"      case {bi}: {{ " + "\n        ".join(upd[cg]) + " } break;")
-        brow.append(f"{{{ib}, {len(irow)}, {tb}, {len(trow)}}}")
-    tables += "\n" + both("mf::HpPair", "pairs", max(len(prow), 1), ",\n  ".join(prow) if prow else "{0}")
-    tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0}")
+    tables += "\n" + both("mf::HpPair", "pairs", max(len(prow), 1), ",\n  ".join(prow) if prow else "{0}", const=not big)
+    tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0}", const=not big)
     tables += "\n" + both("mf::HpTile", "tiles", max(len(trow), 1), ",\n  ".join(trow) if trow else "{0}", const=len(trow) * 32 <= 24576)
     tables += "\n" + both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}")
 
@@ -413,14 +440,34 @@ def emit_hp(ir):
         A.append("      break;")
     A.append("    default: break;")
     A.append("    }")
-    if NCG == 1:
+    unroll = len(used) <= HP_UNROLL_MAX_AMPS
+    cmode = "thread" if unroll else hp_colour_mode(ir, NCG)
+    ncp = -(-ncolor // 8) * 8
+    if cmode == "thread":
+        assert NCG == 1
         C = _emit_colour(ir, J=lambda i: f"J[{i}]")
+    elif cmode == "groups":
+        C = _emit_colour_groups(ir, NCG, NJ, NHP)
     else:
-        C = _emit_colour_groups(ir, NCG, NJ, NH)
+        C = "    return 0.0;  // not used: the colour contraction of this process is table driven (d_cfsym)"
+    cf, den = ir["color_num"], ir["color_denom"]
+    if cmode in ("mma", "loop"):
+        assert len(set(den)) == 1 and all(cf[i][j] == cf[j][i] for i in range(ncolor) for j in range(ncolor))
+        # block-symmetrised colour matrix: blocks of 8x8 colours; below the block diagonal 0, on it cf, above 2 cf
+        vals = []
+        for a_ in range(ncp):
+            for b_ in range(ncp):
+                v = 0
+                if a_ < ncolor and b_ < ncolor:
+                    v = cf[a_][b_] * (0 if b_ // 8 < a_ // 8 else (1 if b_ // 8 == a_ // 8 else 2))
+                vals.append(f"{float(v)!r}")
+        tables += "\n" + both("double", "cfsym", ncp * ncp, ", ".join(vals), const=False)
+    else:
+        tables += "\n" + both("double", "cfsym", 1, "0.0", const=False)
     # straight-line flavour of the same phase for short amplitude lists
     U = ["    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(len(ir["jamp"]))) + ";",
          "    cxd a[6], b[6], c[6], d[6];"]
-    if len(used) <= HP_UNROLL_MAX_AMPS:
+    if unroll:
         for am in used:
             c = am["call"]
             for q, w in enumerate(am["in"]):
@@ -435,12 +482,13 @@ def emit_hp(ir):
         U.append(_emit_colour(ir))
     else:
         U.append("    return 0.0;  // not used: the amplitudes of this process run on the tensor cores")
-    unroll = len(used) <= HP_UNROLL_MAX_AMPS
-    return tables, "\n".join(A), C, "\n".join(U), dict(wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items),
-                                         namps=len(used), unroll=unroll, nbatch=len(batches), npairs=len(pairs),
-                                         nitems_pair=len(irow), ntiles=len(trow), ncg=1 if unroll else NCG,
-                                         nb=max(len(b[1]) for b in batches) if batches else 1,
-                                         scratch=max(max((pairs[pi]["off"] + 4 * pairs[pi]["nv"] for pi in b[0]), default=0) for b in batches) if batches else 0)
+    return tables, "\n".join(A), C, "\n".join(U), dict(
+        wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items), namps=len(used), unroll=unroll,
+        nbatch=len(batches), npairs=len(pairs), nitems_pair=len(irow), ntiles=len(trow), ncg=1 if unroll else NCG,
+        npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
+        colour_denom=float(den[0]),
+        nb=max(len(b_[1]) for b_ in batches) if batches else 1,
+        scratch=max(max((pairs[pi]["off"] + 4 * pairs[pi]["nv"] for pi in b_[0]), default=0) for b_ in batches) if batches else 0)
 
 
 def _emit_colour_groups(ir, ncg, nj, nh):
@@ -521,10 +569,10 @@ def emit_process_source(ir, block=None, minblocks=None):
     hp_nb = 0 if hp['unroll'] else hp['nb']
     hp_ncg = hp['ncg']
     hp_nj = -(-ncolor // hp_ncg)
-    hp_e = hp_events_per_block(ir)
+    hp_e = hp_config(ir, "E")
     use_hp = "true" if use_hp_default(ir) else "false"
     has_thread = "true" if (len(ir["calls"]) <= THREAD_MAX_CALLS or os.environ.get("MADFLOW_B200_BUILD_THREAD") == "1") else "false"
-    hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = int(os.environ.get("MADFLOW_B200_HP_MINBLOCKS", 2)), hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
+    hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = hp_config(ir, "MINBLOCKS"), hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
     pnames = ", ".join(f'"{p}"' for p in ir["params"]) or '""'
     cnames = ", ".join(f'"{c}"' for c in ir["couplings"]) or '""'
     src = f"""// GENERATED by madflow_b200.codegen -- do not edit.  Process: {ir.get('process', ir['name'])}
@@ -574,15 +622,22 @@ struct Proc {{
   static constexpr int HP_E = {hp_e}, HP_MINBLOCKS = {hp_minblocks}, HP_WFSIZE = {hp_wfsize}, HP_MAXLEVEL = {hp_maxlevel};
   static constexpr int HP_NWF = {hp_nwf}, HP_NITEMS = {hp_nitems}, HP_NAMPS = {hp['namps']};
   static constexpr int HP_NBATCH = {hp['nbatch']}, HP_NPAIRS = {hp['npairs']}, HP_SCRATCH = {hp_scratch_n};
-  // tensor-core amplitude phase: HP_NB rows of NCOMB amplitudes per event and batch; the JAMPs of one
-  // helicity combination are spread over HP_NCG threads, HP_NJ colours each
+  // tensor-core amplitude phase: HP_NPASS helicity passes of HP_NHP combinations (the pass = the helicity of
+  // the last leg); HP_NB rows of HP_NHP amplitudes per event and batch; the JAMPs of one helicity
+  // combination are spread over HP_NCG threads, HP_NJ colours each
+  static constexpr int HP_NPASS = {hp['npass']}, HP_NHP = NCOMB / HP_NPASS;
   static constexpr int HP_NB = {hp_nb}, HP_NCG = {hp_ncg}, HP_NJ = {hp_nj}, HP_NTILES = {hp['ntiles']};
-  static constexpr int HP_THREADS = HP_E * NCOMB * HP_NCG;                 // threads per block
+  static constexpr int HP_THREADS = HP_E * HP_NHP * HP_NCG;                // threads per block
   static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 4)) // hp_e)};  // tile descriptors per warp and trip
+  // colour contraction: 0 in-thread, 1 generated code over colour groups, 2 tensor cores, 3 CUDA-core loop
+  // (2 and 3 read the block-symmetrised matrix d_cfsym and JAMP planes of HP_PLANE doubles per colour)
+  static constexpr int HP_COLOUR = {hp['cmode']}, HP_NCP = {hp['ncp']}, HP_PLANE = HP_NHP + 4;
+  static constexpr double HP_COLOUR_DENOM = {hp['colour_denom']!r};
   // shared-memory cxd per event: wavefunctions | pair objects | amplitude buffer (the last two double as the
   // JAMP exchange area of the colour groups)
-  static constexpr int HP_XCHG = HP_NCG > 1 ? NCOLOR * NCOMB : 0;
-  static constexpr int HP_EVSTRIDE = HP_WFSIZE + (HP_SCRATCH + HP_NB * NCOMB > HP_XCHG ? HP_SCRATCH + HP_NB * NCOMB : HP_XCHG);
+  static constexpr int HP_XCHG = HP_COLOUR >= 2 ? HP_NCP * HP_PLANE : (HP_NCG > 1 ? NCOLOR * HP_NHP : 0);
+  static constexpr int HP_EVSTRIDE = HP_WFSIZE + (HP_SCRATCH + HP_NB * HP_NHP > HP_XCHG ? HP_SCRATCH + HP_NB * HP_NHP : HP_XCHG);
+  MF_DEV static const double* cfsym() {{ return MF_TAB(cfsym); }}
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
   MF_DEV static mf::HpItem item(int i) {{ return MF_TAB(items)[i]; }}
@@ -592,11 +647,11 @@ struct Proc {{
   MF_DEV static mf::HpPairItem pair_item(int i) {{ return MF_TAB(pair_items)[i]; }}
   MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
   // JAMP updates of batch `b` for colour group `cg` (warp-uniform switches): ab = the event's amplitude
-  // buffer at this thread's helicity combination, row r at ab[r * NCOMB]; JAMP registers addressed statically
+  // buffer at this thread's helicity combination, row r at ab[r * HP_NHP]; JAMP registers addressed statically
   MF_DEV static void jamp_batch(int b, int cg, const cxd* ab, cxd (&J)[HP_NJ]) {{
 {hp_jamp}
   }}
-  // colour quadratic form; with HP_NCG > 1 the other groups' JAMPs are read from jb[colour * NCOMB]
+  // colour quadratic form (HP_COLOUR 0 / 1); the other groups' JAMPs are read from jb[colour * HP_NHP]
   MF_DEV static double colour_sum(int cg, const cxd (&J)[HP_NJ], const cxd* jb) {{
 {hp_colour}
   }}
@@ -605,7 +660,7 @@ struct Proc {{
 
   // Matrix_{_cname(ir)}.matrix for helicity row `icomb`
   MF_DEV static double matrix(const double (*p)[4], int icomb, const double* par, const cxd* coup, double sqh) {{
-{emit_matrix_body(ir)}
+{emit_matrix_body(ir) if len(ir["calls"]) <= STRAIGHT_LINE_MAX_CALLS else "    return 0.0 / 0.0;  // not emitted: the straight-line form of this process is too long to be useful"}
   }}
 }};
 

@@ -23,7 +23,7 @@
 //             reduction per event.
 //
 // Shared memory: every event of the block owns HP_EVSTRIDE cxd (= 16 bytes): HP_WFSIZE of
-// wavefunctions, HP_SCRATCH of pair objects, HP_NB * NCOMB of amplitudes.  Wavefunction w lives at
+// wavefunctions, HP_SCRATCH of pair objects, HP_NB * HP_NHP of amplitudes.  Wavefunction w lives at
 // offset P::wf(w).off of its event's area:
 //   [ 0..1 ]              momentum slots w0, w1  (helicity independent)
 //   [ 2 + hp_slot(k,nv,v) ]  component k = 0..3 (HELAS slots 2..5), helicity variant v < nv = 2^|S|
@@ -73,7 +73,7 @@ struct HpPair {
   unsigned short off;          // offset in the event's scratch area (cxd)
   unsigned short in_off[3];    // inputs: offset of the wavefunction block in the event's area
   unsigned short in_nv[3];
-  unsigned long long vmap[3];  // 4 bits per output variant: the input's variant index
+  unsigned char vmask[3];      // bits of the object's variant index that form the input's variant index
 };
 
 struct HpPairItem {
@@ -92,8 +92,8 @@ struct alignas(16) HpTile {
   unsigned char rowh[8], colh[8];
 };
 
-struct HpBatch {
-  unsigned short item_begin, item_end, tile_begin, tile_end;
+struct HpBatch {   // one (helicity pass, batch): its pair-object work items and its tiles
+  int item_begin, item_end, tile_begin, tile_end;
 };
 
 struct HpItem {
@@ -102,7 +102,7 @@ struct HpItem {
   unsigned char coup, coup_neg;
   unsigned short out_off, out_nv;    // output wavefunction block (offset in the event's area, variants)
   unsigned short in_off[3], in_nv[3];
-  unsigned long long vmap[3];        // 4 bits per output variant: the input's variant index
+  unsigned char vmask[3];            // bits of the output's variant index that form the input's variant index
 };
 
 // phase 1: work item `it` in [0, NEXT*E*2) = (leg, event, helicity)
@@ -130,6 +130,18 @@ MF_DEV void hp_externals(int it, int E, const double* mom /*[E][NEXT][4]*/, cons
 // (8 lanes = 3 arbitrary helicity bits) over the banks
 MF_DEV int hp_abuf_pos(int h) { return h ^ ((h >> 3) & 7); }
 
+// the input's helicity variant for output variant v: the bits of v selected by `mask`, packed
+MF_DEV int hp_pext(int v, int mask) {
+  int out = 0, pos = 0;
+#pragma unroll
+  for (int b = 0; b < 5; ++b)
+    if (mask & (1 << b)) {
+      out |= ((v >> b) & 1) << pos;
+      ++pos;
+    }
+  return out;
+}
+
 // position of (component k, helicity variant v) inside an object of nv variants (see the header)
 MF_DEV int hp_slot(int k, int nv, int v) { return k * nv + (v ^ ((2 * k) & (nv - 1))); }
 
@@ -145,9 +157,9 @@ template <class P>
 MF_DEV void hp_current(int idx, int v, const double* par, const cxd* coup_e, cxd* wf_e) {
   const HpItem it = P::item(idx);
   cxd a[6], b[6], c[6], r[6];
-  hp_load(wf_e + it.in_off[0], it.in_nv[0], (int)((it.vmap[0] >> (4 * v)) & 15ull), a);
-  hp_load(wf_e + it.in_off[1], it.in_nv[1], (int)((it.vmap[1] >> (4 * v)) & 15ull), b);
-  if (it.nin > 2) hp_load(wf_e + it.in_off[2], it.in_nv[2], (int)((it.vmap[2] >> (4 * v)) & 15ull), c);
+  hp_load(wf_e + it.in_off[0], it.in_nv[0], hp_pext(v, it.vmask[0]), a);
+  hp_load(wf_e + it.in_off[1], it.in_nv[1], hp_pext(v, it.vmask[1]), b);
+  if (it.nin > 2) hp_load(wf_e + it.in_off[2], it.in_nv[2], hp_pext(v, it.vmask[2]), c);
   cxd cp = coup_e[it.coup];
   if (it.coup_neg) cp = -cp;
   const double M = it.mass_idx < 0 ? 0.0 : par[it.mass_idx];
@@ -194,8 +206,8 @@ template <class P>
 MF_DEV void hp_pair(int pi, int v, const cxd* coup_e, const cxd* wf_e, cxd* scratch_e) {
   const HpPair pr = P::pair(pi);
   cxd a[6], b[6], c[6];
-  hp_load(wf_e + pr.in_off[0], pr.in_nv[0], (int)((pr.vmap[0] >> (4 * v)) & 15ull), a);
-  hp_load(wf_e + pr.in_off[1], pr.in_nv[1], (int)((pr.vmap[1] >> (4 * v)) & 15ull), b);
+  hp_load(wf_e + pr.in_off[0], pr.in_nv[0], hp_pext(v, pr.vmask[0]), a);
+  hp_load(wf_e + pr.in_off[1], pr.in_nv[1], hp_pext(v, pr.vmask[1]), b);
   cxd cp = coup_e[pr.coup];
   if (pr.coup_neg) cp = -cp;
   const cxd f = mul_mi(cp);  // -i * COUP
@@ -234,7 +246,7 @@ MF_DEV void hp_pair(int pi, int v, const cxd* coup_e, const cxd* wf_e, cxd* scra
       Q[0] = f * K0, Q[1] = -(f * K1), Q[2] = -(f * K2), Q[3] = -(f * K3);
     } break;
     default: {  // HP_Q_VVVV: K = sum_t sign_t * in[vec_t] * (in[dotA_t] . in[dotB_t])
-      hp_load(wf_e + pr.in_off[2], pr.in_nv[2], (int)((pr.vmap[2] >> (4 * v)) & 15ull), c);
+      hp_load(wf_e + pr.in_off[2], pr.in_nv[2], hp_pext(v, pr.vmask[2]), c);
       // the three Minkowski products once; each term picks one of them and one vector (block-uniform)
       const cxd d01 = vdot(a, b), d02 = vdot(a, c), d12 = vdot(b, c);
       cxd K[4] = {mk(0, 0), mk(0, 0), mk(0, 0), mk(0, 0)};
@@ -314,8 +326,8 @@ __device__ __forceinline__ void hp_mma_tiles(const HpTileWords (&tile)[NT], int 
     xi[t] = evs + 16u * (x + hp_slot(k, xnv, (x0 + r) & (xnv - 1)));
     const int hq = (((r & 4) ? w1.y : w1.x) >> (8 * (r & 3))) & 0xff;
     const unsigned hc = (((k & 2) ? w1.w : w1.z) >> (16 * (k & 1))) & 0xffff;
-    d0[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::NCOMB + hp_abuf_pos(hq | (hc & 0xff)));
-    d1[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::NCOMB + hp_abuf_pos(hq | (hc >> 8)));
+    d0[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::HP_NHP + hp_abuf_pos(hq | (hc & 0xff)));
+    d1[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::HP_NHP + hp_abuf_pos(hq | (hc >> 8)));
     s0[t] = r < qvalid && 2 * k < xvalid, s1[t] = r < qvalid && 2 * k + 1 < xvalid;
   }
   cxd qa[NT][E], xb[NT][E];
@@ -356,7 +368,7 @@ inline void hp_mma_tile_host(const HpTile* tp, const cxd* wf_e, const cxd* scrat
       cxd amp = mk(0.0, 0.0);
       for (int k = 0; k < 4; ++k)
         amp = fma_c(scratch_e[tp->q + hp_slot(k, tp->qnv, tp->q0 + r)], wf_e[tp->x + hp_slot(k, tp->xnv, tp->x0 + c)], amp);
-      abuf_e[tp->slot * P::NCOMB + hp_abuf_pos(tp->rowh[r] | tp->colh[c])] = amp;
+      abuf_e[tp->slot * P::HP_NHP + hp_abuf_pos(tp->rowh[r] | tp->colh[c])] = amp;
     }
 }
 
@@ -379,15 +391,76 @@ __device__ unsigned long long g_hp_prof[8];
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// Table-driven colour contraction  sum_ab J_a* cf_ab J_b  of one helicity pass.  The JAMPs of the pass sit in
+// shared memory as two planes (Re, Im) of HP_NCP rows (colours, padded to a multiple of 8) x HP_PLANE doubles
+// (helicity combinations + 4: the row stride = 4 mod 16 keeps the tensor-core fragment loads conflict free).
+// cfsym is the colour matrix symmetrised in 8x8 blocks (0 below the block diagonal, cf on it, 2 cf above), so
+// that  sum_ab J_a cf_ab J_b = sum_a J_a (cfsym J)_a  with about half the products.
+//
+// Tensor-core flavour: a warp owns (plane, 8 helicity combinations) = one column tile of the HP_NCP x (2 HP_NHP)
+// matrix Z = cfsym [Re J | Im J]; its B fragments (all colours of its columns) stay in registers, the A
+// fragments (cfsym, the same for every block and event) come through L1, each 8x8 tile of Z costs up to
+// HP_NCP/4 mma.sync.m8n8k4.f64 and is contracted with J on the spot.
+template <class P>
+__device__ __forceinline__ double hp_colour_mma(const double* planes /* shared: [2][NCP][PLANE] */, int tid, int only_hl) {
+  constexpr int NCP = P::HP_NCP, PL = P::HP_PLANE, NHP = P::HP_NHP, T = P::HP_THREADS;
+  constexpr int NKK = NCP / 4, NU = 2 * (NHP / 8);
+  const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, k = lane & 3;
+  const double* cf = P::cfsym();
+  double me = 0.0;
+#pragma unroll 1
+  for (int u = warp; u < NU; u += T / 32) {
+    const int pl = u / (NHP / 8), j = u - pl * (NHP / 8);
+    const double* plane = planes + pl * NCP * PL;
+    double B[NKK];
+#pragma unroll
+    for (int kk = 0; kk < NKK; ++kk) B[kk] = plane[(4 * kk + k) * PL + 8 * j + r];
+    const int h0 = 8 * j + 2 * k;
+    const bool keep0 = only_hl < 0 || only_hl == h0, keep1 = only_hl < 0 || only_hl == h0 + 1;
+#pragma unroll 1
+    for (int i = 0; i < NCP / 8; ++i) {
+      double c0 = 0.0, c1 = 0.0;
+      const double* arow = cf + (8 * i + r) * NCP + k;
+#pragma unroll
+      for (int kk = 0; kk < NKK; ++kk)
+        if (kk >= 2 * i) dmma_m8n8k4(c0, c1, __ldg(arow + 4 * kk), B[kk]);
+      const double* jr = plane + (8 * i + r) * PL + h0;
+      if (keep0) me += jr[0] * c0;
+      if (keep1) me += jr[1] * c1;
+    }
+  }
+  return me / P::HP_COLOUR_DENOM;
+}
+
+// CUDA-core flavour of the same contraction (the A/B partner of hp_colour_mma): thread (helicity combination,
+// colour group) takes the rows of its own colours
+template <class P>
+MF_DEV double hp_colour_loop(const double* planes, int hl, int cg, const double* cf) {
+  constexpr int NCP = P::HP_NCP, PL = P::HP_PLANE;
+  double me = 0.0;
+  const int lo = cg * P::HP_NJ, hi = (lo + P::HP_NJ < P::NCOLOR) ? lo + P::HP_NJ : P::NCOLOR;
+  for (int a = lo; a < hi; ++a) {
+    double tr = 0.0, ti = 0.0;
+    for (int b = 8 * (a / 8); b < NCP; ++b) {
+      const double w = cf[a * NCP + b];
+      tr += w * planes[b * PL + hl];
+      ti += w * planes[(NCP + b) * PL + hl];
+    }
+    me += planes[a * PL + hl] * tr + planes[(NCP + a) * PL + hl] * ti;
+  }
+  return me / P::HP_COLOUR_DENOM;
+}
+
+// ------------------------------------------------------------------------------------------------
 // The E-event matrix-element evaluation used by both kernels.  `mom` [E][NEXT][4], `coup` [E][NCOUP]
 // and the event areas `ev` [E][HP_EVSTRIDE] live in shared memory; returns, in the first thread of
 // every event, the event's |M|^2 summed over helicities and colours and averaged (other threads
-// return garbage).  Thread tid = (e * HP_NCG + colour group) * NCOMB + helicity combination.
+// return garbage).  Thread tid = (e * HP_NCG + colour group) * HP_NHP + helicity combination of the pass.
 template <class P>
 __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events */, const double* mom,
                                                    const cxd* coup, const double* par, double sqh, cxd* ev,
                                                    const unsigned char* vtab, double* red /* [T/32] */, int only_h) {
-  constexpr int E = P::HP_E, NH = P::NCOMB, NCG = P::HP_NCG, TE = NH * NCG, T = E * TE, EVS = P::HP_EVSTRIDE;
+  constexpr int E = P::HP_E, NHP = P::HP_NHP, NCG = P::HP_NCG, TE = NHP * NCG, T = E * TE, EVS = P::HP_EVSTRIDE;
   const int tid = threadIdx.x;
   MF_PROF_DECL
   if constexpr (2 * E <= 32 && P::NEXT <= 32) {
@@ -419,71 +492,104 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
     __syncthreads();
   }
   MF_PROF(1);
-  const int e = tid / TE, rr = tid - e * TE, cg = rr / NH, h = rr - cg * NH;
+  const int e = tid / TE, rr = tid - e * TE, cg = rr / NHP, h = rr - cg * NHP;
   const cxd* wf_e = ev + e * EVS;
-  double me;
+  double me = 0.0;
   if constexpr (P::HP_UNROLL) {
     // short amplitude lists: straight-line code, whole vertices per helicity combination
     me = P::hp_amps_unrolled(wf_e, vtab, h, coup + e * P::NCOUP);
+    if (only_h >= 0) me = (h == only_h) ? me : 0.0;
   } else {
     cxd* abuf_h = ev + e * EVS + P::HP_WFSIZE + P::HP_SCRATCH + hp_abuf_pos(h);
-    cxd J[P::HP_NJ];
-#pragma unroll
-    for (int j = 0; j < P::HP_NJ; ++j) J[j] = mk(0.0, 0.0);
     const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
-    for (int bi = 0; bi < P::HP_NBATCH; ++bi) {
-      const HpBatch bt = P::batch(bi);
-      const int total = (bt.item_end - bt.item_begin) * E;
+    for (int pass = 0; pass < P::HP_NPASS; ++pass) {
+      cxd J[P::HP_NJ];
+#pragma unroll
+      for (int j = 0; j < P::HP_NJ; ++j) J[j] = mk(0.0, 0.0);
 #pragma unroll 1
-      for (int w = tid; w < total; w += T) {
-        const int ii = w / E, ee = w - ii * E;
-        const HpPairItem pit = P::pair_item(bt.item_begin + ii);
-        hp_pair<P>(pit.pair, pit.v, coup + ee * P::NCOUP, ev + ee * EVS, ev + ee * EVS + P::HP_WFSIZE);
-      }
-      __syncthreads();
-      MF_PROF(2);
-      {
-        // every warp takes MT tiles per trip; an index past the end repeats the batch's last tile
-        // (same values stored twice) so that the trips stay straight-line
-        constexpr int NW = T / 32, MT = P::HP_TILES_IN_FLIGHT;
-        const unsigned evs = (unsigned)__cvta_generic_to_shared(ev);
-        const int last = bt.tile_end - 1;
-        // the descriptors of the next trip are fetched while the current trip computes
-        HpTileWords cur[MT], nxt[MT];
-        int w = bt.tile_begin + warp;
-#pragma unroll
-        for (int t = 0; t < MT; ++t) cur[t] = hp_tile_words(P::tile(w + t * NW < last ? w + t * NW : last));
+      for (int bi = 0; bi < P::HP_NBATCH; ++bi) {
+        const HpBatch bt = P::batch(pass * P::HP_NBATCH + bi);
+        const int total = (bt.item_end - bt.item_begin) * E;
 #pragma unroll 1
-        for (; w < bt.tile_end; w += MT * NW) {
-          const int wn = w + MT * NW;
-#pragma unroll
-          for (int t = 0; t < MT; ++t) nxt[t] = hp_tile_words(P::tile(wn + t * NW < last ? wn + t * NW : last));
-          hp_mma_tiles<P, MT>(cur, lane, evs);
-#pragma unroll
-          for (int t = 0; t < MT; ++t) cur[t] = nxt[t];
+        for (int w = tid; w < total; w += T) {
+          const int ii = w / E, ee = w - ii * E;
+          const HpPairItem pit = P::pair_item(bt.item_begin + ii);
+          hp_pair<P>(pit.pair, pit.v, coup + ee * P::NCOUP, ev + ee * EVS, ev + ee * EVS + P::HP_WFSIZE);
         }
-      }
-      __syncthreads();
-      MF_PROF(3);
-      P::jamp_batch(bi, cg, abuf_h, J);
-      MF_PROF(4);
-    }
-    if constexpr (NCG > 1) {
-      // exchange the JAMPs of the colour groups through the (now free) scratch + amplitude buffer area
-      static_assert(P::HP_EVSTRIDE - P::HP_WFSIZE >= P::NCOLOR * NH, "JAMP exchange area too small");
-      cxd* jb = ev + e * EVS + P::HP_WFSIZE + h;
-      __syncthreads();
+        __syncthreads();
+        MF_PROF(2);
+        {
+          // every warp takes MT tiles per trip; an index past the end repeats the batch's last tile
+          // (same values stored twice) so that the trips stay straight-line
+          constexpr int NW = T / 32, MT = P::HP_TILES_IN_FLIGHT;
+          const unsigned evs = (unsigned)__cvta_generic_to_shared(ev);
+          const int last = bt.tile_end - 1;
+          // the descriptors of the next trip are fetched while the current trip computes
+          HpTileWords cur[MT], nxt[MT];
+          int w = bt.tile_begin + warp;
 #pragma unroll
-      for (int j = 0; j < P::HP_NJ; ++j)
-        if (cg * P::HP_NJ + j < P::NCOLOR) jb[(cg * P::HP_NJ + j) * NH] = J[j];
-      __syncthreads();
-      me = P::colour_sum(cg, J, jb);
-    } else {
-      me = P::colour_sum(0, J, nullptr);
+          for (int t = 0; t < MT; ++t) cur[t] = hp_tile_words(P::tile(w + t * NW < last ? w + t * NW : last));
+#pragma unroll 1
+          for (; w < bt.tile_end; w += MT * NW) {
+            const int wn = w + MT * NW;
+#pragma unroll
+            for (int t = 0; t < MT; ++t) nxt[t] = hp_tile_words(P::tile(wn + t * NW < last ? wn + t * NW : last));
+            hp_mma_tiles<P, MT>(cur, lane, evs);
+#pragma unroll
+            for (int t = 0; t < MT; ++t) cur[t] = nxt[t];
+          }
+        }
+        __syncthreads();
+        MF_PROF(3);
+        P::jamp_batch(bi, cg, abuf_h, J);
+        MF_PROF(4);
+      }
+      // the helicity combination of this thread within the whole table, and the row asked for (if any)
+      const int hfull = pass * NHP + h;
+      const int only_hl = only_h < 0 ? -1 : (only_h / NHP == pass ? only_h % NHP : NHP);  // NHP: none in this pass
+      if constexpr (P::HP_COLOUR == 0) {
+        const double m = P::colour_sum(0, J, nullptr);
+        me += (only_h < 0 || hfull == only_h) ? m : 0.0;
+      } else if constexpr (P::HP_COLOUR == 1) {
+        // exchange the JAMPs of the colour groups through the (now free) scratch + amplitude buffer area
+        static_assert(P::HP_EVSTRIDE - P::HP_WFSIZE >= P::NCOLOR * NHP, "JAMP exchange area too small");
+        cxd* jb = ev + e * EVS + P::HP_WFSIZE + h;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < P::HP_NJ; ++j)
+          if (cg * P::HP_NJ + j < P::NCOLOR) jb[(cg * P::HP_NJ + j) * NHP] = J[j];
+        __syncthreads();
+        const double m = P::colour_sum(cg, J, jb);
+        me += (only_h < 0 || hfull == only_h) ? m : 0.0;
+        if (pass + 1 < P::HP_NPASS) __syncthreads();  // the next pass overwrites the exchange area
+      } else {
+        static_assert(P::HP_EVSTRIDE - P::HP_WFSIZE >= P::HP_NCP * P::HP_PLANE, "JAMP exchange area too small");
+        static_assert(E == 1 || P::HP_COLOUR == 3, "the tensor-core colour contraction handles one event per block");
+        double* planes = reinterpret_cast<double*>(ev + e * EVS + P::HP_WFSIZE);
+        constexpr int NCP = P::HP_NCP, PL = P::HP_PLANE;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < P::HP_NJ; ++j)
+          if (cg * P::HP_NJ + j < P::NCOLOR) {
+            planes[(cg * P::HP_NJ + j) * PL + h] = J[j].re;
+            planes[(NCP + cg * P::HP_NJ + j) * PL + h] = J[j].im;
+          }
+        for (int i = P::NCOLOR * NHP + rr; i < NCP * NHP; i += TE) {  // zero the padding colours
+          planes[(i / NHP) * PL + i % NHP] = 0.0;
+          planes[(NCP + i / NHP) * PL + i % NHP] = 0.0;
+        }
+        __syncthreads();
+        if constexpr (P::HP_COLOUR == 2) {
+          me += hp_colour_mma<P>(planes, tid, only_hl);
+        } else {
+          const double m = hp_colour_loop<P>(planes, h, cg, P::cfsym());
+          me += (only_h < 0 || hfull == only_h) ? m : 0.0;
+        }
+        if (pass + 1 < P::HP_NPASS) __syncthreads();
+      }
     }
   }
-  if (only_h >= 0) me = (h == only_h) ? me : 0.0;
   if (e >= nev) me = 0.0;
   // sum over the helicities (and colour groups) of one event
   constexpr int W = TE < 32 ? TE : 32;
@@ -505,7 +611,7 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
 
 template <class P>
 struct HpSmatrixSmem {
-  static constexpr int E = P::HP_E, T = E * P::NCOMB * P::HP_NCG;
+  static constexpr int E = P::HP_E, T = P::HP_THREADS;
   double mom[E * P::NEXT * 4];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
   double red[T / 32 + 1];
@@ -514,8 +620,8 @@ struct HpSmatrixSmem {
 };
 
 template <class P>
-__global__ void __launch_bounds__(P::HP_E* P::NCOMB* P::HP_NCG, P::HP_MINBLOCKS) smatrix_kernel_hp(const SmatrixArgs a) {
-  constexpr int E = P::HP_E, NH = P::NCOMB, TE = NH * P::HP_NCG, T = E * TE;
+__global__ void __launch_bounds__(P::HP_THREADS, P::HP_MINBLOCKS) smatrix_kernel_hp(const SmatrixArgs a) {
+  constexpr int E = P::HP_E, TE = P::HP_NHP * P::HP_NCG, T = E * TE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HpSmatrixSmem<P>& s = *reinterpret_cast<HpSmatrixSmem<P>*>(smem_raw);
   cxd* evarea = reinterpret_cast<cxd*>(smem_raw + ((sizeof(HpSmatrixSmem<P>) + 15) / 16) * 16);

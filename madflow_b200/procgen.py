@@ -519,4 +519,4 @@ def generate_ir(n_final_gluons, name=None, root="centroid"):
 
 def builtin_irs():
     """Processes compiled into the package besides the pinned g g > t t~."""
-    return [generate_ir(1), generate_ir(2)]
+    return [generate_ir(1), generate_ir(2), generate_ir(3)]

@@ -63,39 +63,62 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
         for (int h = 0; h < NH; ++h)
           me_h[e * NH + h] = Proc::hp_amps_unrolled(evarea.data() + e * EVS, vtab.data(), h, cp.data() + e * Proc::NCOUP);
     } else {
-      // "thread" t = (e * NCG + cg) * NH + h owns HP_NJ JAMPs
-      constexpr int NJ = Proc::HP_NJ, T = E * NCG * NH;
-      std::vector<cxd> J((size_t)T * NJ, mk(0.0, 0.0));
-      for (int bi = 0; bi < Proc::HP_NBATCH; ++bi) {
-        const mf::HpBatch bt = Proc::batch(bi);
-        for (int w = 0; w < (bt.item_end - bt.item_begin) * E; ++w) {
-          const int ii = w / E, ee = w - ii * E;
-          const mf::HpPairItem pit = Proc::pair_item(bt.item_begin + ii);
-          mf::hp_pair<Proc>(pit.pair, pit.v, cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS,
-                            evarea.data() + ee * EVS + Proc::HP_WFSIZE);
+      // "thread" t = (e * NCG + cg) * NHP + h owns HP_NJ JAMPs; one helicity pass after the other
+      constexpr int NJ = Proc::HP_NJ, NHP = Proc::HP_NHP, T = E * NCG * NHP;
+      for (int pass = 0; pass < Proc::HP_NPASS; ++pass) {
+        std::vector<cxd> J((size_t)T * NJ, mk(0.0, 0.0));
+        for (int bi = 0; bi < Proc::HP_NBATCH; ++bi) {
+          const mf::HpBatch bt = Proc::batch(pass * Proc::HP_NBATCH + bi);
+          for (int w = 0; w < (bt.item_end - bt.item_begin) * E; ++w) {
+            const int ii = w / E, ee = w - ii * E;
+            const mf::HpPairItem pit = Proc::pair_item(bt.item_begin + ii);
+            mf::hp_pair<Proc>(pit.pair, pit.v, cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS,
+                              evarea.data() + ee * EVS + Proc::HP_WFSIZE);
+          }
+          for (int w = 0; w < (bt.tile_end - bt.tile_begin) * E; ++w) {
+            const int ti = w / E, ee = w - ti * E;
+            cxd* a_e = evarea.data() + ee * EVS;
+            mf::hp_mma_tile_host<Proc>(Proc::tile(bt.tile_begin + ti), a_e, a_e + Proc::HP_WFSIZE,
+                                       a_e + Proc::HP_WFSIZE + Proc::HP_SCRATCH);
+          }
+          for (int t = 0; t < T; ++t) {
+            const int e = t / (NCG * NHP), cg = (t / NHP) % NCG, h = t % NHP;
+            cxd(&Jt)[NJ] = *reinterpret_cast<cxd(*)[NJ]>(&J[(size_t)t * NJ]);
+            Proc::jamp_batch(bi, cg, evarea.data() + e * EVS + Proc::HP_WFSIZE + Proc::HP_SCRATCH + mf::hp_abuf_pos(h), Jt);
+          }
         }
-        for (int w = 0; w < (bt.tile_end - bt.tile_begin) * E; ++w) {
-          const int ti = w / E, ee = w - ti * E;
-          cxd* a_e = evarea.data() + ee * EVS;
-          mf::hp_mma_tile_host<Proc>(Proc::tile(bt.tile_begin + ti), a_e, a_e + Proc::HP_WFSIZE,
-                                     a_e + Proc::HP_WFSIZE + Proc::HP_SCRATCH);
+        if (Proc::HP_COLOUR == 1)
+          for (int t = 0; t < T; ++t) {
+            const int e = t / (NCG * NHP), cg = (t / NHP) % NCG, h = t % NHP;
+            for (int j = 0; j < NJ; ++j)
+              if (cg * NJ + j < Proc::NCOLOR) evarea[(size_t)e * EVS + Proc::HP_WFSIZE + h + (cg * NJ + j) * NHP] = J[(size_t)t * NJ + j];
+          }
+        if (Proc::HP_COLOUR >= 2) {
+          constexpr int NCP = Proc::HP_NCP, PL = Proc::HP_PLANE;
+          for (int e = 0; e < E; ++e) {
+            double* planes = reinterpret_cast<double*>(evarea.data() + (size_t)e * EVS + Proc::HP_WFSIZE);
+            for (int i = 0; i < 2 * NCP * PL; ++i) planes[i] = 0.0;
+          }
+          for (int t = 0; t < T; ++t) {
+            const int e = t / (NCG * NHP), cg = (t / NHP) % NCG, h = t % NHP;
+            double* planes = reinterpret_cast<double*>(evarea.data() + (size_t)e * EVS + Proc::HP_WFSIZE);
+            for (int j = 0; j < NJ; ++j)
+              if (cg * NJ + j < Proc::NCOLOR) {
+                planes[(cg * NJ + j) * PL + h] = J[(size_t)t * NJ + j].re;
+                planes[(NCP + cg * NJ + j) * PL + h] = J[(size_t)t * NJ + j].im;
+              }
+          }
         }
         for (int t = 0; t < T; ++t) {
-          const int e = t / (NCG * NH), cg = (t / NH) % NCG, h = t % NH;
+          const int e = t / (NCG * NHP), cg = (t / NHP) % NCG, h = t % NHP;
           cxd(&Jt)[NJ] = *reinterpret_cast<cxd(*)[NJ]>(&J[(size_t)t * NJ]);
-          Proc::jamp_batch(bi, cg, evarea.data() + e * EVS + Proc::HP_WFSIZE + Proc::HP_SCRATCH + mf::hp_abuf_pos(h), Jt);
+          double m;
+          if (Proc::HP_COLOUR >= 2)  // both table-driven flavours compute sum_a J_a (cfsym J)_a
+            m = mf::hp_colour_loop<Proc>(reinterpret_cast<const double*>(evarea.data() + (size_t)e * EVS + Proc::HP_WFSIZE), h, cg, Proc::cfsym());
+          else
+            m = Proc::colour_sum(cg, Jt, evarea.data() + e * EVS + Proc::HP_WFSIZE + h);
+          me_h[e * NH + pass * NHP + h] += m;
         }
-      }
-      if (NCG > 1)
-        for (int t = 0; t < T; ++t) {
-          const int e = t / (NCG * NH), cg = (t / NH) % NCG, h = t % NH;
-          for (int j = 0; j < NJ; ++j)
-            if (cg * NJ + j < Proc::NCOLOR) evarea[(size_t)e * EVS + Proc::HP_WFSIZE + h + (cg * NJ + j) * NH] = J[(size_t)t * NJ + j];
-        }
-      for (int t = 0; t < T; ++t) {
-        const int e = t / (NCG * NH), cg = (t / NH) % NCG, h = t % NH;
-        cxd(&Jt)[NJ] = *reinterpret_cast<cxd(*)[NJ]>(&J[(size_t)t * NJ]);
-        me_h[e * NH + h] += Proc::colour_sum(cg, Jt, evarea.data() + e * EVS + Proc::HP_WFSIZE + h);
       }
     }
     for (int e = 0; e < nev; ++e) {
