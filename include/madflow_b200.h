@@ -83,6 +83,24 @@ int mf_vegas_reduce(const double* d_partial, int nblocks, int ndim, int add, dou
 /* Lepage refinement (alpha = 1.5) of d_grid in place from the histogram in d_sums[4:]             */
 int mf_vegas_refine(double* d_grid, const double* d_sums, int ndim, void* stream);
 
+/* ---- event output (python_package/madflow/lhe_writer.py:151-239, example/compare_mg5_hists.py:16-57) ----
+ * The events are the slots of an event buffer in device memory: momenta d_mom (nevt, nexternal, 4) and a
+ * weight per slot = d_w1[i] * d_w2[i] (d_w2 may be NULL); slots of weight 0 (cut events, padding) are ignored.
+ * mfp_integrand_events() of a process library exposes the buffer of the last integrand call.
+ *
+ * histogram: d_hist[nbins + 2] += weights, [0] underflow, [nbins + 1] overflow (and NaN); `observable` of
+ * particle `particle`: 0 pt, 1 pseudorapidity, 2 rapidity, 3 energy, 4 invariant mass.                     */
+int mf_event_histogram(const double* d_mom, const double* d_w1, const double* d_w2, int64_t nevt, int nexternal,
+                       int particle, int observable, double lo, double hi, int nbins, double* d_hist, void* stream);
+/* *d_max = max(*d_max, max |weight|)                                                                       */
+int mf_max_weight(const double* d_w1, const double* d_w2, int64_t nevt, double* d_max, void* stream);
+/* unweighting + compaction: slot i is kept with probability |w_i| / wmax (Philox: key seed, counter
+ * first_index + i) and appended -- momenta, weight sign(w) * max(|w|, wmax), global index first_index + i --
+ * at position (*d_count)++ of the output arrays (capacity slots; *d_count keeps counting past it).        */
+int mf_select_events(const double* d_mom, const double* d_w1, const double* d_w2, int64_t nevt, int nexternal, double wmax,
+                     uint64_t seed, uint64_t first_index, double* d_out_mom, double* d_out_w, int64_t* d_out_index,
+                     int32_t* d_count, int64_t capacity, void* stream);
+
 /* ---- measurement -------------------------------------------------------------------------------
  * FP64 FMA throughput of the current device, measured: `iters` dependent DFMA per chain, 8 chains
  * per thread, full grid.  Synchronous.  Returns TFLOP/s in *tflops (2 flop per DFMA).            */

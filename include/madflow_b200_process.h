@@ -111,6 +111,20 @@ int64_t mfp_integrand_workspace(int64_t nevents);
  * block partial sums of xjac*f, (xjac*f)^2 and the per-dimension histogram of (xjac*f)^2.      */
 int mfp_integrand(const mfp_integrand_args* args, void* stream);
 
+/* The events of the LAST mfp_integrand call on this workspace (helicity-parallel flavour): the slots
+ * that reached the matrix element, grouped in segments; slots of weight 0 are padding.  The integrand value
+ * of slot i is d_me[i] * d_weight[i].  What the reference passes to its LHE writer from inside the integrand
+ * (scripts/madflow_exec.py:462-464: all_ps and weight * ret).  Returns -2 for the one-event-per-thread
+ * flavour, whose single kernel keeps the events on chip.                                                   */
+typedef struct mfp_event_view {
+  const double* d_mom;      /* (capacity, nexternal, 4) momenta the matrix element was evaluated on       */
+  const double* d_weight;   /* (capacity) xjac * phase-space weight (0 = empty slot)                       */
+  const double* d_me;       /* (capacity) |M|^2                                                             */
+  const double* d_alpha_s;  /* (capacity) alpha_s of the event                                              */
+  int64_t capacity;
+} mfp_event_view;
+int mfp_integrand_events(void* d_workspace, int64_t nevents, mfp_event_view* out);
+
 /* Kernel flavour (DESIGN.md "Kernel mapping"): 0 = the process's default, 1 = one event per thread,
  * 2 = helicity-parallel thread blocks.  Both flavours compute the same numbers; the switch exists so
  * that the choice per process is made on measurements.  mfp_get_variant returns 1 or 2.            */

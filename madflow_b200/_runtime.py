@@ -59,6 +59,11 @@ class mfp_integrand_args(ctypes.Structure):
     ]
 
 
+class mfp_event_view(ctypes.Structure):
+    _fields_ = [("d_mom", ctypes.c_void_p), ("d_weight", ctypes.c_void_p), ("d_me", ctypes.c_void_p),
+                ("d_alpha_s", ctypes.c_void_p), ("capacity", ctypes.c_int64)]
+
+
 def _require_cuda():
     if not torch.cuda.is_available():
         raise MadflowB200Error("no CUDA device visible: madflow_b200 has no CPU implementation")
@@ -176,6 +181,13 @@ class ProcessLib:
     def integrand(self, args):
         _require_cuda()
         self._check(self.lib.mfp_integrand(ctypes.byref(args), stream_ptr()))
+
+    def integrand_events(self, d_workspace, nevents):
+        """Device pointers of the events of the last integrand call on this workspace (mfp_event_view)."""
+        view = mfp_event_view()
+        self._check(self.lib.mfp_integrand_events(ctypes.c_void_p(d_workspace), ctypes.c_int64(int(nevents)),
+                                                  ctypes.byref(view)))
+        return view
 
 
 _process_cache = {}

@@ -9,6 +9,7 @@
 #include "philox.cuh"
 #include "vegas.cuh"
 #include "pipeline_kernels.cuh"
+#include "events.cuh"
 
 using namespace mf;
 
@@ -416,6 +417,34 @@ int mf_vegas_refine(double* d_grid, const double* d_sums, int ndim, void* stream
   if (ndim < 1 || ndim > MF_MAX_DIM) return fail_msg("mf_vegas_refine: 1 <= ndim <= 32");
   vegas_refine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_grid, d_sums, ndim);
   return check_launch("vegas_refine_kernel");
+}
+
+int mf_event_histogram(const double* d_mom, const double* d_w1, const double* d_w2, int64_t nevt, int nexternal,
+                       int particle, int observable, double lo, double hi, int nbins, double* d_hist, void* stream) {
+  if (nevt <= 0) return 0;
+  if (particle < 0 || particle >= nexternal) return fail_msg("mf_event_histogram: particle index out of range");
+  if (observable < 0 || observable > OBS_MASS) return fail_msg("mf_event_histogram: unknown observable");
+  if (nbins < 1 || nbins > EVH_MAX_BINS || !(hi > lo)) return fail_msg("mf_event_histogram: need 1 <= nbins <= 1022 and lo < hi");
+  event_histogram_kernel<<<grid_for(nevt, EVH_BLOCK, 8), EVH_BLOCK, (nbins + 2) * sizeof(double), (cudaStream_t)stream>>>(
+      d_mom, d_w1, d_w2, nevt, nexternal, particle, observable, lo, nbins / (hi - lo), nbins, d_hist);
+  return check_launch("event_histogram_kernel");
+}
+
+int mf_max_weight(const double* d_w1, const double* d_w2, int64_t nevt, double* d_max, void* stream) {
+  if (nevt <= 0) return 0;
+  max_weight_kernel<<<grid_for(nevt, EVH_BLOCK, 8), EVH_BLOCK, 0, (cudaStream_t)stream>>>(d_w1, d_w2, nevt, d_max);
+  return check_launch("max_weight_kernel");
+}
+
+int mf_select_events(const double* d_mom, const double* d_w1, const double* d_w2, int64_t nevt, int nexternal, double wmax,
+                     uint64_t seed, uint64_t first_index, double* d_out_mom, double* d_out_w, int64_t* d_out_index,
+                     int32_t* d_count, int64_t capacity, void* stream) {
+  if (nevt <= 0) return 0;
+  if (!(wmax > 0.0)) return fail_msg("mf_select_events: wmax must be positive");
+  select_events_kernel<<<grid_for(nevt, EVH_BLOCK, 8), EVH_BLOCK, 0, (cudaStream_t)stream>>>(
+      d_mom, d_w1, d_w2, nevt, nexternal, wmax, seed, first_index, d_out_mom, d_out_w, (long long*)d_out_index, d_count,
+      capacity);
+  return check_launch("select_events_kernel");
 }
 
 int mf_fp64_peak(int iters, double* tflops, double* ms) {

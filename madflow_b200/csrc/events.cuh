@@ -1,0 +1,104 @@
+// Event output of the integrand pipeline: weighted histograms of kinematic observables and
+// unweighting + compaction of the generated events, both on the device.
+//
+// The reference hands every event of every chunk to Python (tf.py_function -> per-event dicts -> MG5's
+// lhe_parser -> gzip, python_package/madflow/lhe_writer.py:151-239) and histograms the LHE file afterwards
+// (example/compare_mg5_hists.py:16-57).  Here the events of the pipeline's HBM buffer (momenta, weight
+// factors) are histogrammed where they are, and only the events that survive the unweighting
+// (probability |w| / w_max, Philox counter = global slot index) travel to the host writer.
+#pragma once
+#include "philox.cuh"
+
+namespace mf {
+
+enum Observable { OBS_PT = 0, OBS_ETA = 1, OBS_RAPIDITY = 2, OBS_ENERGY = 3, OBS_MASS = 4 };
+
+// p = (E, px, py, pz); FourMomentum of MG5's lhe_parser (lhe_writer.py:385-433): pt, pseudorapidity, rapidity
+MF_DEV double observable_value(int obs, const double p[4]) {
+  const double pt2 = p[1] * p[1] + p[2] * p[2];
+  switch (obs) {
+    case OBS_PT: return sqrt(pt2);
+    case OBS_ETA: {
+      const double pabs = sqrt(pt2 + p[3] * p[3]);
+      return 0.5 * log((pabs + p[3]) / (pabs - p[3]));
+    }
+    case OBS_RAPIDITY: return 0.5 * log((p[0] + p[3]) / (p[0] - p[3]));
+    case OBS_ENERGY: return p[0];
+    default: {
+      const double m2 = p[0] * p[0] - pt2 - p[3] * p[3];
+      return m2 > 0.0 ? sqrt(m2) : 0.0;
+    }
+  }
+}
+
+// bin of value v in [lo, hi) with nbins bins: 0 = underflow, 1..nbins, nbins+1 = overflow (NaN -> overflow)
+MF_DEV int histogram_bin(double v, double lo, double inv_width, int nbins) {
+  const double t = (v - lo) * inv_width;
+  if (!(t >= 0.0)) return t < 0.0 ? 0 : nbins + 1;
+  return t >= (double)nbins ? nbins + 1 : 1 + (int)t;
+}
+
+constexpr int EVH_BLOCK = 256;
+constexpr int EVH_MAX_BINS = 1022;
+
+// hist[nbins + 2] += weights; weight of slot i = w1[i] * (w2 ? w2[i] : 1); slots with weight 0 are skipped
+__global__ void __launch_bounds__(EVH_BLOCK) event_histogram_kernel(const double* mom, const double* w1, const double* w2,
+                                                                   long long nevt, int next, int particle, int obs,
+                                                                   double lo, double inv_width, int nbins, double* hist) {
+  extern __shared__ double sh[];
+  for (int i = threadIdx.x; i < nbins + 2; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
+    const double w = w2 ? w1[e] * w2[e] : w1[e];
+    if (w == 0.0) continue;
+    const double4 v = reinterpret_cast<const double4*>(mom)[e * next + particle];
+    const double p[4] = {v.x, v.y, v.z, v.w};
+    atomicAdd(&sh[histogram_bin(observable_value(obs, p), lo, inv_width, nbins)], w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins + 2; i += blockDim.x)
+    if (sh[i] != 0.0) atomicAdd(&hist[i], sh[i]);
+}
+
+// *dmax = max(*dmax, max_i |w_i|)   (non-negative doubles order like their bit patterns)
+__global__ void __launch_bounds__(EVH_BLOCK) max_weight_kernel(const double* w1, const double* w2, long long nevt, double* dmax) {
+  double m = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
+    const double w = fabs(w2 ? w1[e] * w2[e] : w1[e]);
+    m = (w > m && w == w) ? w : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_down_sync(0xffffffffu, m, o);
+    m = other > m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long*>(dmax), (unsigned long long)__double_as_longlong(m));
+}
+
+// Unweighting: slot i survives with probability |w_i| / wmax (always, if |w_i| >= wmax) and is appended to the
+// output with weight sign(w_i) * max(|w_i|, wmax).  The random number depends only on (seed, first_index + i).
+// out_index receives the global slot index so that the host can restore a scheduling-independent order.
+__global__ void __launch_bounds__(EVH_BLOCK) select_events_kernel(const double* mom, const double* w1, const double* w2,
+                                                                 long long nevt, int next, double wmax, unsigned long long seed,
+                                                                 unsigned long long first_index, double* out_mom, double* out_w,
+                                                                 long long* out_index, int* count, long long capacity) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
+    const double w = w2 ? w1[e] * w2[e] : w1[e];
+    if (w == 0.0 || w != w) continue;
+    double u0, u1;
+    philox_pair(seed, 0xFFFFFFFFu, first_index + (unsigned long long)e, 0xFFFFFFFFu, u0, u1);
+    const double a = fabs(w);
+    if (a < u0 * wmax) continue;
+    const int slot = atomicAdd(count, 1);
+    if (slot >= capacity) continue;  // the counter keeps counting: the host sees the overflow
+    for (int i = 0; i < next; ++i)
+      reinterpret_cast<double4*>(out_mom)[(long long)slot * next + i] = reinterpret_cast<const double4*>(mom)[e * next + i];
+    out_w[slot] = (w < 0.0 ? -1.0 : 1.0) * (a > wmax ? a : wmax);
+    out_index[slot] = (long long)(first_index + (unsigned long long)e);
+  }
+}
+
+}  // namespace mf

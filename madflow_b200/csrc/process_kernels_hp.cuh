@@ -727,6 +727,15 @@ long long integrand_workspace_hp(long long nevents) {
   return (long long)event_buffer_layout(nevents, hp_segments<P>(integrand_blocks_hp<P>()), P::NEXT, NDIM, nullptr, nullptr);
 }
 
+template <class P>
+int integrand_events_hp(void* d_workspace, long long nevents, mfp_event_view* out) {
+  constexpr int NDIM = 4 * (P::NEXT - 2) + 2;
+  EventBuffer b;
+  event_buffer_layout(nevents, hp_segments<P>(integrand_blocks_hp<P>()), P::NEXT, NDIM, d_workspace, &b);
+  out->d_mom = b.mom, out->d_weight = b.w, out->d_me = b.me, out->d_alpha_s = b.as, out->capacity = b.cap;
+  return 0;
+}
+
 // One pass of the integrand = three launches on the caller's stream (see pipeline_kernels.cuh)
 template <class P>
 int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
@@ -856,6 +865,11 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
       if (!mf::use_hp<P>()) return mf::launch_integrand<P>(a, (cudaStream_t)st);                               \
     }                                                                                                          \
     return mf::launch_integrand_hp<P>(a, (cudaStream_t)st);                                                    \
+  }                                                                                                            \
+  int mfp_integrand_events(void* d_workspace, int64_t nevents, mfp_event_view* out) {                          \
+    if (!out || !d_workspace) return mf::fail_msg("mfp_integrand_events: null pointer");                       \
+    if (!mf::use_hp<P>()) return mf::fail_msg("mfp_integrand_events: the one-event-per-thread flavour has no event buffer"); \
+    return mf::integrand_events_hp<P>(d_workspace, nevents, out);                                              \
   }                                                                                                            \
   const char* mfp_last_error(void) { return mf::g_err; }                                                       \
   MF_DEFINE_PROFILE_HOOK                                                                                       \

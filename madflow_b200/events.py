@@ -1,0 +1,134 @@
+"""Event output of the fused integrand: histograms and unweighted events, filled on the device.
+
+The reference produces events by calling back into Python from inside the integrand
+(scripts/madflow_exec.py:462-464 -> lhe_writer.LheWriter.lhe_parser, python_package/madflow/lhe_writer.py:
+151-208) and histograms the LHE file afterwards (example/compare_mg5_hists.py:16-57).  Here an `EventSink`
+attached to a `FusedIntegrand` sees, after every launch, the event buffer of the kernel pipeline in device
+memory (include/madflow_b200_process.h: mfp_integrand_events):
+
+    sink = EventSink(integrand, histograms=[Histogram("pt", 2, 0.0, 300.0, 50), Histogram("eta", 2, -4.0, 4.0, 50)],
+                     unweight=True, capacity=100_000)
+    vegas.run_integration(n)                  # histograms accumulate, unweighted events are kept
+    sink.histograms[0].values(n_iterations)   # d(sigma)/bin in pb
+    with LheWriter(folder, "run_01", no_unweight=True) as w: sink.write_lhe(w)
+
+Only the events that survive the unweighting leave the GPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _runtime as rt
+from . import config
+
+OBSERVABLES = {"pt": 0, "eta": 1, "pseudorapidity": 1, "rapidity": 2, "y": 2, "energy": 3, "E": 3, "mass": 4}
+
+
+class Histogram:
+    """Weighted 1-d histogram of one particle's observable with under/overflow, accumulated on the device."""
+
+    def __init__(self, observable, particle, lo, hi, nbins=50):
+        if observable not in OBSERVABLES:
+            raise ValueError(f"observable must be one of {sorted(OBSERVABLES)}")
+        self.observable, self.particle = observable, int(particle)
+        self.lo, self.hi, self.nbins = float(lo), float(hi), int(nbins)
+        self._hist = torch.zeros(self.nbins + 2, dtype=torch.float64, device=config.device())
+
+    @property
+    def edges(self):
+        return np.linspace(self.lo, self.hi, self.nbins + 1)
+
+    def fill(self, mom, w1, w2=None):
+        """mom (nevt, nexternal, 4) and the weight factors w1 (* w2) as CUDA float64 tensors."""
+        lib = rt.core()
+        nevt, nexternal = int(mom.shape[0]), int(mom.shape[1])
+        rt.check(lib, lib.mf_event_histogram(rt.ptr(mom), rt.ptr(w1), rt.ptr(w2), ctypes.c_int64(nevt), nexternal,
+                                             self.particle, OBSERVABLES[self.observable], ctypes.c_double(self.lo),
+                                             ctypes.c_double(self.hi), self.nbins, rt.ptr(self._hist), rt.stream_ptr()))
+
+    def allreduce(self):
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self._hist, op=dist.ReduceOp.SUM)
+
+    def values(self, n_iterations=1, with_overflow=False):
+        """Sum of weights per bin divided by the number of iterations that filled it (each VEGAS iteration
+        is an independent estimate of the cross section, so this is d(sigma) per bin)."""
+        h = self._hist.cpu().numpy() / float(n_iterations)
+        return h if with_overflow else h[1:-1]
+
+    def reset(self):
+        self._hist.zero_()
+
+
+class EventSink:
+    """Consumes the device event buffer after every launch of a FusedIntegrand."""
+
+    def __init__(self, integrand, histograms=(), unweight=False, capacity=1_000_000, seed=1234, wmax=None):
+        self.integrand = integrand
+        self.histograms = list(histograms)
+        self.unweight = bool(unweight)
+        self.capacity = int(capacity)
+        self.seed = int(seed)
+        self.wmax = float(wmax) if wmax else None   # None: the largest weight seen in earlier launches
+        self.enabled = True
+        dev = config.device()
+        n = integrand.nexternal
+        self._max = torch.zeros(1, dtype=torch.float64, device=dev)
+        if self.unweight:
+            self._mom = torch.empty((self.capacity, n, 4), dtype=torch.float64, device=dev)
+            self._w = torch.empty(self.capacity, dtype=torch.float64, device=dev)
+            self._idx = torch.empty(self.capacity, dtype=torch.int64, device=dev)
+            self._count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.launches = 0
+        integrand.event_sink = self
+
+    # called by FusedIntegrand.launch
+    def consume(self, mom, weight, me, alpha_s, first_event):
+        if not self.enabled:
+            return
+        lib = rt.core()
+        nslots = int(mom.shape[0])
+        for h in self.histograms:
+            h.fill(mom, me, weight)
+        if self.unweight:
+            wmax = self.wmax
+            if wmax is None and self.launches > 0:
+                wmax = float(self._max.item())
+            if wmax:
+                # global slot index: unique per (iteration, rank, launch) as long as capacities do not change
+                rt.check(lib, lib.mf_select_events(rt.ptr(mom), rt.ptr(me), rt.ptr(weight), ctypes.c_int64(nslots),
+                                                   int(mom.shape[1]), ctypes.c_double(wmax), ctypes.c_uint64(self.seed),
+                                                   ctypes.c_uint64(int(first_event) * 4 + self.launches * (1 << 40)),
+                                                   rt.ptr(self._mom), rt.ptr(self._w), rt.ptr(self._idx),
+                                                   rt.ptr(self._count), ctypes.c_int64(self.capacity), rt.stream_ptr()))
+            rt.check(lib, lib.mf_max_weight(rt.ptr(me), rt.ptr(weight), ctypes.c_int64(nslots), rt.ptr(self._max),
+                                            rt.stream_ptr()))
+        self.launches += 1
+
+    @property
+    def max_weight(self):
+        return float(self._max.item())
+
+    def events(self):
+        """(momenta (n, nexternal, 4), weights (n,)) of the kept events as numpy arrays, in global-index order."""
+        if not self.unweight:
+            raise RuntimeError("EventSink(unweight=True) keeps events")
+        n = min(int(self._count.item()), self.capacity)
+        order = torch.argsort(self._idx[:n])
+        return self._mom[:n][order].cpu().numpy(), self._w[:n][order].cpu().numpy()
+
+    @property
+    def overflowed(self):
+        return self.unweight and int(self._count.item()) > self.capacity
+
+    def write_lhe(self, writer, cross=None):
+        """Write the kept events through an LheWriter; every event gets weight `cross` (the integrated cross
+        section, as the reference does after unweighting, lhe_writer.py:339-341) or its own weight."""
+        mom, w = self.events()
+        if cross is not None:
+            w = np.sign(w) * float(cross)
+        writer.lhe_parser(mom, w)
+        return len(w)

@@ -48,6 +48,7 @@ class FusedIntegrand:
         if pt_cut is not None:  # madflow_exec.py:392-395
             self.cuts += [("pt", i, float(pt_cut), None) for i in range(2, n)]
         self.lab_frame = bool(lab_frame)
+        self.event_sink = None                 # madflow_b200.events.EventSink
         self.max_events_per_launch = 1 << 23   # bounds the HBM scratch of the pipeline flavour (~2 GB)
         self.running = bool(running)
         if alpha_s is None:
@@ -103,6 +104,26 @@ class FusedIntegrand:
         a.d_workspace = ws.data_ptr() if ws is not None else None
         a.workspace_bytes = ws.numel() if ws is not None else 0
         self._lib.integrand(a)
+        if self.event_sink is not None:
+            self.event_sink.consume(*self.events(nevents), first_event)
+
+    def events(self, nevents):
+        """The device event buffer of the last launch of `nevents` events as tensors (views of the workspace):
+        momenta (capacity, nexternal, 4), weight, |M|^2, alpha_s (capacity,); the integrand value of slot i is
+        me[i] * weight[i], empty slots have weight 0 (include/madflow_b200_process.h: mfp_integrand_events)."""
+        ws = getattr(self, "_ws", None)
+        if ws is None:
+            raise rt.MadflowB200Error("no event buffer: the one-event-per-thread flavour keeps the events on chip; "
+                                      "select the helicity-parallel flavour (matrix.set_variant('hp'))")
+        v = self._lib.integrand_events(ws.data_ptr(), nevents)
+        cap, n = int(v.capacity), self.nexternal
+
+        def view(ptr, count):
+            off = int(ptr) - ws.data_ptr()
+            return ws[off:off + count * 8].view(torch.float64)
+
+        return (view(v.d_mom, cap * n * 4).view(cap, n, 4), view(v.d_weight, cap), view(v.d_me, cap),
+                view(v.d_alpha_s, cap))
 
     # -- the same integrand from the separate API calls (reference structure, madflow_exec.py:422-470)
     def python_integrand(self):

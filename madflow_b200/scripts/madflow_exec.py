@@ -1,0 +1,186 @@
+#!/usr/bin/env python3
+"""Leading-order cross sections and event generation on the GPU -- the `madflow` command
+(python_package/madflow/scripts/madflow_exec.py:243-530).
+
+    python -m madflow_b200.scripts.madflow_exec --madgraph_process "g g > t t~ g g" --no_pdf -c -i 10 -f 5 \\
+        --events_per_iteration 10000000 --histograms -o out/
+
+Same arguments and the same warm-up / frozen-grid schedule as the reference (madflow_exec.py:491-510); what is
+not available offline is refused loudly instead of approximated: PDFs (`--no_pdf` is required: pdfflow and
+LHAPDF grids are absent) and MG5 process generation (the process must be one of the compiled process
+libraries -- the built-in g g > t t~ + n g, or anything exported through the `pyout` plugin's CUDA backend).
+Extensions for long runs: --target_error stops the final iterations once the combined relative error is below
+it, --unweighted_events sets the capacity of the on-device unweighting buffer.
+"""
+import argparse
+import json
+import logging
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+logger = logging.getLogger("madflow")
+
+DEFAULT_PDF = "NNPDF31_nnlo_as_0118"
+
+
+def process_library_name(madgraph_process):
+    """'g g > t t~ g' -> '1_gg_ttxg' (MG5's shell_string for process number 1, PyOut_exporter.py:138)."""
+    ini, fin = madgraph_process.split(">")
+    shell = lambda side: "".join(side.split()).replace("~", "x")
+    return f"1_{shell(ini)}_{shell(fin)}"
+
+
+def build_parser():
+    arger = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    arger.add_argument("-v", "--verbose", help="Print extra info", action="store_true")
+    arger.add_argument("-p", "--pdf", help="PDF set (needs pdfflow: not available, use --no_pdf)", type=str, default=DEFAULT_PDF)
+    arger.add_argument("--no_pdf", help="Don't use a PDF for the initial state", action="store_true")
+    arger.add_argument("--madgraph_process", help="Set the madgraph process to be run", type=str, default="g g > t t~")
+    arger.add_argument("-m", "--massive_particles", help="Number of massive particles", type=int, default=2)
+    arger.add_argument("-q", "--fixed_scale", help="Fix value of scale muR=muF (and alphas(q)), if this flag is not provided "
+                       "take dynamical scale q2 = sum(mT)/2", type=float, nargs="?", const=91.46)
+    arger.add_argument("-c", "--pt_cut", help="Enable a pt cut for the outgoing particles", type=float, nargs="?", const=30.0)
+    arger.add_argument("--histograms", help="Generate LHE files/histograms", action="store_true")
+    arger.add_argument("-i", "--iterations", help="Iterations of vegas to run", type=int, default=10)
+    arger.add_argument("-f", "--frozen_iter", help="Iterations with frozen grid", type=int, default=0)
+    arger.add_argument("--events_per_device", help="How many events to send to each device per launch", type=int)
+    arger.add_argument("-o", "--output", help="Output folder", type=Path)
+    arger.add_argument("--dry_run", help="Resolve the process and its library but don't run anything", action="store_true")
+    arger.add_argument("--events_per_iteration", help="How many events to run per iteration", type=int, default=int(1e6))
+    arger.add_argument("--custom_op", help="Accepted for compatibility: the CUDA kernels are the only implementation",
+                       action="store_true")
+    arger.add_argument("--target_error", help="Stop the final iterations at this relative error of the combined result",
+                       type=float, default=None)
+    arger.add_argument("--unweighted_events", help="Capacity of the unweighted-event buffer (--histograms)", type=int,
+                       default=100_000)
+    arger.add_argument("--seed", type=int, default=4)
+    return arger
+
+
+def madflow_main(args=None, quick_return=False):
+    args = build_parser().parse_args(args)
+    if quick_return:
+        return args, None, None
+    from madflow_b200 import config  # noqa: F401  (installs the "madflow" log handler, config.py:22-28)
+
+    if args.verbose:
+        logger.setLevel(logging.DEBUG)
+    if not args.no_pdf:
+        raise SystemExit("PDF luminosities need pdfflow and an LHAPDF grid, which are not available: run with --no_pdf")
+
+    import torch
+
+    from madflow_b200 import events as mfe
+    from madflow_b200 import integrand as mfi
+    from madflow_b200 import matrix as mfm
+    from madflow_b200 import vegas as mfv
+    from madflow_b200.lhe_writer import LheWriter
+
+    name = process_library_name(args.madgraph_process)
+    if name not in mfm.available_processes():
+        raise SystemExit(f"process '{args.madgraph_process}' ({name}) has no compiled process library; available: "
+                         f"{mfm.available_processes()} (export it through the pyout plugin's CUDA backend)")
+    output_path = args.output if args.output is not None else Path(tempfile.mkdtemp(prefix="mad_"))
+    output_path.mkdir(parents=True, exist_ok=True)
+    if args.dry_run:
+        logger.info("Process %s -> library %s; dry run, nothing executed", args.madgraph_process, name)
+        return None, None, None
+
+    dist = None
+    rank, world = 0, 1
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
+
+    matrix, model = mfm.get_process(name)
+    if args.histograms:
+        matrix.set_variant("hp")   # the kernel pipeline that keeps the events in device memory
+    nparticles = int(matrix.nexternal)
+    non_massive = nparticles - args.massive_particles - 2
+    param_masses = [float(m) for m in model.get_masses()]
+    if len(param_masses) < args.massive_particles:
+        param_masses *= args.massive_particles
+    masses = param_masses[: args.massive_particles] + [0.0] * non_massive   # madflow_exec.py:362-370
+    if args.fixed_scale is None:
+        logger.info("Set variable muF=muR=sum(mT)/2")
+    else:
+        logger.info("Setting fixed muF=muR=%.2f GeV, alpha_s = 0.118", args.fixed_scale)   # madflow_exec.py:376-380
+    fi = mfi.FusedIntegrand(matrix, model, sqrts=13e3, masses=masses, pt_cut=args.pt_cut, lab_frame=True,
+                            running=args.fixed_scale is None, alpha_s=0.118)
+    if args.events_per_device:
+        fi.max_events_per_launch = args.events_per_device
+    if nparticles >= 5 and args.frozen_iter == 0:
+        logger.warning("With this many particles (> 5) it is recommended to run with frozen iterations")
+
+    vegas = mfv.VegasFlow(fi.n_dim, args.events_per_iteration, seed=args.seed)
+    vegas.compile(fi)
+    if args.frozen_iter == 0:   # madflow_exec.py:491-510
+        warmup_iterations, final_iterations = args.iterations // 2, args.iterations // 2
+    else:
+        warmup_iterations, final_iterations = max(args.iterations - args.frozen_iter, 2), args.frozen_iter
+    t0 = time.time()
+    logger.info("Running %d warm-up iterations of %d events each", warmup_iterations, args.events_per_iteration)
+    vegas.run_integration(warmup_iterations)
+    if args.frozen_iter > 0:
+        vegas.freeze_grid()
+    logger.info("Running %d iterations of %d events each%s", final_iterations, vegas.events_per_run,
+                " with the grid frozen" if args.frozen_iter > 0 else "")
+
+    sink = None
+    if args.histograms:
+        top = 2  # the first outgoing particle: the top quark in the built-in processes (compare_mg5_hists.py:31-32)
+        sink = mfe.EventSink(fi, histograms=[mfe.Histogram("pt", top, 0.0, 300.0, 50), mfe.Histogram("eta", top, -4.0, 4.0, 50)],
+                             unweight=True, capacity=args.unweighted_events, seed=args.seed)
+    results = []
+    n_final = 0
+    for _ in range(final_iterations):
+        results.append(vegas.run_iteration())
+        n_final += 1
+        res, err, chi2 = mfv.combine_iterations(results)
+        logger.info("Result for final iteration %d: %.6g +/- %.3g -> combined %.6g +/- %.3g (%.3g %%)", n_final,
+                    results[-1][0], results[-1][1], res, err, 100 * err / abs(res))
+        if args.target_error and err / abs(res) < args.target_error:
+            break
+    res, err, chi2 = mfv.combine_iterations(results)
+    wall = time.time() - t0
+    logger.info(" > Final results: %g +/- %g pb  (chi2/dof %.2f, %d events, %.1f s)", res, err, chi2,
+                (warmup_iterations + n_final) * args.events_per_iteration, wall)
+
+    proc_folder = None
+    if args.histograms:
+        proc_name = args.madgraph_process.replace(" ", "_").replace(">", "to").replace("~", "b")
+        run = proc_name if world == 1 else f"{proc_name}_rank{rank}"
+        for h in sink.histograms:
+            h.allreduce()
+        with LheWriter(output_path, run, no_unweight=True, pdg=(matrix.ir or {}).get("pdg")) as lhe_writer:
+            nkept = sink.write_lhe(lhe_writer, cross=res)
+            lhe_writer.store_result((res, err))
+            proc_folder = output_path / f"Events/{run}"
+            lhe_writer.dump_result(proc_folder / "cross_err.txt")
+        # the events of the sink are already unweighted on the device: the file is the unweighted sample
+        (proc_folder / "weighted_events.lhe.gz").rename(proc_folder / "unweighted_events.lhe.gz")
+        if rank == 0:
+            hists = {f"{h.observable}_{h.particle}": {"edges": h.edges.tolist(), "dsigma_pb": h.values(n_final).tolist(),
+                                                     "underflow_overflow_pb": [float(h.values(n_final, True)[0]),
+                                                                               float(h.values(n_final, True)[-1])]}
+                     for h in sink.histograms}
+            (proc_folder / "histograms.json").write_text(json.dumps(hists, indent=1))
+        logger.info("Written %d unweighted events%s, histograms and cross_err.txt to %s", nkept,
+                    " (buffer full)" if sink.overflowed else "", proc_folder)
+    if dist is not None:
+        dist.destroy_process_group()
+    return args, (res, err), proc_folder
+
+
+def main():
+    madflow_main()
+
+
+if __name__ == "__main__":
+    main()

@@ -126,3 +126,49 @@ def test_two_rank_gloo_allreduce(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_lhe_writer_round_trip(tmp_path):
+    """LheWriter with the reference's protocol (lhe_writer.py:94-356): weighted file, unweighting, cross_err.txt."""
+    from madflow_b200.lhe_writer import EventFileFlow, FourMomentumFlow, LheWriter
+
+    rng = np.random.default_rng(0)
+    ps = rng.normal(size=(60, 6, 4)) * 50.0
+    ps[:, :, 0] = np.sqrt(np.sum(ps[:, :, 1:] ** 2, axis=-1) + np.array([0, 0, 173.0, 173.0, 0, 0]) ** 2)
+    w = rng.random(60)
+    w[::6] = 0.0   # events cut away are not written
+    with LheWriter(tmp_path, "run_01") as lw:
+        lw.lhe_parser(ps[:30], w[:30])
+        lw.lhe_parser(ps[30:], w[30:])
+        lw.store_result((12.5, 0.1))
+        lw.dump_result(tmp_path / "cross_err.txt")
+    kept = np.nonzero(w)[0]
+    events = list(EventFileFlow(tmp_path / "Events/run_01/weighted_events.lhe.gz"))
+    assert len(events) == len(kept)
+    for ev, i in zip(events, kept):
+        assert ev.nexternal == 6 and ev.wgt == pytest.approx(w[i], rel=1e-7)
+        assert [p.pid for p in ev] == [21, 21, 6, -6, 21, 21] and [p.status for p in ev] == [-1, -1, 1, 1, 1, 1]
+        np.testing.assert_allclose([[p.E, p.px, p.py, p.pz] for p in ev], ps[i], rtol=1e-10)
+    top = FourMomentumFlow(events[0][2])
+    assert top.pt == pytest.approx(np.hypot(ps[kept[0], 2, 1], ps[kept[0], 2, 2]), rel=1e-10)
+    assert top.mass == pytest.approx(173.0, rel=1e-6)
+    unw = list(EventFileFlow(tmp_path / "Events/run_01/unweighted_events.lhe.gz"))
+    assert 0 < len(unw) <= len(events) and all(e.wgt == pytest.approx(12.5) for e in unw)
+    np.testing.assert_allclose(np.loadtxt(tmp_path / "cross_err.txt"), [12.5, 0.1])
+
+
+def test_madflow_cli_arguments_and_process_names():
+    """The `madflow` command line of scripts/madflow_exec.py:243-308 (names, defaults, optional values)."""
+    from madflow_b200.scripts.madflow_exec import madflow_main, process_library_name
+
+    args, _, _ = madflow_main(["--no_pdf", "-c", "-q", "-i", "6", "-f", "3", "--histograms",
+                               "--madgraph_process", "g g > t t~ g g"], quick_return=True)
+    assert args.pt_cut == 30.0 and args.fixed_scale == 91.46 and args.iterations == 6 and args.frozen_iter == 3
+    assert args.events_per_iteration == int(1e6) and args.massive_particles == 2 and args.histograms and args.no_pdf
+    assert process_library_name(args.madgraph_process) == "1_gg_ttxgg"
+    assert process_library_name("g g > t t~") == "1_gg_ttx"
+    with pytest.raises(SystemExit):
+        madflow_main(["--dry_run"])           # PDFs are refused, not approximated
+    with pytest.raises(SystemExit):
+        madflow_main(["--no_pdf", "--dry_run", "--madgraph_process", "u u~ > t t~"])   # no such library
+    assert madflow_main(["--no_pdf", "--dry_run", "--madgraph_process", "g g > t t~ g"]) == (None, None, None)
