@@ -321,6 +321,11 @@ def main():
     exec_flops = executed.get("flops_per_me_event")
     exec_tflops = exec_flops * me_per_launch / (kernel_ms * 1e-3) / 1e12 if exec_flops else None
     final, err, chi2 = mfv.combine_iterations(results)
+    # kernels of this package inside the timed region, per step: the integrand (1 fused kernel, or generate +
+    # matrix element + accumulate for the helicity-parallel pipeline) and the block-partial reduction per launch
+    # chunk, plus the grid refinement
+    chunks = -(-n_per_gpu // min(n_per_gpu, fi.max_events_per_launch))
+    gpu_launches = args.steps * (chunks * ((3 if m.variant == "hp" else 1) + 1) + 1)
     bytes_per_event = 0.0  # the fused kernel reads no per-event input from HBM
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -336,7 +341,8 @@ def main():
         },
         "roofline": {
             "bound": "fp64", "achieved": achieved, "peak": fp64_sustained, "unit": "TFLOP/s",
-            "frac": achieved / fp64_sustained, "traffic": None,
+            "frac": achieved / fp64_sustained, "traffic": executed.get("dram_bytes_per_launch"),
+            "traffic_source": executed.get("dram_source"),
             "kernel": "integrand_kernel_hp<Proc>" if m.variant == "hp" else "integrand_kernel<Proc>", "kernel_ms": kernel_ms,
             "flops_per_event_algorithmic": flops,
             "peak_source": "mf_fp64_peak DFMA probe in this run (sustained, after the timed kernels); burst "
@@ -355,7 +361,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "Matrix.smatrix on pinned host momenta (+ per-event couplings): H2D, fused kernel, D2H of |M|^2",
                 "events_per_step": n_e2e},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": gpu_launches,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -636,7 +636,10 @@ struct Proc {{
   // shared-memory cxd per event: wavefunctions | pair objects | amplitude buffer (the last two double as the
   // JAMP exchange area of the colour groups)
   static constexpr int HP_XCHG = HP_COLOUR >= 2 ? HP_NCP * HP_PLANE : (HP_NCG > 1 ? NCOLOR * HP_NHP : 0);
-  static constexpr int HP_EVSTRIDE = HP_WFSIZE + (HP_SCRATCH + HP_NB * HP_NHP > HP_XCHG ? HP_SCRATCH + HP_NB * HP_NHP : HP_XCHG);
+  static constexpr int HP_EVSIZE = HP_WFSIZE + (HP_SCRATCH + HP_NB * HP_NHP > HP_XCHG ? HP_SCRATCH + HP_NB * HP_NHP : HP_XCHG);
+  // the E events of a block sit HP_EVSTRIDE apart; the stride is padded to 8/E (mod 8) elements of 16 bytes so
+  // that threads working on the same object of different events hit different banks
+  static constexpr int HP_EVSTRIDE = HP_E > 1 ? HP_EVSIZE + ((8 / HP_E) - HP_EVSIZE % 8 + 8) % 8 : HP_EVSIZE;
   MF_DEV static const double* cfsym() {{ return MF_TAB(cfsym); }}
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
