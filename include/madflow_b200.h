@@ -40,8 +40,8 @@ int mf_aloha(int id, const double* d_a, const double* d_b, const double* d_c, co
 
 /* ---- phase space (phasespace.py) --------------------------------------------------------------- */
 typedef struct mf_cut {
-  int32_t var;       /* 0 pt, 1 mt, 2 mt2 */
-  int32_t particle;
+  int32_t var;       /* 0 pt, 1 mt, 2 mt2; pairs (extension): 3 invariant mass, 4 Delta R */
+  int32_t particle;  /* pair variables: i + 256 * j */
   int32_t has_min, has_max;
   double vmin, vmax;
 } mf_cut;
@@ -92,8 +92,9 @@ int mf_vegas_refine(double* d_grid, const double* d_sums, int ndim, void* stream
  * particle `particle`: 0 pt, 1 pseudorapidity, 2 rapidity, 3 energy, 4 invariant mass.                     */
 int mf_event_histogram(const double* d_mom, const double* d_w1, const double* d_w2, int64_t nevt, int nexternal,
                        int particle, int observable, double lo, double hi, int nbins, double* d_hist, void* stream);
-/* *d_max = max(*d_max, max |weight|)                                                                       */
-int mf_max_weight(const double* d_w1, const double* d_w2, int64_t nevt, double* d_max, void* stream);
+/* weight statistics: d_partial (nblocks, 3) = per block {max |w|, sum |w|, sum w^2}; the caller reduces the rows    */
+int mf_weight_stats_blocks(void);
+int mf_weight_stats(const double* d_w1, const double* d_w2, int64_t nevt, double* d_partial, int nblocks, void* stream);
 /* unweighting + compaction: slot i is kept with probability |w_i| / wmax (Philox: key seed, counter
  * first_index + i) and appended -- momenta, weight sign(w) * max(|w|, wmax), global index first_index + i --
  * at position (*d_count)++ of the output arrays (capacity slots; *d_count keeps counting past it).        */

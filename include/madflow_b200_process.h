@@ -63,7 +63,8 @@ int mfp_matrix_hel(const double* d_p, int layout, int64_t nevt, int icomb, const
                    const double* d_coup, int64_t coup_stride, double sqh, double* d_out, void* stream);
 
 typedef struct mfp_cut {
-  int32_t var;        /* 0 = pt, 1 = mt, 2 = mt2   (phasespace.py:405-422)   */
+  int32_t var;        /* 0 = pt, 1 = mt, 2 = mt2   (phasespace.py:405-422); extension for PAIRS of particles:
+                       * 3 = invariant mass, 4 = Delta R, with particle = i + 256 * j */
   int32_t particle;   /* index into the nexternal momenta                     */
   int32_t has_min, has_max;
   double vmin, vmax;  /* strict: vmin < var < vmax (phasespace.py:444-461)   */

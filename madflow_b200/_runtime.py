@@ -18,7 +18,16 @@ LIBDIR = os.path.join(HERE, "lib")
 c_dp = ctypes.c_void_p
 MFP_MAX_PARAMS, MFP_MAX_COUPLINGS, MFP_MAX_OUT, MFP_MAX_CUTS = 8, 8, 8, 16
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
-CUT_VARS = {"pt": 0, "mt": 1, "mt2": 2}
+CUT_VARS = {"pt": 0, "mt": 1, "mt2": 2, "mij": 3, "dr": 4}
+PAIR_CUTS = ("mij", "dr")   # extension: cuts on a pair of particles, particle = (i, j)
+
+
+def cut_particle(variable, particle):
+    """The `particle` field of mf_cut: an index, or i + 256 * j for the pair variables."""
+    if variable in PAIR_CUTS:
+        i, j = particle
+        return int(i) + 256 * int(j)
+    return int(particle)
 
 
 class MadflowB200Error(RuntimeError):

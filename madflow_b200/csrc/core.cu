@@ -347,8 +347,10 @@ int mf_phasespace(int next, const double* d_x, int64_t nevt, double com_sqrts, c
   CutList cl;
   cl.n = ncuts;
   for (int i = 0; i < ncuts; ++i) {
-    if (cuts[i].particle < 0 || cuts[i].particle >= next) return fail_msg("mf_phasespace: cut on a non-existent particle");
-    if (cuts[i].var < 0 || cuts[i].var > 2) return fail_msg("mf_phasespace: unknown cut variable");
+    if (cuts[i].var < 0 || cuts[i].var > CUT_DR) return fail_msg("mf_phasespace: unknown cut variable");
+    const int pi_ = cuts[i].particle & 0xff, pj_ = cuts[i].var >= CUT_MIJ ? (cuts[i].particle >> 8) & 0xff : 0;
+    if (cuts[i].particle < 0 || pi_ >= next || pj_ >= next || (cuts[i].var < CUT_MIJ && cuts[i].particle >= next))
+      return fail_msg("mf_phasespace: cut on a non-existent particle");
     cl.c[i] = Cut{cuts[i].var, cuts[i].particle, cuts[i].has_min, cuts[i].has_max, cuts[i].vmin, cuts[i].vmax};
   }
   const PSConst c = make_psconst(k, nout);
@@ -430,10 +432,12 @@ int mf_event_histogram(const double* d_mom, const double* d_w1, const double* d_
   return check_launch("event_histogram_kernel");
 }
 
-int mf_max_weight(const double* d_w1, const double* d_w2, int64_t nevt, double* d_max, void* stream) {
-  if (nevt <= 0) return 0;
-  max_weight_kernel<<<grid_for(nevt, EVH_BLOCK, 8), EVH_BLOCK, 0, (cudaStream_t)stream>>>(d_w1, d_w2, nevt, d_max);
-  return check_launch("max_weight_kernel");
+int mf_weight_stats_blocks(void) { return sm_count() * 4; }
+
+int mf_weight_stats(const double* d_w1, const double* d_w2, int64_t nevt, double* d_partial, int nblocks, void* stream) {
+  if (nblocks < 1) return fail_msg("mf_weight_stats: nblocks < 1");
+  weight_stats_kernel<<<nblocks, EVH_BLOCK, 0, (cudaStream_t)stream>>>(d_w1, d_w2, nevt, d_partial);
+  return check_launch("weight_stats_kernel");
 }
 
 int mf_select_events(const double* d_mom, const double* d_w1, const double* d_w2, int64_t nevt, int nexternal, double wmax,

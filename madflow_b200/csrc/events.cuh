@@ -61,20 +61,37 @@ __global__ void __launch_bounds__(EVH_BLOCK) event_histogram_kernel(const double
     if (sh[i] != 0.0) atomicAdd(&hist[i], sh[i]);
 }
 
-// *dmax = max(*dmax, max_i |w_i|)   (non-negative doubles order like their bit patterns)
-__global__ void __launch_bounds__(EVH_BLOCK) max_weight_kernel(const double* w1, const double* w2, long long nevt, double* dmax) {
-  double m = 0.0;
+// per block: partial[block] = {max |w|, sum |w|, sum w^2} over its slots (the caller reduces the blocks in a fixed
+// order, so the statistics -- and the unweighting threshold derived from them -- do not depend on scheduling)
+__global__ void __launch_bounds__(EVH_BLOCK) weight_stats_kernel(const double* w1, const double* w2, long long nevt, double* partial) {
+  __shared__ double red[3][EVH_BLOCK / 32];
+  double m = 0.0, s1 = 0.0, s2 = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
     const double w = fabs(w2 ? w1[e] * w2[e] : w1[e]);
-    m = (w > m && w == w) ? w : m;
+    if (w == w) {
+      m = w > m ? w : m;
+      s1 += w;
+      s2 += w * w;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     const double other = __shfl_down_sync(0xffffffffu, m, o);
     m = other > m ? other : m;
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+    s2 += __shfl_down_sync(0xffffffffu, s2, o);
   }
-  if ((threadIdx.x & 31) == 0 && m > 0.0)
-    atomicMax(reinterpret_cast<unsigned long long*>(dmax), (unsigned long long)__double_as_longlong(m));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[0][warp] = m, red[1][warp] = s1, red[2][warp] = s2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < EVH_BLOCK / 32; ++w) {
+      m = red[0][w] > m ? red[0][w] : m;
+      s1 += red[1][w];
+      s2 += red[2][w];
+    }
+    partial[blockIdx.x * 3 + 0] = m, partial[blockIdx.x * 3 + 1] = s1, partial[blockIdx.x * 3 + 2] = s2;
+  }
 }
 
 // Unweighting: slot i survives with probability |w_i| / wmax (always, if |w_i| >= wmax) and is appended to the

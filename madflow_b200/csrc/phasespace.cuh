@@ -27,11 +27,13 @@ struct PSConst {
   double inv_norm; // 1/(2 pi)^(3n-4)                                     (phasespace.py:191)
 };
 
-enum CutVar { CUT_PT = 0, CUT_MT = 1, CUT_MT2 = 2 };
+// CUT_MIJ / CUT_DR act on a PAIR of particles (an extension: the reference only has single-particle cuts, which
+// leave the final-state gluon-gluon collinear singularity of g g > t t~ g g (g) unregulated)
+enum CutVar { CUT_PT = 0, CUT_MT = 1, CUT_MT2 = 2, CUT_MIJ = 3, CUT_DR = 4 };
 
 struct Cut {
   int var;        // CutVar
-  int particle;   // index into the nexternal momenta
+  int particle;   // index into the nexternal momenta; pair variables: i + 256 * j
   int has_min, has_max;
   double vmin, vmax;
 };
@@ -52,13 +54,28 @@ MF_DEV double cut_value(int var, const double p[4]) {
   return var == CUT_MT2 ? v : sqrt(v);
 }
 
+// invariant mass / Delta R = sqrt(d eta^2 + d phi^2) of a pair
+MF_DEV double pair_cut_value(int var, const double a[4], const double b[4]) {
+  if (var == CUT_MIJ) {
+    const double e = a[0] + b[0], x = a[1] + b[1], y = a[2] + b[2], z = a[3] + b[3];
+    const double m2 = e * e - (x * x + y * y + z * z);
+    return m2 > 0.0 ? sqrt(m2) : 0.0;
+  }
+  const double pa = sqrt(a[1] * a[1] + a[2] * a[2] + a[3] * a[3]), pb = sqrt(b[1] * b[1] + b[2] * b[2] + b[3] * b[3]);
+  const double deta = 0.5 * log((pa + a[3]) / (pa - a[3])) - 0.5 * log((pb + b[3]) / (pb - b[3]));
+  double dphi = fabs(atan2(a[2], a[1]) - atan2(b[2], b[1]));
+  if (dphi > M_PI) dphi = 2.0 * M_PI - dphi;
+  return sqrt(deta * deta + dphi * dphi);
+}
+
 // phasespace.py:444-461: strict inequalities, all cuts must pass
 template <int NEXT>
 MF_DEV bool pass_cuts(const CutList& cuts, const double p[NEXT][4]) {
   bool ok = true;
   for (int i = 0; i < cuts.n; ++i) {
     const Cut& c = cuts.c[i];
-    const double v = cut_value(c.var, p[c.particle]);
+    const double v = c.var >= CUT_MIJ ? pair_cut_value(c.var, p[c.particle & 0xff], p[(c.particle >> 8) & 0xff])
+                                      : cut_value(c.var, p[c.particle]);
     if (c.has_min) ok = ok && (v > c.vmin);
     if (c.has_max) ok = ok && (v < c.vmax);
   }

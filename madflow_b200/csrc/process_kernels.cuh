@@ -322,8 +322,10 @@ int prepare_integrand_args(const mfp_integrand_args* u, IntegrandArgs& a) {
   a.cuts.n = u->ncuts;
   for (int i = 0; i < u->ncuts; ++i) {
     const mfp_cut& c = u->cuts[i];
-    if (c.particle < 0 || c.particle >= P::NEXT) return fail_msg("mfp_integrand: cut on a non-existent particle");
-    if (c.var < 0 || c.var > 2) return fail_msg("mfp_integrand: unknown cut variable");
+    const int pi_ = c.particle & 0xff, pj_ = c.var >= CUT_MIJ ? (c.particle >> 8) & 0xff : 0;
+    if (c.particle < 0 || pi_ >= P::NEXT || pj_ >= P::NEXT || (c.var < CUT_MIJ && c.particle >= P::NEXT))
+      return fail_msg("mfp_integrand: cut on a non-existent particle");
+    if (c.var < 0 || c.var > CUT_DR) return fail_msg("mfp_integrand: unknown cut variable");
     a.cuts.c[i] = Cut{c.var, c.particle, c.has_min, c.has_max, c.vmin, c.vmax};
   }
   return 0;

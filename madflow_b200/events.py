@@ -66,17 +66,25 @@ class Histogram:
 class EventSink:
     """Consumes the device event buffer after every launch of a FusedIntegrand."""
 
-    def __init__(self, integrand, histograms=(), unweight=False, capacity=1_000_000, seed=1234, wmax=None):
+    def __init__(self, integrand, histograms=(), unweight=False, capacity=1_000_000, seed=1234, wmax=None, wmax_scale=8.0):
+        """unweight: keep slot i with probability min(1, |w_i| / wmax) and weight sign(w_i) max(|w_i|, wmax) -- an
+        unbiased sample in which all events but the few above wmax carry the same weight.  wmax: fixed threshold,
+        or None: min(largest weight seen, wmax_scale * sum w^2 / sum |w|) from the launches seen so far (the
+        first launch only feeds the statistics).  With the heavy-tailed weights of a flat phase space the largest
+        weight alone would make the efficiency collapse."""
         self.integrand = integrand
         self.histograms = list(histograms)
         self.unweight = bool(unweight)
         self.capacity = int(capacity)
         self.seed = int(seed)
-        self.wmax = float(wmax) if wmax else None   # None: the largest weight seen in earlier launches
+        self.wmax = float(wmax) if wmax else None
+        self.wmax_scale = float(wmax_scale)
         self.enabled = True
         dev = config.device()
         n = integrand.nexternal
-        self._max = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._nstat = int(rt.core().mf_weight_stats_blocks())
+        self._stat_partial = torch.zeros((self._nstat, 3), dtype=torch.float64, device=dev)
+        self._stats = torch.zeros(3, dtype=torch.float64, device=dev)   # max |w|, sum |w|, sum w^2
         if self.unweight:
             self._mom = torch.empty((self.capacity, n, 4), dtype=torch.float64, device=dev)
             self._w = torch.empty(self.capacity, dtype=torch.float64, device=dev)
@@ -96,21 +104,30 @@ class EventSink:
         if self.unweight:
             wmax = self.wmax
             if wmax is None and self.launches > 0:
-                wmax = float(self._max.item())
+                wmax = self.threshold()
             if wmax:
                 # global slot index: unique per (iteration, rank, launch) as long as capacities do not change
                 rt.check(lib, lib.mf_select_events(rt.ptr(mom), rt.ptr(me), rt.ptr(weight), ctypes.c_int64(nslots),
                                                    int(mom.shape[1]), ctypes.c_double(wmax), ctypes.c_uint64(self.seed),
-                                                   ctypes.c_uint64(int(first_event) * 4 + self.launches * (1 << 40)),
+                                                   ctypes.c_uint64(2 * int(first_event) + (self.launches << 40)),
                                                    rt.ptr(self._mom), rt.ptr(self._w), rt.ptr(self._idx),
                                                    rt.ptr(self._count), ctypes.c_int64(self.capacity), rt.stream_ptr()))
-            rt.check(lib, lib.mf_max_weight(rt.ptr(me), rt.ptr(weight), ctypes.c_int64(nslots), rt.ptr(self._max),
-                                            rt.stream_ptr()))
+            rt.check(lib, lib.mf_weight_stats(rt.ptr(me), rt.ptr(weight), ctypes.c_int64(nslots), rt.ptr(self._stat_partial),
+                                              self._nstat, rt.stream_ptr()))
+            self._stats[0] = torch.maximum(self._stats[0], self._stat_partial[:, 0].max())
+            self._stats[1:] += self._stat_partial[:, 1:].sum(dim=0)
         self.launches += 1
 
     @property
     def max_weight(self):
-        return float(self._max.item())
+        return float(self._stats[0].item())
+
+    def threshold(self):
+        """The unweighting threshold the next launch will use (see __init__)."""
+        if self.wmax is not None:
+            return self.wmax
+        mx, s1, s2 = self._stats.tolist()
+        return min(mx, self.wmax_scale * s2 / s1) if s1 > 0.0 else 0.0
 
     def events(self):
         """(momenta (n, nexternal, 4), weights (n,)) of the kept events as numpy arrays, in global-index order."""

@@ -82,7 +82,7 @@ class FusedIntegrand:
         a.lab_frame = int(self.lab_frame)
         a.ncuts = len(self.cuts)
         for i, (var, particle, lo, hi) in enumerate(self.cuts):
-            a.cuts[i] = rt.mf_cut(rt.CUT_VARS[var], int(particle), lo is not None, hi is not None,
+            a.cuts[i] = rt.mf_cut(rt.CUT_VARS[var], rt.cut_particle(var, particle), lo is not None, hi is not None,
                                   float(lo) if lo is not None else 0.0, float(hi) if hi is not None else 0.0)
         k = config.get_constants()
         a.pi, a.acc, a.gev2pb, a.sqh = k.PI, k.ACC, k.GEV2PB, k.SQH

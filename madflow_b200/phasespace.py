@@ -12,6 +12,8 @@ import ctypes
 import logging
 
 import numpy as np
+import math
+
 import torch
 
 from . import _runtime as rt
@@ -92,7 +94,7 @@ def _phasespace(xrand, nparticles, com_sqrts, masses, cuts, lab):
     ok = torch.empty(nevt, dtype=torch.uint8, device=dev) if cuts else None
     carr = (rt.mf_cut * max(len(cuts), 1))()
     for i, (var, particle, lo, hi) in enumerate(cuts):
-        carr[i] = rt.mf_cut(rt.CUT_VARS[var], particle, lo is not None, hi is not None,
+        carr[i] = rt.mf_cut(rt.CUT_VARS[var], rt.cut_particle(var, particle), lo is not None, hi is not None,
                             float(lo) if lo is not None else 0.0, float(hi) if hi is not None else 0.0)
     k = _psconst()
     lib = rt.core()
@@ -162,11 +164,35 @@ class PhaseSpaceGenerator:
         """pt of the ps point (nevents, [:], 4) (phasespace.py:417-422)"""
         return torch.sqrt(ps_point[..., 1] ** 2 + ps_point[..., 2] ** 2)
 
+    @staticmethod
+    def mij(ps_a, ps_b):
+        """Invariant mass of a pair of ps points (nevents, 4) -- extension, see register_cut."""
+        s = ps_a + ps_b
+        return torch.sqrt(torch.clamp(_invariant_mass(s), min=0.0))
+
+    @staticmethod
+    def dr(ps_a, ps_b):
+        """Delta R = sqrt(d eta^2 + d phi^2) of a pair of ps points (nevents, 4) -- extension, see register_cut."""
+        def eta(p):
+            pabs = torch.sqrt(p[..., 1] ** 2 + p[..., 2] ** 2 + p[..., 3] ** 2)
+            return 0.5 * torch.log((pabs + p[..., 3]) / (pabs - p[..., 3]))
+        dphi = torch.abs(torch.atan2(ps_a[..., 2], ps_a[..., 1]) - torch.atan2(ps_b[..., 2], ps_b[..., 1]))
+        dphi = torch.where(dphi > math.pi, 2.0 * math.pi - dphi, dphi)
+        return torch.sqrt((eta(ps_a) - eta(ps_b)) ** 2 + dphi**2)
+
     def register_cut(self, variable, particle=None, min_val=None, max_val=None):
-        """Register min_val < variable(particle) < max_val (phasespace.py:424-478)."""
+        """Register min_val < variable(particle) < max_val (phasespace.py:424-478).
+
+        Extension: the pair variables "mij" (invariant mass) and "dr" (Delta R) take particle=(i, j).  The
+        reference only cuts on single particles, which leaves the collinear singularity between final-state
+        gluons of g g > t t~ g g (g) unregulated (its cross section is not finite with pt cuts alone)."""
         if not hasattr(self, variable) or variable not in rt.CUT_VARS:
             raise ValueError(f"{variable} is not implemented")
-        if particle is not None and particle >= self._nparticles:
+        if variable in rt.PAIR_CUTS:
+            if particle is None or len(tuple(particle)) != 2 or max(particle) >= self._nparticles or min(particle) < 0:
+                raise ValueError(f"{variable} cuts need particle=(i, j) with valid indices")
+            particle = (int(particle[0]), int(particle[1]))
+        elif particle is not None and particle >= self._nparticles:
             raise ValueError(f"Cannot apply cuts to particle {particle}, python idx starts at 0!")
         if particle is None:
             raise ValueError("madflow_b200 cuts need the `particle` argument")
@@ -175,7 +201,7 @@ class PhaseSpaceGenerator:
             return
         if len(self._cuts) >= rt.MFP_MAX_CUTS:
             raise ValueError(f"at most {rt.MFP_MAX_CUTS} cuts are supported")
-        self._cuts.append((variable, int(particle), min_val, max_val))
+        self._cuts.append((variable, particle if variable in rt.PAIR_CUTS else int(particle), min_val, max_val))
         self._cuts_info.append(f"{min_val} < {variable}({particle}) < {max_val}")
 
     @property

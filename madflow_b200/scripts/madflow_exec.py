@@ -55,6 +55,8 @@ def build_parser():
                        type=float, default=None)
     arger.add_argument("--unweighted_events", help="Capacity of the unweighted-event buffer (--histograms)", type=int,
                        default=100_000)
+    arger.add_argument("--dr_cut", help="Extension: Delta R > value between every pair of outgoing massless particles (the "
+                       "reference's pt cuts leave their collinear singularity open)", type=float, nargs="?", const=0.4)
     arger.add_argument("--seed", type=int, default=4)
     return arger
 
@@ -111,7 +113,12 @@ def madflow_main(args=None, quick_return=False):
         logger.info("Set variable muF=muR=sum(mT)/2")
     else:
         logger.info("Setting fixed muF=muR=%.2f GeV, alpha_s = 0.118", args.fixed_scale)   # madflow_exec.py:376-380
-    fi = mfi.FusedIntegrand(matrix, model, sqrts=13e3, masses=masses, pt_cut=args.pt_cut, lab_frame=True,
+    cuts = []
+    if args.dr_cut is not None:
+        light = [i for i in range(2, nparticles) if masses[i - 2] == 0.0]
+        cuts = [("dr", (i, j), args.dr_cut, None) for a, i in enumerate(light) for j in light[a + 1:]]
+        logger.info("Applying Delta R > %.2f to the pairs %s", args.dr_cut, [c[1] for c in cuts])
+    fi = mfi.FusedIntegrand(matrix, model, sqrts=13e3, masses=masses, pt_cut=args.pt_cut, cuts=cuts, lab_frame=True,
                             running=args.fixed_scale is None, alpha_s=0.118)
     if args.events_per_device:
         fi.max_events_per_launch = args.events_per_device

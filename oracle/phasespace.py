@@ -218,13 +218,28 @@ class PhaseSpaceGenerator:
     mt = staticmethod(mt)
     mt2 = staticmethod(mt2)
 
+    # pair variables (an extension of this package's PhaseSpaceGenerator, not in the reference): particle=(i, j)
+    @staticmethod
+    def mij(a, b):
+        s = a + b
+        return np.sqrt(np.maximum(s[..., 0] ** 2 - s[..., 1] ** 2 - s[..., 2] ** 2 - s[..., 3] ** 2, 0.0))
+
+    @staticmethod
+    def dr(a, b):
+        def eta(p):
+            pabs = np.sqrt(p[..., 1] ** 2 + p[..., 2] ** 2 + p[..., 3] ** 2)
+            return 0.5 * np.log((pabs + p[..., 3]) / (pabs - p[..., 3]))
+        dphi = np.abs(np.arctan2(a[..., 2], a[..., 1]) - np.arctan2(b[..., 2], b[..., 1]))
+        dphi = np.where(dphi > np.pi, 2.0 * np.pi - dphi, dphi)
+        return np.sqrt((eta(a) - eta(b)) ** 2 + dphi**2)
+
     def register_cut(self, variable, particle=None, min_val=None, max_val=None):
         """phasespace.py:424-478: min < var(p_particle) < max, strict inequalities."""
         try:
             fun = getattr(self, variable)
         except AttributeError:
             raise ValueError(f"{variable} is not implemented")
-        if particle is not None and particle >= self._n:
+        if particle is not None and not isinstance(particle, tuple) and particle >= self._n:
             raise ValueError(f"Cannot apply cuts to particle {particle}, python idx starts at 0!")
         self._cuts.append((fun, particle, min_val, max_val))
 
@@ -234,7 +249,10 @@ class PhaseSpaceGenerator:
         if self._cuts:
             ok = np.ones(ps.shape[0], dtype=bool)
             for fun, particle, lo, hi in self._cuts:
-                val = fun(ps[:, particle, :] if particle is not None else ps)
+                if isinstance(particle, tuple):
+                    val = fun(ps[:, particle[0], :], ps[:, particle[1], :])
+                else:
+                    val = fun(ps[:, particle, :] if particle is not None else ps)
                 if lo is not None:
                     ok &= val > lo
                 if hi is not None:

@@ -141,7 +141,7 @@ class Vegas:
 
 
 def make_cross_section(ir, params_fn, sqrts, masses, pt_cut=None, const=None, lab_frame=True,
-                       alpha_s_fn=None):
+                       alpha_s_fn=None, cuts=()):
     """The integrand of scripts/madflow_exec.py:422-470 with --no_pdf (luminosity 1):
     ramboflow -> cuts on COM momenta -> boost -> alpha_s(q2=(sum mT/2)^2) or frozen ->
     smatrix * wts, zeros at cut events."""
@@ -153,6 +153,8 @@ def make_cross_section(ir, params_fn, sqrts, masses, pt_cut=None, const=None, la
     if pt_cut is not None:
         for i in range(2, n):
             gen.register_cut("pt", particle=i, min_val=pt_cut)
+    for var, particle, lo, hi in cuts:
+        gen.register_cut(var, particle=particle, min_val=lo, max_val=hi)
 
     def cross_section(xrand, n_dim=None, weight=None):
         all_ps, wts, x1, x2, idx = gen(xrand)
@@ -165,7 +167,7 @@ def make_cross_section(ir, params_fn, sqrts, masses, pt_cut=None, const=None, la
         else:
             params = params_fn(None)
         val = om.smatrix(ir, all_ps, params, const) * wts
-        if pt_cut is not None:
+        if pt_cut is not None or cuts:
             ret[idx[:, 0]] = val
         else:
             ret = val

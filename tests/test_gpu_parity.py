@@ -465,7 +465,7 @@ def test_event_histogram_and_unweighting_kernels(mf):
     obs = {"pt": pt, "eta": 0.5 * np.log((pabs + p[:, 3]) / (pabs - p[:, 3])),
            "rapidity": 0.5 * np.log((p[:, 0] + p[:, 3]) / (p[:, 0] - p[:, 3])), "energy": p[:, 0],
            "mass": np.sqrt(np.maximum(p[:, 0] ** 2 - pabs**2, 0.0))}
-    ranges = {"pt": (0.0, 300.0), "eta": (-4.0, 4.0), "rapidity": (-2.0, 2.0), "energy": (50.0, 400.0), "mass": (49.0, 51.0)}
+    ranges = {"pt": (0.0, 300.0), "eta": (-4.0, 4.0), "rapidity": (-2.0, 2.0), "energy": (50.0, 400.0), "mass": (49.013, 51.017)}   # 50 GeV must not sit on a bin edge
     for name, vals in obs.items():
         lo, hi = ranges[name]
         h = mf.events.Histogram(name, 3, lo, hi, 40)
@@ -473,11 +473,14 @@ def test_event_histogram_and_unweighting_kernels(mf):
         h.fill(d_mom, d_w1, d_w2)
         ref, _ = np.histogram(vals, bins=np.linspace(lo, hi, 41), weights=w)
         got = h.values(2, with_overflow=True)
-        np.testing.assert_allclose(got[1:-1], ref, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(got[1:-1], ref, rtol=1e-9, atol=1e-9, err_msg=name)
         np.testing.assert_allclose(got[0] + got[-1], np.sum(w[(vals < lo) | (vals >= hi)]), rtol=1e-9, atol=1e-9)
-    dmax = torch.zeros(1, dtype=torch.float64, device="cuda")
-    rt.check(lib, lib.mf_max_weight(rt.ptr(d_w1), rt.ptr(d_w2), ctypes.c_int64(n), rt.ptr(dmax), rt.stream_ptr()))
+    nb = int(lib.mf_weight_stats_blocks())
+    part = torch.zeros((nb, 3), dtype=torch.float64, device="cuda")
+    rt.check(lib, lib.mf_weight_stats(rt.ptr(d_w1), rt.ptr(d_w2), ctypes.c_int64(n), rt.ptr(part), nb, rt.stream_ptr()))
+    dmax = part[:, 0].max()
     assert dmax.item() == np.max(np.abs(w))
+    np.testing.assert_allclose(cpu(part[:, 1:].sum(dim=0)), [np.sum(np.abs(w)), np.sum(w * w)], rtol=1e-12)
     # unweighting: with wmax = max|w| every kept event has |weight| = wmax and the kept fraction is <|w|>/wmax
     cap = n
     o_mom = torch.empty((cap, nx, 4), dtype=torch.float64, device="cuda")
@@ -516,23 +519,26 @@ def test_event_sink_histograms_and_lhe(mf, tmp_path):
     v.run_integration(2, log_time=False)
     v.freeze_grid()
     hists = [mf.events.Histogram("pt", 2, 0.0, 300.0, 50), mf.events.Histogram("eta", 2, -4.0, 4.0, 50)]
-    sink = mf.events.EventSink(fi, histograms=hists, unweight=True, capacity=50_000, seed=3)
+    wmax = 20.0 * v.history[-1][0] / 200_000   # 20 x the mean weight of an iteration
+    sink = mf.events.EventSink(fi, histograms=hists, unweight=True, capacity=50_000, seed=3, wmax=wmax)
     results = [v.run_iteration() for _ in range(3)]
     for h in hists:
         total = np.sum(h.values(1, with_overflow=True))
         np.testing.assert_allclose(total, sum(r[0] for r in results), rtol=1e-10)
     mom, w = sink.events()
-    assert 0 < len(w) <= 50_000 and not sink.overflowed
-    assert np.all(np.abs(w) >= sink.max_weight * 0.0) and np.all(w > 0)
+    assert 1000 < len(w) <= 50_000 and not sink.overflowed
+    assert np.all(w >= wmax) and np.mean(w == wmax) > 0.3 and sink.max_weight >= np.max(w)
+    # unbiased: the kept weights add up to the integral of the three iterations, within the sampling error
+    assert abs(np.sum(w) - sum(r[0] for r in results)) < 5.0 * np.sqrt(np.sum(w * w))
     np.testing.assert_allclose(np.sum(mom[:, :2], axis=1), np.sum(mom[:, 2:], axis=1), rtol=1e-9, atol=1e-6)
     np.testing.assert_allclose(mom[:, 2, 0] ** 2 - np.sum(mom[:, 2, 1:] ** 2, axis=-1), MT * MT, rtol=1e-7)
     assert np.all(np.hypot(mom[:, 2:, 1], mom[:, 2:, 2]) > 30.0)
-    # unweighted sample ~ the weighted histogram (shape): compare the mean top pt
-    pt_w = np.sum(hists[0].values(3) * 0.5 * (hists[0].edges[1:] + hists[0].edges[:-1])) / np.sum(hists[0].values(3))
+    # the unweighted sample has the shape of the weighted histogram: top-pt spectrum bin by bin, within 5 sigma
     pt_top = np.hypot(mom[:, 2, 1], mom[:, 2, 2])
-    sel = pt_top < 300.0
-    pt_u = np.average(pt_top[sel], weights=w[sel])
-    assert abs(pt_u / pt_w - 1) < 0.1
+    hu, _ = np.histogram(pt_top, bins=hists[0].edges, weights=w)
+    hu2, _ = np.histogram(pt_top, bins=hists[0].edges, weights=w * w)
+    hw = hists[0].values(1)   # summed over the three iterations, like the kept events
+    assert np.all(np.abs(hu - hw) < 5.0 * np.sqrt(hu2) + 0.05 * hw + 1e-12)
     res, err, _ = mf.vegas.combine_iterations(results)
     with LheWriter(tmp_path, "run_01", no_unweight=True, pdg=m.ir["pdg"]) as lw:
         n = sink.write_lhe(lw, cross=res)
@@ -544,3 +550,37 @@ def test_event_sink_histograms_and_lhe(mf, tmp_path):
     np.testing.assert_allclose([[p.E, p.px, p.py, p.pz] for p in back[5]], mom[5], rtol=1e-10)
     assert back[0].wgt == pytest.approx(res, rel=1e-7)
     np.testing.assert_allclose(np.loadtxt(tmp_path / "cross_err.txt"), [res, err])
+
+
+def test_pair_cuts_extension(mf):
+    """Delta R and invariant-mass cuts on pairs of particles (an extension: they regulate the final-state collinear
+    singularity the reference's single-particle cuts leave open): fused kernel == separate API calls == oracle."""
+    from madflow_b200 import procgen
+
+    ir = procgen.generate_ir(2)
+    masses = [MT, MT, 0.0, 0.0]
+    cuts = [("dr", (4, 5), 0.4, None), ("mij", (2, 3), None, 3000.0)]
+    m, model = mf.matrix.get_process("1_gg_ttxgg")
+    fi = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=masses, pt_cut=30.0, cuts=cuts, lab_frame=True, running=True)
+    nev = 3000
+    v1 = mf.vegas.VegasFlow(fi.n_dim, nev, seed=4)
+    v1.compile(fi)
+    r1 = v1.run_iteration()
+    v2 = mf.vegas.VegasFlow(fi.n_dim, nev, seed=4)
+    v2.compile(fi.python_integrand())
+    r2 = v2.run_iteration()
+    assert abs(r1[0] / r2[0] - 1) < 1e-10 and v1.last_me_events == v2.last_me_events
+    xs = ovegas.make_cross_section(ir, lambda a: sm_params(alpha_s=a), 13e3, masses, pt_cut=30.0, lab_frame=True, cuts=cuts,
+                                   alpha_s_fn=lambda q2: 0.118 / (1 + 0.118 * fi.b0 * np.log(q2 / fi.mz2)))
+    ov = ovegas.Vegas(fi.n_dim, nev, seed=4)
+    ov.compile(xs)
+    r0 = ov.run_iteration()
+    assert abs(r1[0] / r0[0] - 1) < 1e-10
+    # the pair cuts do remove events on top of the pt cuts
+    fi0 = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=masses, pt_cut=30.0, lab_frame=True, running=True)
+    v0 = mf.vegas.VegasFlow(fi.n_dim, nev, seed=4)
+    v0.compile(fi0)
+    v0.run_iteration()
+    assert v1.last_me_events < v0.last_me_events
+    with pytest.raises(ValueError):
+        mf.phasespace.PhaseSpaceGenerator(6, 13e3, masses).register_cut("dr", particle=4, min_val=0.4)
