@@ -355,7 +355,13 @@ def emit_hp(ir):
     for k, r in enumerate(amp_rows):
         by_pair.setdefault(r["pair"], []).append(k)
     batches, cur_pairs, cur_amps, fill = [], [], [], 0
-    for pi in sorted(by_pair, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
+    sig_id = {}
+    for r in amp_rows:   # colour signature of an amplitude: its JAMP coefficients up to a common phase
+        t = by_amp[r["am"]["call"]["amp"]]
+        c0 = complex(t[0][1], t[0][2])
+        r["sig"] = sig_id.setdefault(tuple((j, complex(re, im) / c0) for j, re, im in sorted(t)), len(sig_id))
+    # ... and within a kind, pair objects whose amplitudes share a colour signature next to each other (see the JAMP code)
+    for pi in sorted(by_pair, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], min(amp_rows[k]["sig"] for k in by_pair[q]), q)):
         need = 4 * pairs[pi]["nv"]
         assert need <= scratch and len(by_pair[pi]) <= NB
         if fill + need > scratch or len(cur_amps) + len(by_pair[pi]) > NB:
@@ -411,20 +417,45 @@ def emit_hp(ir):
                         trow.append(f"{{{pr['off']}, {xw['off'] + 2}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
                                     f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
             brow.append(f"{{{ib}, {len(irow)}, {tb}, {len(trow)}}}")
+    # JAMP code per (batch, colour group).  Amplitudes of a batch that feed the same colours of the group with the
+    # same coefficients up to a common phase (+-1, +-i) are summed first and the sum is applied once:
+    #   J_c += k_c (A_0 + p_1 A_1 + ...)   instead of   J_c += k_c A_0; J_c += k_c p_1 A_1; ...
+    def phase_add(dst, ph, src):
+        """C++ statement dst += ph * src for ph in {1, -1, i, -i}"""
+        if ph == 1:
+            return f"{dst} += {src};"
+        if ph == -1:
+            return f"{dst} -= {src};"
+        return f"{dst} += mul_i({src});" if ph == 1j else f"{dst} += mul_mi({src});"
+
     jamp_cases = [[] for _ in range(NCG)]
+    jamp_terms = 0
     for bi, (cur_pairs, cur_amps) in enumerate(batches):
-        upd = [[] for _ in range(NCG)]
-        for slot, k in enumerate(cur_amps):
-            am = amp_rows[k]["am"]
-            per_cg = [[] for _ in range(NCG)]
-            for j, re, im in by_amp[am["call"]["amp"]]:
-                cg, jl = divmod(j, NJ)
-                per_cg[cg].append(_jamp_update(jl, re, im, "a").replace(f"J{jl} ", f"J[{jl}] "))
-            for cg in range(NCG):
-                if per_cg[cg]:
-                    upd[cg].append(f"{{ const cxd a = ab[{slot * NHP}]; " + " ".join(per_cg[cg]) + " }")
         for cg in range(NCG):
-            jamp_cases[cg].append(f"      case {bi}: {{ " + "\n        ".join(upd[cg]) + " } break;")
+            groups = {}   # signature within the colour group -> [(slot, phase relative to the group's first amplitude)]
+            for slot, k in enumerate(cur_amps):
+                terms = [(j - cg * NJ, complex(re, im)) for j, re, im in by_amp[amp_rows[k]["am"]["call"]["amp"]] if j // NJ == cg]
+                if not terms:
+                    continue
+                unit = all(c in (1, -1, 1j, -1j) for _, c in terms)
+                c0 = terms[0][1] if unit else 1.0
+                sig = tuple((jl, c / c0) for jl, c in sorted(terms)) if unit else ("own", slot)
+                groups.setdefault(sig, []).append((slot, c0, terms))
+            stm = []
+            for sig, members in groups.items():
+                slot0, c00, terms0 = members[0]
+                if len(members) == 1:
+                    upd = " ".join(_jamp_update(jl, c.real, c.imag, "a").replace(f"J{jl} ", f"J[{jl}] ") for jl, c in terms0)
+                    stm.append(f"{{ const cxd a = ab[{slot0 * NHP}]; {upd} }}")
+                    jamp_terms += len(terms0)
+                    continue
+                body = [f"cxd a = ab[{slot0 * NHP}];"]
+                for slot, c0, _ in members[1:]:
+                    body.append(phase_add("a", c0 / c00, f"ab[{slot * NHP}]"))
+                body += [_jamp_update(jl, c.real, c.imag, "a").replace(f"J{jl} ", f"J[{jl}] ") for jl, c in terms0]
+                stm.append("{ " + " ".join(body) + " }")
+                jamp_terms += len(members) - 1 + len(terms0)
+            jamp_cases[cg].append(f"      case {bi}: {{ " + "\n        ".join(stm) + " } break;")
     tables += "\n" + both("mf::HpPair", "pairs", max(len(prow), 1), ",\n  ".join(prow) if prow else "{0}", const=not big)
     tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0}", const=not big)
     tables += "\n" + both("mf::HpTile", "tiles", max(len(trow), 1), ",\n  ".join(trow) if trow else "{0}", const=len(trow) * 32 <= 24576)
@@ -484,7 +515,7 @@ def emit_hp(ir):
         U.append("    return 0.0;  // not used: the amplitudes of this process run on the tensor cores")
     return tables, "\n".join(A), C, "\n".join(U), dict(
         wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items), namps=len(used), unroll=unroll,
-        nbatch=len(batches), npairs=len(pairs), nitems_pair=len(irow), ntiles=len(trow), ncg=1 if unroll else NCG,
+        nbatch=len(batches), npairs=len(pairs), nitems_pair=len(irow), ntiles=len(trow), ncg=1 if unroll else NCG, jamp_terms=jamp_terms,
         npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
         colour_denom=float(den[0]),
         nb=max(len(b_[1]) for b_ in batches) if batches else 1,
