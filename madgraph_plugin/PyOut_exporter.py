@@ -218,8 +218,28 @@ class PyOutExporter(export_python.ProcessExporterPython):
         shutil.rmtree(target, ignore_errors=True)
         shutil.copytree(model.get('modelpath'), target, ignore=shutil.ignore_patterns('*.pyc', '*.dat', '*.py~'))
 
+    def write_leading_order_wrapper(self, outfile, history):
+        """leading_order.py: a runnable integration script for the exported process
+        (PyOut_exporter.py:442-468, template_files/leading_order.inc)."""
+        imports, tree_level, masses = '', '\n', '\n'
+        for name, proc, mass in zip(self.me_names, self.proc_names, self.mass_lists):
+            info = {'me': name, 'proc': proc, 'me_class': name.capitalize()}
+            imports += 'from %(me)s import %(me_class)s, get_model_param as model_%(proc)s\n' % info
+            tree_level += '    "%(proc)s": (%(me_class)s, model_%(proc)s),\n' % info
+            masses += ('    "%s": [' % proc) + ", ".join('"%s"' % m for m in mass) + '],\n'
+        try:
+            info_lines = "Generated with the madflow B200 backend and MG5_aMC v%s" % misc.get_pkg_info().get('version', '?')
+        except Exception:
+            info_lines = "Generated with the madflow B200 backend"
+        hist = "\n".join(str(h) for h in history) if history else ""
+        template = open(pjoin(plugin_path, 'template_files', 'leading_order_cuda.inc')).read()
+        outfile.write(template % {'info_lines': info_lines, 'history': hist, 'matrix_element_imports': imports,
+                                  'tree_level_keys': tree_level, 'masses': masses})
+
     def finalize(self, matrix_elements, history, mg5options, flaglist):
-        """Cards/param_card.dat and the command history (PyOut_exporter.py:544-559)."""
+        """leading_order.py, Cards/param_card.dat and the command history (PyOut_exporter.py:544-559)."""
+        with open(pjoin(self.dir_path, 'leading_order.py'), 'w') as fout:
+            self.write_leading_order_wrapper(fout, history)
         cardpath = pjoin(self.dir_path, 'Cards')
         if not os.path.isdir(cardpath):
             os.mkdir(cardpath)

@@ -185,3 +185,24 @@ def test_aloha_cpp_to_cuda_retargeting():
     assert cu.startswith("__device__ __forceinline__ void VVV1P0_1(const cxtype V2[], const cxtype V3[], cxtype COUP")
     assert "cxtype V1[])" in cu and "const cxtype V1[]" not in cu
     assert "const cxtype cI(0., 1.);" in cu and "static" not in cu and "std::complex" not in cu
+
+
+def test_leading_order_wrapper(tmp_path):
+    """finalize() writes leading_order.py like the reference's exporter (PyOut_exporter.py:442-468, 544-549); the
+    script is valid Python that imports the generated matrix module and builds the fused integrand."""
+    import ast
+    import io
+
+    from madgraph_plugin import PyOut_exporter
+
+    exp = PyOut_exporter.PyOutExporter.__new__(PyOut_exporter.PyOutExporter)
+    exp.dir_path = str(tmp_path)
+    exp.me_names, exp.proc_names, exp.mass_lists = ["matrix_1_gg_ttx"], ["1_gg_ttx"], [["ZERO", "ZERO", "mdl_MT", "mdl_MT"]]
+    out = io.StringIO()
+    exp.write_leading_order_wrapper(out, ["generate g g > t t~", "output pyout out"])
+    text = out.getvalue()
+    ast.parse(text)
+    assert "from matrix_1_gg_ttx import Matrix_1_gg_ttx, get_model_param as model_1_gg_ttx" in text
+    assert '"1_gg_ttx": (Matrix_1_gg_ttx, model_1_gg_ttx)' in text
+    assert '"1_gg_ttx": ["ZERO", "ZERO", "mdl_MT", "mdl_MT"]' in text
+    assert "generate g g > t t~" in text and "FusedIntegrand(matrix, model, sqrts=SQRTS" in text
