@@ -31,6 +31,7 @@ struct EventBuffer {
   int* count;
   long long cap;   // total slots = nseg * seg
   long long seg;   // slots per segment (multiple of the generator's block size)
+  long long per;   // generated events per segment = ceil(nevents / nseg): the segments are filled evenly
   int nseg;
 };
 
@@ -60,16 +61,16 @@ __global__ void __launch_bounds__(GEN_BLOCK) ps_generate_kernel(const GenArgs a)
   __syncthreads();
   const EventBuffer& q = a.buf;
   for (int sgi = blockIdx.x; sgi < q.nseg; sgi += gridDim.x) {
-    const long long ev_begin = (long long)sgi * q.seg;
-    const long long base = ev_begin;  // segment sgi owns slots [base, base + seg)
+    const long long ev_begin = (long long)sgi * q.per;  // segment sgi generates events [ev_begin, ev_begin + per)
+    const long long base = (long long)sgi * q.seg;      // ... and owns slots [base, base + seg)
     int filled = 0;
-    for (long long off = 0; off < q.seg; off += B) {
+    for (long long off = 0; off < q.per; off += B) {
       const long long local = ev_begin + off + tid;
       bool ok = false;
       double m[NEXT][4];
       double wgt = 0.0, as = 0.0;
       unsigned char bins[NDIM];
-      if (local < a.u.nevents) {
+      if (off + tid < q.per && local < a.u.nevents) {
         const unsigned long long ev = a.u.first_event + (unsigned long long)local;
         double xr[NDIM];
         double w = 1.0;
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const double* f, 
 
 // carve the caller's workspace into the event buffer; returns bytes needed (buf may be null)
 inline size_t event_buffer_layout(long long nevents, int nseg, int next, int ndim, void* workspace, EventBuffer* buf) {
-  long long seg = (nevents + nseg - 1) / nseg;
-  seg = ((seg + GEN_BLOCK - 1) / GEN_BLOCK) * GEN_BLOCK;
+  const long long per = (nevents + nseg - 1) / nseg;
+  const long long seg = ((per + GEN_BLOCK - 1) / GEN_BLOCK) * GEN_BLOCK;
   const long long cap = seg * nseg;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -198,7 +199,7 @@ inline size_t event_buffer_layout(long long nevents, int nseg, int next, int ndi
     buf->me = reinterpret_cast<double*>(p + o_me);
     buf->bins = reinterpret_cast<unsigned char*>(p + o_bins);
     buf->count = reinterpret_cast<int*>(p + o_cnt);
-    buf->cap = cap, buf->seg = seg, buf->nseg = nseg;
+    buf->cap = cap, buf->seg = seg, buf->per = per, buf->nseg = nseg;
   }
   return off;
 }
