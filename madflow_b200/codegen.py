@@ -294,7 +294,22 @@ def emit_hp(ir):
                     f"{{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
                     f"{{{vm[0]}, {vm[1]}, {vm[2]}}}}}")
     L.append(both("mf::HpItem", "items", max(len(rows), 1), ",\n  ".join(rows) if rows else "{0}"))
-    begins = [sum(1 for it in items if wfs[it["out"]]["level"] < lev) for lev in range(0, maxlevel + 2)]
+
+    def pext(v, m):
+        return sum(((v >> b_) & 1) << q for q, b_ in enumerate(b2 for b2 in range(5) if m >> b2 & 1))
+
+    # work items of the current phases: (current, variant, variants of the inputs), level by level
+    crow, begins = [], []
+    for lev in range(0, maxlevel + 2):
+        begins.append(len(crow))
+        for idx, it in enumerate(items):
+            W = wfs[it["out"]]
+            if W["level"] != lev:
+                continue
+            masks = [vmask(W["legs"], wfs[i]["legs"]) for i in it["in"]] + [0] * (3 - len(it["in"]))
+            for v in range(W["nv"]):
+                crow.append(f"{{{idx}, {v}, {{{pext(v, masks[0])}, {pext(v, masks[1])}, {pext(v, masks[2])}}}, 0}}")
+    L.append(both("mf::HpPairItem", "cur_items", max(len(crow), 1), ", ".join(crow) if crow else "{0, 0, {0, 0, 0}, 0}", const=False))
     L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
     tables = "\n".join(L)
 
@@ -403,8 +418,11 @@ def emit_hp(ir):
         for bi, (cur_pairs, cur_amps) in enumerate(batches):
             ib, tb = len(irow), len(trow)
             for pi in sorted(cur_pairs, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
-                for v in vrange(pairs[pi]["legs"], pairs[pi]["nv"], p):
-                    irow.append(f"{{{pi}, {v}}}")
+                pr = pairs[pi]
+                masks = [vmask(pr["legs"], wfs[w]["legs"]) for w in pr["rest"]] + [0] * (3 - len(pr["rest"]))
+                for v in vrange(pr["legs"], pr["nv"], p):
+                    iv = [pext(v, m) for m in masks]
+                    irow.append(f"{{{pi}, {v}, {{{iv[0]}, {iv[1]}, {iv[2]}}}, 0}}")
             for slot, k in enumerate(cur_amps):
                 r = amp_rows[k]
                 xw, pr = wfs[r["x"]], pairs[r["pair"]]
@@ -458,7 +476,7 @@ def emit_hp(ir):
                 jamp_terms += len(members) - 1 + len(terms0)
             jamp_cases[cg].append(f"      case {bi}: {{ " + "\n        ".join(stm) + " } break;")
     tables += "\n" + both("mf::HpPair", "pairs", max(len(prow), 1), ",\n  ".join(prow) if prow else "{0}", const=not big)
-    tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0}", const=not big)
+    tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0, {0, 0, 0}, 0}", const=False)
     tables += "\n" + both("mf::HpTile", "tiles", max(len(trow), 1), ",\n  ".join(trow) if trow else "{0}", const=len(trow) * 32 <= 24576)
     tables += "\n" + both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}")
 
@@ -675,11 +693,12 @@ struct Proc {{
   MF_DEV static const double* cfsym() {{ return MF_TAB(cfsym); }}
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
-  MF_DEV static mf::HpItem item(int i) {{ return MF_TAB(items)[i]; }}
+  MF_DEV static mf::HpItem item(int i) {{ return mf::hp_fetch32(&MF_TAB(items)[i]); }}
   MF_DEV static int level_begin(int L) {{ return MF_TAB(level_begin)[L]; }}
   MF_DEV static const mf::HpTile* tile(int i) {{ return &MF_TAB(tiles)[i]; }}
-  MF_DEV static mf::HpPair pair(int i) {{ return MF_TAB(pairs)[i]; }}
-  MF_DEV static mf::HpPairItem pair_item(int i) {{ return MF_TAB(pair_items)[i]; }}
+  MF_DEV static mf::HpPair pair(int i) {{ return mf::hp_fetch32(&MF_TAB(pairs)[i]); }}
+  MF_DEV static mf::HpPairItem pair_item(int i) {{ return MF_TAB(pair_items)[i]; }}  // one 8-byte load
+  MF_DEV static mf::HpPairItem cur_item(int i) {{ return MF_TAB(cur_items)[i]; }}
   MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
   // JAMP updates of batch `b` for colour group `cg` (warp-uniform switches): ab = the event's amplitude
   // buffer at this thread's helicity combination, row r at ab[r * HP_NHP]; JAMP registers addressed statically

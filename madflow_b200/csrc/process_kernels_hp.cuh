@@ -66,7 +66,8 @@ struct HpExt {
 // 2^n combinations only a 4-term complex dot product.
 enum HpPairType : unsigned char { HP_Q_ROW = 0, HP_Q_COL = 1, HP_Q_CUR = 2, HP_Q_VVV = 3, HP_Q_VVVV = 4 };
 
-struct HpPair {
+// (32 bytes, fetched with two 16-byte loads: hp_fetch32)
+struct alignas(16) HpPair {
   unsigned char type, nin, coup, coup_neg;
   unsigned char term[2];       // HP_Q_VVVV: sign<<6 | vector<<4 | dotA<<2 | dotB  (indices into the inputs)
   unsigned short nv;           // helicity variants of the object
@@ -74,11 +75,16 @@ struct HpPair {
   unsigned short in_off[3];    // inputs: offset of the wavefunction block in the event's area
   unsigned short in_nv[3];
   unsigned char vmask[3];      // bits of the object's variant index that form the input's variant index
+  unsigned char pad[7];
 };
+static_assert(sizeof(HpPair) == 32, "HpPair is fetched as two 16-byte words");
 
-struct HpPairItem {
-  unsigned short pair, v;      // work item of a pair phase: (object, helicity variant)
+struct alignas(8) HpPairItem {  // work item of a pair phase: (object, helicity variant) and, precomputed, the
+  unsigned short pair;          // variants of the object's inputs that belong to it
+  unsigned char v, iv[3];
+  unsigned short pad;
 };
+static_assert(sizeof(HpPairItem) == 8, "HpPairItem is fetched with one 8-byte load");
 
 // One tensor-core work item of the amplitude phase: rows = 8 helicity variants of the pair object Q
 // (from variant q0), columns = 8 variants of the wavefunction x (from x0); element (r, c) is the
@@ -96,14 +102,29 @@ struct HpBatch {   // one (helicity pass, batch): its pair-object work items and
   int item_begin, item_end, tile_begin, tile_end;
 };
 
-struct HpItem {
+struct alignas(16) HpItem {
   unsigned char type, nin;
   signed char mass_idx, width_idx;   // < 0: ZERO
   unsigned char coup, coup_neg;
   unsigned short out_off, out_nv;    // output wavefunction block (offset in the event's area, variants)
   unsigned short in_off[3], in_nv[3];
   unsigned char vmask[3];            // bits of the output's variant index that form the input's variant index
+  unsigned char pad[7];
 };
+static_assert(sizeof(HpItem) == 32, "HpItem is fetched as two 16-byte words");
+
+// a 32-byte table row with two 16-byte loads instead of one load per field
+template <class T>
+MF_DEV T hp_fetch32(const T* p) {
+  static_assert(sizeof(T) == 32, "two 16-byte words");
+  union {
+    uint4 w[2];
+    T t;
+  } u;
+  u.w[0] = reinterpret_cast<const uint4*>(p)[0];
+  u.w[1] = reinterpret_cast<const uint4*>(p)[1];
+  return u.t;
+}
 
 // phase 1: work item `it` in [0, NEXT*E*2) = (leg, event, helicity)
 template <class P>
@@ -130,36 +151,28 @@ MF_DEV void hp_externals(int it, int E, const double* mom /*[E][NEXT][4]*/, cons
 // (8 lanes = 3 arbitrary helicity bits) over the banks
 MF_DEV int hp_abuf_pos(int h) { return h ^ ((h >> 3) & 7); }
 
-// the input's helicity variant for output variant v: the bits of v selected by `mask`, packed
-MF_DEV int hp_pext(int v, int mask) {
-  int out = 0, pos = 0;
-#pragma unroll
-  for (int b = 0; b < 5; ++b)
-    if (mask & (1 << b)) {
-      out |= ((v >> b) & 1) << pos;
-      ++pos;
-    }
-  return out;
-}
-
 // position of (component k, helicity variant v) inside an object of nv variants (see the header)
 MF_DEV int hp_slot(int k, int nv, int v) { return k * nv + (v ^ ((2 * k) & (nv - 1))); }
 
-// the 6 slots of one helicity variant of a wavefunction block
-MF_DEV void hp_load(const cxd* blk, int nv, int v, cxd out[6]) {
-  out[0] = blk[0], out[1] = blk[1];
+// the four components of one helicity variant of a wavefunction block (slots 2..5), and all 6 slots
+MF_DEV void hp_load_comp(const cxd* blk, int nv, int v, cxd out[6]) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) out[2 + k] = blk[2 + hp_slot(k, nv, v)];
 }
+MF_DEV void hp_load(const cxd* blk, int nv, int v, cxd out[6]) {
+  out[0] = blk[0], out[1] = blk[1];
+  hp_load_comp(blk, nv, v, out);
+}
 
-// phase 2: work item (item index `idx`, output variant v) of the event whose area is wf_e
+// phase 2: work item (current, output variant, variants of its inputs) of the event whose area is wf_e
 template <class P>
-MF_DEV void hp_current(int idx, int v, const double* par, const cxd* coup_e, cxd* wf_e) {
-  const HpItem it = P::item(idx);
+MF_DEV void hp_current(const HpPairItem w, const double* par, const cxd* coup_e, cxd* wf_e) {
+  const HpItem it = P::item(w.pair);
+  const int v = w.v;
   cxd a[6], b[6], c[6], r[6];
-  hp_load(wf_e + it.in_off[0], it.in_nv[0], hp_pext(v, it.vmask[0]), a);
-  hp_load(wf_e + it.in_off[1], it.in_nv[1], hp_pext(v, it.vmask[1]), b);
-  if (it.nin > 2) hp_load(wf_e + it.in_off[2], it.in_nv[2], hp_pext(v, it.vmask[2]), c);
+  hp_load(wf_e + it.in_off[0], it.in_nv[0], w.iv[0], a);
+  hp_load(wf_e + it.in_off[1], it.in_nv[1], w.iv[1], b);
+  if (it.nin > 2) hp_load(wf_e + it.in_off[2], it.in_nv[2], w.iv[2], c);
   cxd cp = coup_e[it.coup];
   if (it.coup_neg) cp = -cp;
   const double M = it.mass_idx < 0 ? 0.0 : par[it.mass_idx];
@@ -201,13 +214,36 @@ MF_DEV void hp_load_amp(const cxd* wf_e, const unsigned char* vtab, int h, int w
   hp_load(wf_e + d.off, d.nv, vtab[d.legs * P::NCOMB + h], out);
 }
 
-// pair phase: work item (object pi, event e, variant v) -> Q[4] into the scratch area
+// K += sign * in[vi] * (in[da] . in[db]) for one term of a four-gluon structure (all indices warp-uniform)
+MF_DEV void hp_quartic_term(unsigned char d, const cxd a[6], const cxd b[6], const cxd c[6], cxd d01, cxd d02, cxd d12,
+                            cxd K[4]) {
+  const int vi = (d >> 4) & 3, key = ((d >> 2) & 3) + (d & 3);  // dot: {0,1} -> 1, {0,2} -> 2, {1,2} -> 3
+  cxd dot = key == 1 ? d01 : (key == 2 ? d02 : d12);
+  if (d & 0x40) dot = -dot;
+  switch (vi) {
+    case 0:
+#pragma unroll
+      for (int k = 0; k < 4; ++k) K[k] = fma_c(a[2 + k], dot, K[k]);
+      break;
+    case 1:
+#pragma unroll
+      for (int k = 0; k < 4; ++k) K[k] = fma_c(b[2 + k], dot, K[k]);
+      break;
+    default:
+#pragma unroll
+      for (int k = 0; k < 4; ++k) K[k] = fma_c(c[2 + k], dot, K[k]);
+      break;
+  }
+}
+
+// pair phase: work item (object, variant, variants of its inputs) of one event -> Q[4] into the scratch area
 template <class P>
-MF_DEV void hp_pair(int pi, int v, const cxd* coup_e, const cxd* wf_e, cxd* scratch_e) {
-  const HpPair pr = P::pair(pi);
+MF_DEV void hp_pair(const HpPairItem item, const cxd* coup_e, const cxd* wf_e, cxd* scratch_e) {
+  const HpPair pr = P::pair(item.pair);
+  const int v = item.v;
   cxd a[6], b[6], c[6];
-  hp_load(wf_e + pr.in_off[0], pr.in_nv[0], hp_pext(v, pr.vmask[0]), a);
-  hp_load(wf_e + pr.in_off[1], pr.in_nv[1], hp_pext(v, pr.vmask[1]), b);
+  hp_load_comp(wf_e + pr.in_off[0], pr.in_nv[0], item.iv[0], a);
+  hp_load_comp(wf_e + pr.in_off[1], pr.in_nv[1], item.iv[1], b);
   cxd cp = coup_e[pr.coup];
   if (pr.coup_neg) cp = -cp;
   const cxd f = mul_mi(cp);  // -i * COUP
@@ -233,7 +269,9 @@ MF_DEV void hp_pair(int pi, int v, const cxd* coup_e, const cxd* wf_e, cxd* scra
       Q[2] = f * mul_i(u0 - u1 - u2 + u3);       // -J2
       Q[3] = f * (t0 - t1 - t2 + t3);            // -J3
     } break;
-    case HP_Q_VVV: {  // a = V2, b = V3 of VVV1_0(V1,V2,V3); P1 = -(P2+P3)
+    case HP_Q_VVV: {  // a = V2, b = V3 of VVV1_0(V1,V2,V3); P1 = -(P2+P3); the only kind that needs the momenta
+      a[0] = wf_e[pr.in_off[0]], a[1] = wf_e[pr.in_off[0] + 1];
+      b[0] = wf_e[pr.in_off[1]], b[1] = wf_e[pr.in_off[1] + 1];
       const Mom P2 = mom_of(a, 1.0), P3 = mom_of(b, 1.0);
       const Mom d12 = Mom{-2.0 * P2.e - P3.e, -2.0 * P2.x - P3.x, -2.0 * P2.y - P3.y, -2.0 * P2.z - P3.z};  // P1-P2
       const Mom d31 = Mom{2.0 * P3.e + P2.e, 2.0 * P3.x + P2.x, 2.0 * P3.y + P2.y, 2.0 * P3.z + P2.z};      // P3-P1
@@ -246,23 +284,12 @@ MF_DEV void hp_pair(int pi, int v, const cxd* coup_e, const cxd* wf_e, cxd* scra
       Q[0] = f * K0, Q[1] = -(f * K1), Q[2] = -(f * K2), Q[3] = -(f * K3);
     } break;
     default: {  // HP_Q_VVVV: K = sum_t sign_t * in[vec_t] * (in[dotA_t] . in[dotB_t])
-      hp_load(wf_e + pr.in_off[2], pr.in_nv[2], hp_pext(v, pr.vmask[2]), c);
-      // the three Minkowski products once; each term picks one of them and one vector (block-uniform)
+      hp_load_comp(wf_e + pr.in_off[2], pr.in_nv[2], item.iv[2], c);
+      // the three Minkowski products once; each term picks one of them and one vector (warp-uniform)
       const cxd d01 = vdot(a, b), d02 = vdot(a, c), d12 = vdot(b, c);
       cxd K[4] = {mk(0, 0), mk(0, 0), mk(0, 0), mk(0, 0)};
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const unsigned char d = pr.term[t];
-        const int vi = (d >> 4) & 3, da = (d >> 2) & 3, db = d & 3;
-        const int key = da + db;  // {0,1} -> 1, {0,2} -> 2, {1,2} -> 3
-        cxd dot = key == 1 ? d01 : (key == 2 ? d02 : d12);
-        if (d & 0x40) dot = -dot;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const cxd V = vi == 0 ? a[2 + k] : (vi == 1 ? b[2 + k] : c[2 + k]);
-          K[k] += V * dot;
-        }
-      }
+      hp_quartic_term(pr.term[0], a, b, c, d01, d02, d12, K);
+      hp_quartic_term(pr.term[1], a, b, c, d01, d02, d12, K);
       Q[0] = f * K[0], Q[1] = -(f * K[1]), Q[2] = -(f * K[2]), Q[3] = -(f * K[3]);
     } break;
   }
@@ -479,15 +506,12 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
   MF_PROF(0);
 #pragma unroll 1
   for (int L = 2; L <= P::HP_MAXLEVEL; ++L) {
-    const int begin = P::level_begin(L), cnt = P::level_begin(L + 1) - begin;
-    const int nv = 1 << L;
-    const int total = cnt * E * nv;
+    // work items (current, variant) of this level, from a table that also holds the variants of the inputs
+    const int begin = P::level_begin(L), total = (P::level_begin(L + 1) - begin) * E;
 #pragma unroll 1
     for (int w = tid; w < total; w += T) {
-      const int ci = w / (E * nv);
-      const int r = w - ci * (E * nv);
-      const int e = r / nv, v = r - e * nv;
-      hp_current<P>(begin + ci, v, par, coup + e * P::NCOUP, ev + e * EVS);
+      const int ii = w / E, e = w - ii * E;
+      hp_current<P>(P::cur_item(begin + ii), par, coup + e * P::NCOUP, ev + e * EVS);
     }
     __syncthreads();
   }
@@ -514,8 +538,7 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
 #pragma unroll 1
         for (int w = tid; w < total; w += T) {
           const int ii = w / E, ee = w - ii * E;
-          const HpPairItem pit = P::pair_item(bt.item_begin + ii);
-          hp_pair<P>(pit.pair, pit.v, coup + ee * P::NCOUP, ev + ee * EVS, ev + ee * EVS + P::HP_WFSIZE);
+          hp_pair<P>(P::pair_item(bt.item_begin + ii), coup + ee * P::NCOUP, ev + ee * EVS, ev + ee * EVS + P::HP_WFSIZE);
         }
         __syncthreads();
         MF_PROF(2);

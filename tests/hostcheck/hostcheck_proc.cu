@@ -51,10 +51,10 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
     }
     for (int it = 0; it < Proc::NEXT * E * 2; ++it) mf::hp_externals<Proc>(it, E, mom.data(), par, sqh, evarea.data());
     for (int L = 2; L <= Proc::HP_MAXLEVEL; ++L) {
-      const int begin = Proc::level_begin(L), cnt = Proc::level_begin(L + 1) - begin, nv = 1 << L;
-      for (int w = 0; w < cnt * E * nv; ++w) {
-        const int ci = w / (E * nv), r = w - ci * (E * nv), e = r / nv, v = r - e * nv;
-        mf::hp_current<Proc>(begin + ci, v, par, cp.data() + e * Proc::NCOUP, evarea.data() + e * EVS);
+      const int begin = Proc::level_begin(L), total = (Proc::level_begin(L + 1) - begin) * E;
+      for (int w = 0; w < total; ++w) {
+        const int ii = w / E, e = w - ii * E;
+        mf::hp_current<Proc>(Proc::cur_item(begin + ii), par, cp.data() + e * Proc::NCOUP, evarea.data() + e * EVS);
       }
     }
     std::vector<double> me_h((size_t)E * NH, 0.0);
@@ -71,8 +71,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
           const mf::HpBatch bt = Proc::batch(pass * Proc::HP_NBATCH + bi);
           for (int w = 0; w < (bt.item_end - bt.item_begin) * E; ++w) {
             const int ii = w / E, ee = w - ii * E;
-            const mf::HpPairItem pit = Proc::pair_item(bt.item_begin + ii);
-            mf::hp_pair<Proc>(pit.pair, pit.v, cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS,
+            mf::hp_pair<Proc>(Proc::pair_item(bt.item_begin + ii), cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS,
                               evarea.data() + ee * EVS + Proc::HP_WFSIZE);
           }
           for (int w = 0; w < (bt.tile_end - bt.tile_begin) * E; ++w) {
