@@ -189,7 +189,8 @@ class PhaseSpaceGenerator:
         if not hasattr(self, variable) or variable not in rt.CUT_VARS:
             raise ValueError(f"{variable} is not implemented")
         if variable in rt.PAIR_CUTS:
-            if particle is None or len(tuple(particle)) != 2 or max(particle) >= self._nparticles or min(particle) < 0:
+            if (not isinstance(particle, (tuple, list)) or len(particle) != 2 or max(particle) >= self._nparticles
+                    or min(particle) < 0):
                 raise ValueError(f"{variable} cuts need particle=(i, j) with valid indices")
             particle = (int(particle[0]), int(particle[1]))
         elif particle is not None and particle >= self._nparticles:
