@@ -1,7 +1,8 @@
 /* C ABI of the process-independent library  (libmadflow_b200.so).
  *
  * HELAS external wavefunctions, ALOHA vertices (test hooks), RAMBO phase space with cuts and
- * boost, Philox/VEGAS sampling, accumulation and grid refinement, and an FP64 peak probe.
+ * boost, Philox/VEGAS sampling, accumulation and grid refinement, PDF / alpha_s interpolation, and an FP64
+ * peak probe.
  * It replaces the TensorFlow graphs of python_package/madflow/wavefunctions_flow.py and
  * phasespace.py and the vegasflow calls of scripts/madflow_exec.py:487-525 (reference has no
  * native ABI for these; its only native boundary is the per-process TF custom op, see
@@ -101,6 +102,18 @@ int mf_weight_stats(const double* d_w1, const double* d_w2, int64_t nevt, double
 int mf_select_events(const double* d_mom, const double* d_w1, const double* d_w2, int64_t nevt, int nexternal, double wmax,
                      uint64_t seed, uint64_t first_index, double* d_out_mom, double* d_out_w, int64_t* d_out_index,
                      int32_t* d_count, int64_t capacity, void* stream);
+
+/* ---- PDFs and alpha_s from an LHAPDF lhagrid1 set (what the reference asks pdfflow for:
+ * scripts/madflow_exec.py:412-413 pdf.xfxQ2(pids, x, q2), :431 pdf.alphasQ2(q2)) ------------------------
+ * d_table: one member packed into doubles (header, subgrid descriptors, knots and their logarithms, values;
+ * layout in madflow_b200/csrc/pdf.cuh, packer madflow_b200/pdf.py).  columns: for each requested flavour
+ * its column in the table (host ints).  d_out: (nevt, ncolumns) x*f(x, Q2); log-bicubic interpolation
+ * (LHAPDF LogBicubicInterpolator), frozen at the grid edges.                                             */
+#define MF_PDF_MAX_FLAVOURS 16
+int mf_pdf_xfxq2(const double* d_table, const int32_t* columns, int ncolumns, const double* d_x, const double* d_q2,
+                 int64_t nevt, double* d_out, void* stream);
+/* alpha_s(Q2) from the set's AlphaS_Qs / AlphaS_Vals table (LHAPDF AlphaS_Ipol)                          */
+int mf_pdf_alphasq2(const double* d_table, const double* d_q2, int64_t nevt, double* d_out, void* stream);
 
 /* ---- measurement -------------------------------------------------------------------------------
  * FP64 FMA throughput of the current device, measured: `iters` dependent DFMA per chain, 8 chains

@@ -22,6 +22,7 @@ extern "C" {
 #define MFP_MAX_COUPLINGS 8  /* couplings (complex)                 */
 #define MFP_MAX_OUT 8        /* outgoing particles                  */
 #define MFP_MAX_CUTS 16
+#define MFP_MAX_CHANNELS 32  /* initial-state flavour pairs of one subprocess (incl. mirrored) */
 #define MFP_LAYOUT_AOS 0     /* (nevt, nexternal, 4)  -- the reference's layout, phasespace.py:4-5 */
 #define MFP_LAYOUT_SOA 1     /* (nexternal, 4, nevt)  -- coalesced                                 */
 
@@ -87,7 +88,8 @@ typedef struct mfp_integrand_args {
   double pi, acc, gev2pb;   /* constants: reference (float32-rounded) or exact                   */
   /* model (parameters.py) */
   double par[MFP_MAX_PARAMS];
-  int32_t alpha_mode;       /* 0: frozen alpha_s;  1: one-loop running at q2 = (sum mT / 2)^2    */
+  int32_t alpha_mode;       /* 0: frozen alpha_s;  1: one-loop running at q2 = (sum mT / 2)^2;
+                             * 2: the PDF set's alpha_s table at q2 (pdf.alphasQ2, madflow_exec.py:431) */
   double alpha_s;           /* frozen value, or alpha_s(mz2) for the running                      */
   double mz2, b0;           /* running: alpha_s / (1 + alpha_s*b0*log(q2/mz2))                    */
   double sqh;
@@ -100,6 +102,14 @@ typedef struct mfp_integrand_args {
    * helicity-parallel flavour); size from mfp_integrand_workspace(); may be NULL/0 otherwise   */
   void* d_workspace;
   int64_t workspace_bytes;
+  /* parton luminosity (madflow_exec.py:410-417, 450-454): sum over the subprocess's initial-state flavour
+   * pairs of xf_a(x1,q2) xf_b(x2,q2) / x1 / x2, multiplied into the event weight.  d_pdf: one member of an
+   * lhagrid1 set packed by mf_pdf_* (madflow_b200.h; layout in csrc/pdf.cuh); NULL = --no_pdf, luminosity 1
+   * (:437-438).  chan_fl1/2: column of the flavour in the table, for hadron 1 / 2.                          */
+  const double* d_pdf;
+  int32_t nchannels;
+  int8_t chan_fl1[MFP_MAX_CHANNELS], chan_fl2[MFP_MAX_CHANNELS];
+  double fixed_q2;          /* > 0: muF^2 = muR^2 fixed (madflow -q, :376-386); else q2 = (sum mT/2)^2    */
 } mfp_integrand_args;
 
 /* recommended persistent grid size for the current device (multiple of the SM count)          */
@@ -107,8 +117,8 @@ int mfp_integrand_blocks(void);
 /* bytes of device scratch mfp_integrand needs for a call generating `nevents` events (0 for the
  * one-event-per-thread flavour, whose single kernel keeps everything on chip)                   */
 int64_t mfp_integrand_workspace(int64_t nevents);
-/* One pass of the integrand of scripts/madflow_exec.py:422-470 (--no_pdf) over `nevents` events:
- * Philox -> VEGAS map -> x1,x2 -> RAMBO -> cuts -> boost -> alpha_s -> smatrix -> weight ->
+/* One pass of the integrand of scripts/madflow_exec.py:422-470 over `nevents` events:
+ * Philox -> VEGAS map -> x1,x2 -> RAMBO -> cuts -> boost -> scale, alpha_s, luminosity -> smatrix -> weight ->
  * block partial sums of xjac*f, (xjac*f)^2 and the per-dimension histogram of (xjac*f)^2.      */
 int mfp_integrand(const mfp_integrand_args* args, void* stream);
 

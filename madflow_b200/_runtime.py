@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIBDIR = os.path.join(HERE, "lib")
 
 c_dp = ctypes.c_void_p
-MFP_MAX_PARAMS, MFP_MAX_COUPLINGS, MFP_MAX_OUT, MFP_MAX_CUTS = 8, 8, 8, 16
+MFP_MAX_PARAMS, MFP_MAX_COUPLINGS, MFP_MAX_OUT, MFP_MAX_CUTS, MFP_MAX_CHANNELS = 8, 8, 8, 16, 32
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 CUT_VARS = {"pt": 0, "mt": 1, "mt2": 2, "mij": 3, "dr": 4}
 PAIR_CUTS = ("mij", "dr")   # extension: cuts on a pair of particles, particle = (i, j)
@@ -65,6 +65,9 @@ class mfp_integrand_args(ctypes.Structure):
         ("mz2", ctypes.c_double), ("b0", ctypes.c_double), ("sqh", ctypes.c_double),
         ("d_partial", ctypes.c_void_p), ("nblocks", ctypes.c_int32), ("accumulate_hist", ctypes.c_int32),
         ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+        ("d_pdf", ctypes.c_void_p), ("nchannels", ctypes.c_int32),
+        ("chan_fl1", ctypes.c_int8 * MFP_MAX_CHANNELS), ("chan_fl2", ctypes.c_int8 * MFP_MAX_CHANNELS),
+        ("fixed_q2", ctypes.c_double),
     ]
 
 

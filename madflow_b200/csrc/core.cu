@@ -5,6 +5,7 @@
 #include "../../include/madflow_b200.h"
 #include "aloha_sm.cuh"
 #include "helas.cuh"
+#include "pdf.cuh"
 #include "phasespace.cuh"
 #include "philox.cuh"
 #include "vegas.cuh"
@@ -281,6 +282,20 @@ __global__ void __launch_bounds__(256) dfma_kernel(int iters, double seed, doubl
   if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
 }
 
+
+// ------------------------------------------------------------------------------ PDFs (csrc/pdf.cuh)
+struct PdfFlavours { int n; int col[MF_PDF_MAX_FLAVOURS]; };
+__global__ void pdf_xfx_kernel(const double* T, PdfFlavours f, const double* x, const double* q2, long long nevt, double* out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
+    const PdfPoint c = pdf_locate(T, x[e], q2[e]);
+    for (int k = 0; k < f.n; ++k) out[e * f.n + k] = pdf_eval(c, f.col[k]);
+  }
+}
+__global__ void pdf_alphas_kernel(const double* T, const double* q2, long long nevt, double* out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) out[e] = pdf_alphas(T, q2[e]);
+}
 }  // namespace
 
 extern "C" {
@@ -449,6 +464,25 @@ int mf_select_events(const double* d_mom, const double* d_w1, const double* d_w2
       d_mom, d_w1, d_w2, nevt, nexternal, wmax, seed, first_index, d_out_mom, d_out_w, (long long*)d_out_index, d_count,
       capacity);
   return check_launch("select_events_kernel");
+}
+
+int mf_pdf_xfxq2(const double* d_table, const int32_t* columns, int ncolumns, const double* d_x, const double* d_q2,
+                 int64_t nevt, double* d_out, void* stream) {
+  if (!d_table) return fail_msg("mf_pdf_xfxq2: null table");
+  if (ncolumns < 1 || ncolumns > MF_PDF_MAX_FLAVOURS) return fail_msg("mf_pdf_xfxq2: 1 <= ncolumns <= MF_PDF_MAX_FLAVOURS");
+  if (nevt <= 0) return 0;
+  PdfFlavours f;
+  f.n = ncolumns;
+  for (int k = 0; k < ncolumns; ++k) f.col[k] = columns[k];
+  pdf_xfx_kernel<<<grid_for(nevt, 128), 128, 0, (cudaStream_t)stream>>>(d_table, f, d_x, d_q2, nevt, d_out);
+  return check_launch("pdf_xfx_kernel");
+}
+
+int mf_pdf_alphasq2(const double* d_table, const double* d_q2, int64_t nevt, double* d_out, void* stream) {
+  if (!d_table) return fail_msg("mf_pdf_alphasq2: null table");
+  if (nevt <= 0) return 0;
+  pdf_alphas_kernel<<<grid_for(nevt, 128), 128, 0, (cudaStream_t)stream>>>(d_table, d_q2, nevt, d_out);
+  return check_launch("pdf_alphas_kernel");
 }
 
 int mf_fp64_peak(int iters, double* tflops, double* ms) {

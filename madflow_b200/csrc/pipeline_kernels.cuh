@@ -1,7 +1,7 @@
 // Event-generation and accumulation kernels of the three-stage integrand pipeline used by the
 // helicity-parallel flavour:
 //
-//   ps_generate_kernel<NEXT>   Philox -> VEGAS map -> x1,x2 -> RAMBO -> cuts -> boost -> alpha_s;
+//   ps_generate_kernel<NEXT>   Philox -> VEGAS map -> x1,x2 -> RAMBO -> cuts -> boost -> scale, alpha_s, luminosity;
 //                              one event per thread; every block appends the events that pass the
 //                              cuts to ITS OWN segment of the event buffer (stable order, so the
 //                              buffer contents do not depend on scheduling) and zero-fills the rest
@@ -12,9 +12,10 @@
 // The reference does the same three steps as separate TensorFlow graphs with a boolean_mask
 // compaction in between (phasespace.py:506-515, madflow_exec.py:444-468).  Buffers (HBM), for a
 // capacity of `cap` event slots split into `nseg` segments of `seg` slots:
-//   mom    (cap, NEXT, 4) f64     w (cap) f64 = xjac * phase-space weight     as (cap) f64 alpha_s
+//   mom    (cap, NEXT, 4) f64     w (cap) f64 = xjac * ps weight * lumi      as (cap) f64 alpha_s
 //   bins   (ndim, cap) u8         me (cap) f64                                count (nseg) i32
 #pragma once
+#include "pdf.cuh"
 #include "phasespace.cuh"
 #include "philox.cuh"
 #include "vegas.cuh"
@@ -45,11 +46,6 @@ struct GenArgs {
 };
 
 constexpr int GEN_BLOCK = 128;
-
-MF_DEV double alpha_s_running(const mfp_integrand_args& u, double q2) {
-  if (u.alpha_mode == 0) return u.alpha_s;
-  return u.alpha_s / (1.0 + u.alpha_s * u.b0 * log(q2 / u.mz2));
-}
 
 template <int NEXT>
 __global__ void __launch_bounds__(GEN_BLOCK) ps_generate_kernel(const GenArgs a) {
@@ -92,14 +88,9 @@ __global__ void __launch_bounds__(GEN_BLOCK) ps_generate_kernel(const GenArgs a)
         ok = ok && (wgt == wgt) && (wgt != 0.0);
         if (ok) {
           if (a.u.lab_frame) boost_to_lab<NEXT>(m, x1, x2);
-          double q2 = 0.0;
-          if (a.u.alpha_mode != 0) {
-            double smt = 0.0;  // madflow_exec.py:428-430: q2 = (sum_out mT / 2)^2
-#pragma unroll
-            for (int i = 2; i < NEXT; ++i) smt += cut_value(CUT_MT, m[i]);
-            q2 = (smt / 2.0) * (smt / 2.0);
-          }
-          as = alpha_s_running(a.u, q2);
+          double lumi;
+          event_scale<NEXT>(a.u, m, x1, x2, as, lumi);  // madflow_exec.py:426-454
+          wgt *= lumi;
           wgt *= w * a.u.inv_total_events;
         }
       }

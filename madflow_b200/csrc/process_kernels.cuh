@@ -21,6 +21,7 @@
 #include "../../include/madflow_b200_process.h"
 #include "aloha_sm.cuh"
 #include "helas.cuh"
+#include "pdf.cuh"
 #include "phasespace.cuh"
 #include "philox.cuh"
 #include "vegas.cuh"
@@ -125,11 +126,6 @@ struct IntegrandSmem {
   double red[3][32];
 };
 
-MF_DEV double alpha_s_of(const mfp_integrand_args& u, double q2) {
-  if (u.alpha_mode == 0) return u.alpha_s;
-  return u.alpha_s / (1.0 + u.alpha_s * u.b0 * log(q2 / u.mz2));
-}
-
 template <class P>
 __device__ __forceinline__ void integrand_process_entry(const IntegrandArgs& a, IntegrandSmem<P>& s, int slot,
                                                         double& s1, double& s2, double& cnt) {
@@ -205,14 +201,9 @@ __global__ void __launch_bounds__(P::BLOCK, P::MINBLOCKS) integrand_kernel(const
       ok = ok && (wgt == wgt) && (wgt != 0.0);
       if (ok) {
         if (a.u.lab_frame) boost_to_lab<P::NEXT>(m, x1, x2);
-        double q2 = 0.0;
-        if (a.u.alpha_mode != 0) {
-          double smt = 0.0;  // madflow_exec.py:428-430: q2 = (sum_out mT / 2)^2
-#pragma unroll
-          for (int i = 2; i < P::NEXT; ++i) smt += cut_value(CUT_MT, m[i]);
-          q2 = (smt / 2.0) * (smt / 2.0);
-        }
-        as = alpha_s_of(a.u, q2);
+        double lumi;
+        event_scale<P::NEXT>(a.u, m, x1, x2, as, lumi);  // madflow_exec.py:426-454
+        wgt *= lumi;
         wgt *= w * a.u.inv_total_events;
       }
     }
@@ -311,6 +302,10 @@ int prepare_integrand_args(const mfp_integrand_args* u, IntegrandArgs& a) {
   if (u->ncuts < 0 || u->ncuts > MFP_MAX_CUTS) return fail_msg("mfp_integrand: too many cuts");
   if (u->nblocks <= 0) return fail_msg("mfp_integrand: nblocks must come from mfp_integrand_blocks()");
   if (!u->d_grid || !u->d_partial) return fail_msg("mfp_integrand: null grid or partial buffer");
+  if (u->alpha_mode < 0 || u->alpha_mode > 2) return fail_msg("mfp_integrand: alpha_mode must be 0, 1 or 2");
+  if (u->alpha_mode == 2 && !u->d_pdf) return fail_msg("mfp_integrand: alpha_mode 2 needs the PDF table (d_pdf)");
+  if (u->d_pdf && (u->nchannels <= 0 || u->nchannels > MFP_MAX_CHANNELS))
+    return fail_msg("mfp_integrand: a PDF table needs 1..MFP_MAX_CHANNELS initial-state channels");
   a.u = *u;
   double msum = 0.0;
   for (int i = 0; i < NOUT; ++i) msum += u->masses[i];

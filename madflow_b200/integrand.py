@@ -1,6 +1,9 @@
 """The cross-section integrand of scripts/madflow_exec.py:422-470 as ONE fused kernel.
 
-    sigma-integrand(xrand) = smatrix(ps(xrand); couplings(alpha_s)) * ps_weight   (--no_pdf: luminosity 1)
+    sigma-integrand(xrand) = luminosity(x1, x2, q2) * smatrix(ps(xrand); couplings(alpha_s(q2))) * ps_weight
+
+with the parton luminosity and alpha_s from an LHAPDF grid (madflow_b200.pdf, the reference's pdfflow calls) or
+luminosity 1 and a frozen / one-loop alpha_s (--no_pdf).
 
 `FusedIntegrand` describes it (process, collider energy, masses, cuts, frame, alpha_s mode) and
 `VegasFlow` launches it (include/madflow_b200_process.h: mfp_integrand).  `python_integrand` gives
@@ -32,9 +35,13 @@ def alpha_s_one_loop(q2, alpha_mz=0.118, mz2=MZ * MZ, b0=None):
 
 class FusedIntegrand:
     def __init__(self, matrix, model, sqrts=13e3, masses=None, pt_cut=None, cuts=None, lab_frame=True,
-                 alpha_s=None, running=False, alpha_mz=0.118, mz=MZ, nf=5):
+                 alpha_s=None, running=False, alpha_mz=0.118, mz=MZ, nf=5, pdf=None, fixed_scale=None):
         """alpha_s: frozen value (default: 0.118 as `madflow --no_pdf -q`, madflow_exec.py:379-380);
-        running=True: q2 = (sum mT/2)^2 per event (madflow_exec.py:428-431) with one-loop alpha_s."""
+        running=True: q2 = (sum mT/2)^2 per event (madflow_exec.py:428-431) with one-loop alpha_s.
+        pdf: a madflow_b200.pdf.PDF -- the event weight gets the parton luminosity of the process's initial
+        states at muF^2 = q2 (madflow_exec.py:410-417, 450-454) and, with running=True, alpha_s comes from the
+        set's table (`pdf.alphasQ2`, :431); fixed_scale (GeV): muF = muR fixed and alpha_s frozen at
+        `pdf.alphasQ2(fixed_scale^2)` (`madflow -q`, :376-386)."""
         self.matrix, self.model = matrix, model
         self._lib = matrix._lib
         n = int(matrix.nexternal)
@@ -51,6 +58,20 @@ class FusedIntegrand:
         self.event_sink = None                 # madflow_b200.events.EventSink
         self.max_events_per_launch = 1 << 23   # bounds the HBM scratch of the pipeline flavour (~2 GB)
         self.running = bool(running)
+        self.pdf = pdf
+        self.fixed_q2 = float(fixed_scale) ** 2 if fixed_scale is not None else 0.0
+        if fixed_scale is not None and running:
+            raise ValueError("a fixed scale freezes alpha_s: running=True contradicts fixed_scale")
+        self.channels = None
+        if pdf is not None:
+            from .pdf import initial_state_channels
+
+            self.channels = initial_state_channels(matrix, pdf)
+            if not 0 < len(self.channels[0]) <= rt.MFP_MAX_CHANNELS:
+                raise ValueError(f"{len(self.channels[0])} initial-state channels (1..{rt.MFP_MAX_CHANNELS} supported): "
+                                 "does the process know its initial_states?")
+            if fixed_scale is not None and alpha_s is None and pdf.has_alphas:
+                alpha_s = float(pdf.alphasQ2([self.fixed_q2]))   # madflow_exec.py:382
         if alpha_s is None:
             alpha_s = 0.118
         if not running and config.get_constants().mode == "reference":
@@ -88,8 +109,14 @@ class FusedIntegrand:
         a.pi, a.acc, a.gev2pb, a.sqh = k.PI, k.ACC, k.GEV2PB, k.SQH
         for i, v in enumerate(self.par):
             a.par[i] = v
-        a.alpha_mode = 1 if self.running else 0
+        a.alpha_mode = (2 if self.pdf is not None and self.pdf.has_alphas else 1) if self.running else 0
         a.alpha_s, a.mz2, a.b0 = self.alpha_s, self.mz2, self.b0
+        a.fixed_q2 = self.fixed_q2
+        if self.pdf is not None:
+            a.d_pdf = self.pdf.table.data_ptr()
+            a.nchannels = len(self.channels[0])
+            for i, (c1, c2) in enumerate(zip(*self.channels)):
+                a.chan_fl1[i], a.chan_fl2[i] = c1, c2
         return a
 
     def launch(self, divisions, seed, iteration, first_event, nevents, inv_total, partial, nblocks, train):
@@ -134,14 +161,34 @@ class FusedIntegrand:
         if not self.running and not self.model.frozen:
             self.model.freeze_alpha_s(self.alpha_s)
 
+        pdf = self.pdf
+        if pdf is not None:
+            ini = [tuple(int(f) for f in pr) for pr in self.matrix.initial_states]
+            if self.matrix.mirror_initial_states:
+                ini += [(b, a) for a, b in ini]
+            had1, had2 = [a for a, _ in ini], [b for _, b in ini]
+
         def cross_section(xrand, n_dim=None, weight=None):
             all_ps, wts, x1, x2, idx = psg(xrand)
-            if self.running:
+            q2array = None
+            if self.fixed_q2 > 0.0:
+                q2array = torch.full_like(x1, self.fixed_q2)
+            elif self.running or pdf is not None:
                 full_mt = torch.sum(psg.mt(all_ps[:, 2:n, :]), dim=-1)
-                alpha = alpha_s_one_loop((full_mt / 2.0) ** 2, self.alpha_s, self.mz2, self.b0)
+                q2array = (full_mt / 2.0) ** 2
+            if self.running:
+                if pdf is not None and pdf.has_alphas:
+                    alpha = pdf.alphasQ2(q2array).reshape(-1)
+                else:
+                    alpha = alpha_s_one_loop(q2array, self.alpha_s, self.mz2, self.b0)
             else:
                 alpha = None
-            ret = self.matrix.smatrix(all_ps, *self.model.evaluate(alpha)) * wts
+            smatrix = self.matrix.smatrix(all_ps, *self.model.evaluate(alpha))
+            if pdf is not None:   # madflow_exec.py:410-417, 450-454
+                proton_1 = pdf.xfxQ2(had1, x1, q2array).reshape(-1, len(had1))
+                proton_2 = pdf.xfxQ2(had2, x2, q2array).reshape(-1, len(had2))
+                smatrix = torch.sum(proton_1 * proton_2, dim=1) / x1 / x2 * smatrix
+            ret = smatrix * wts
             if self.cuts:
                 out = torch.zeros(xrand.shape[0], dtype=torch.float64, device=ret.device)
                 out[idx[:, 0].long()] = ret

@@ -5,10 +5,12 @@
     python -m madflow_b200.scripts.madflow_exec --madgraph_process "g g > t t~ g g" --no_pdf -c -i 10 -f 5 \\
         --events_per_iteration 10000000 --histograms -o out/
 
-Same arguments and the same warm-up / frozen-grid schedule as the reference (madflow_exec.py:491-510); what is
-not available offline is refused loudly instead of approximated: PDFs (`--no_pdf` is required: pdfflow and
-LHAPDF grids are absent) and MG5 process generation (the process must be one of the compiled process
-libraries -- the built-in g g > t t~ + n g, or anything exported through the `pyout` plugin's CUDA backend).
+Same arguments and the same warm-up / frozen-grid schedule as the reference (madflow_exec.py:491-510).  Without
+`--no_pdf` the parton luminosity and alpha_s come from the LHAPDF set `--pdf` (member 0, madflow_exec.py:342),
+interpolated on the GPU (madflow_b200.pdf); the set has to be on disk (`--pdf_dir`, PDFFLOW_DATA_PATH or
+LHAPDF_DATA_PATH) -- none ships with this package and a missing set is refused loudly, not approximated.  MG5
+process generation is not available: the process must be one of the compiled process libraries -- the built-in
+g g > t t~ + n g, or anything exported through the `pyout` plugin's CUDA backend.
 Extensions for long runs: --target_error stops the final iterations once the combined relative error is below
 it, --unweighted_events sets the capacity of the on-device unweighting buffer.
 """
@@ -35,7 +37,9 @@ def process_library_name(madgraph_process):
 def build_parser():
     arger = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     arger.add_argument("-v", "--verbose", help="Print extra info", action="store_true")
-    arger.add_argument("-p", "--pdf", help="PDF set (needs pdfflow: not available, use --no_pdf)", type=str, default=DEFAULT_PDF)
+    arger.add_argument("-p", "--pdf", help="PDF set", type=str, default=DEFAULT_PDF)
+    arger.add_argument("--pdf_dir", help="Directory holding the LHAPDF sets (default: PDFFLOW_DATA_PATH / LHAPDF_DATA_PATH)",
+                       type=str, default=None)
     arger.add_argument("--no_pdf", help="Don't use a PDF for the initial state", action="store_true")
     arger.add_argument("--madgraph_process", help="Set the madgraph process to be run", type=str, default="g g > t t~")
     arger.add_argument("-m", "--massive_particles", help="Number of massive particles", type=int, default=2)
@@ -69,8 +73,6 @@ def madflow_main(args=None, quick_return=False):
 
     if args.verbose:
         logger.setLevel(logging.DEBUG)
-    if not args.no_pdf:
-        raise SystemExit("PDF luminosities need pdfflow and an LHAPDF grid, which are not available: run with --no_pdf")
 
     import torch
 
@@ -89,6 +91,16 @@ def madflow_main(args=None, quick_return=False):
     if args.dry_run:
         logger.info("Process %s -> library %s; dry run, nothing executed", args.madgraph_process, name)
         return None, None, None
+
+    pdf = None
+    if not args.no_pdf:   # madflow_exec.py:339-342
+        from madflow_b200 import pdf as mfpdf
+
+        try:
+            pdf = mfpdf.mkPDF(args.pdf + "/0", dirname=args.pdf_dir)
+        except mfpdf.PDFError as e:
+            raise SystemExit(str(e))
+        logger.info("PDF set %s", pdf)
 
     dist = None
     rank, world = 0, 1
@@ -112,14 +124,16 @@ def madflow_main(args=None, quick_return=False):
     if args.fixed_scale is None:
         logger.info("Set variable muF=muR=sum(mT)/2")
     else:
-        logger.info("Setting fixed muF=muR=%.2f GeV, alpha_s = 0.118", args.fixed_scale)   # madflow_exec.py:376-380
+        logger.info("Setting fixed muF=muR=%.2f GeV, alpha_s = %s", args.fixed_scale,   # madflow_exec.py:376-386
+                    "0.118" if pdf is None else "alphasQ2 of the PDF set")
     cuts = []
     if args.dr_cut is not None:
         light = [i for i in range(2, nparticles) if masses[i - 2] == 0.0]
         cuts = [("dr", (i, j), args.dr_cut, None) for a, i in enumerate(light) for j in light[a + 1:]]
         logger.info("Applying Delta R > %.2f to the pairs %s", args.dr_cut, [c[1] for c in cuts])
     fi = mfi.FusedIntegrand(matrix, model, sqrts=13e3, masses=masses, pt_cut=args.pt_cut, cuts=cuts, lab_frame=True,
-                            running=args.fixed_scale is None, alpha_s=0.118)
+                            running=args.fixed_scale is None, alpha_s=0.118 if pdf is None else None, pdf=pdf,
+                            fixed_scale=args.fixed_scale if pdf is not None else None)
     if args.events_per_device:
         fi.max_events_per_launch = args.events_per_device
     if nparticles >= 5 and args.frozen_iter == 0:

@@ -141,10 +141,11 @@ class Vegas:
 
 
 def make_cross_section(ir, params_fn, sqrts, masses, pt_cut=None, const=None, lab_frame=True,
-                       alpha_s_fn=None, cuts=()):
-    """The integrand of scripts/madflow_exec.py:422-470 with --no_pdf (luminosity 1):
-    ramboflow -> cuts on COM momenta -> boost -> alpha_s(q2=(sum mT/2)^2) or frozen ->
-    smatrix * wts, zeros at cut events."""
+                       alpha_s_fn=None, cuts=(), pdf=None, fixed_q2=None):
+    """The integrand of scripts/madflow_exec.py:422-470: ramboflow -> cuts on COM momenta -> boost ->
+    alpha_s(q2=(sum mT/2)^2) or frozen -> luminosity * smatrix * wts, zeros at cut events.
+    pdf (oracle.pdf.GridPDF): luminosity = sum over the initial states (+ mirrored) of
+    xf_a(x1,q2) xf_b(x2,q2) / x1 / x2 (:410-417, 450-454); None = --no_pdf, luminosity 1 (:437-438)."""
     from . import REFERENCE, matrix as om, phasespace as ps
 
     const = const or REFERENCE
@@ -161,12 +162,22 @@ def make_cross_section(ir, params_fn, sqrts, masses, pt_cut=None, const=None, la
         ret = np.zeros(xrand.shape[0])
         if all_ps.shape[0] == 0:
             return ret
-        if alpha_s_fn is not None:
+        q2 = None
+        if fixed_q2:
+            q2 = np.full_like(x1, fixed_q2)
+        elif alpha_s_fn is not None or pdf is not None:
             full_mt = np.sum(ps.mt(all_ps[:, 2:n, :]), axis=-1)
-            params = params_fn(alpha_s_fn((full_mt / 2.0) ** 2))
-        else:
-            params = params_fn(None)
-        val = om.smatrix(ir, all_ps, params, const) * wts
+            q2 = (full_mt / 2.0) ** 2
+        params = params_fn(alpha_s_fn(q2)) if alpha_s_fn is not None else params_fn(None)
+        val = om.smatrix(ir, all_ps, params, const)
+        if pdf is not None:
+            ini = [tuple(pr) for pr in ir["initial_states"]]
+            if ir.get("mirror_initial_states"):
+                ini += [(b, a) for a, b in ini]
+            p1 = pdf.xfxQ2([a for a, _ in ini], x1, q2)
+            p2 = pdf.xfxQ2([b for _, b in ini], x2, q2)
+            val = np.sum(p1 * p2, axis=1) / x1 / x2 * val
+        val = val * wts
         if pt_cut is not None or cuts:
             ret[idx[:, 0]] = val
         else:

@@ -1,7 +1,10 @@
 // TEST INFRASTRUCTURE: CPU execution of the process-independent device functions
-// (HELAS wavefunctions, ALOHA vertices, RAMBO, Philox, VEGAS map) for checks without a GPU.
+// (HELAS wavefunctions, ALOHA vertices, RAMBO, Philox, VEGAS map, PDF interpolation) for checks without a GPU.
+#include <cstring>
+
 #include "aloha_sm.cuh"
 #include "helas.cuh"
+#include "pdf.cuh"
 #include "phasespace.cuh"
 #include "philox.cuh"
 #include "vegas.cuh"
@@ -113,6 +116,36 @@ int hc_vegas_map(const double* grid, const double* r, long long nevt, int ndim, 
     double ww = 1.0;
     for (int d = 0; d < ndim; ++d) x[e * ndim + d] = vegas_map(grid + d * VEGAS_EDGES, r[e * ndim + d], bins[e * ndim + d], ww);
     w[e] = ww;
+  }
+  return 0;
+}
+// csrc/pdf.cuh on a packed table T: out (nevt, ncol) = x f(x, Q2) of the table columns `col`
+int hc_pdf_xfx(const double* T, const int* col, int ncol, const double* x, const double* q2, long long nevt, double* out) {
+  for (long long e = 0; e < nevt; ++e) {
+    const PdfPoint c = pdf_locate(T, x[e], q2[e]);
+    for (int k = 0; k < ncol; ++k) out[e * ncol + k] = pdf_eval(c, col[k]);
+  }
+  return 0;
+}
+
+int hc_pdf_alphas(const double* T, const double* q2, long long nevt, double* out) {
+  for (long long e = 0; e < nevt; ++e) out[e] = pdf_alphas(T, q2[e]);
+  return 0;
+}
+
+// event_scale<4> as the integrand kernels call it: alpha_s and luminosity of events given lab momenta (nevt,4,4)
+int hc_event_scale(const double* T, int alpha_mode, double alpha_s, double mz2, double b0, double fixed_q2, int nch,
+                   const signed char* fl1, const signed char* fl2, const double* p, const double* x1, const double* x2,
+                   long long nevt, double* as, double* lumi) {
+  mfp_integrand_args u;
+  memset(&u, 0, sizeof(u));
+  u.d_pdf = T, u.alpha_mode = alpha_mode, u.alpha_s = alpha_s, u.mz2 = mz2, u.b0 = b0, u.fixed_q2 = fixed_q2, u.nchannels = nch;
+  for (int c = 0; c < nch; ++c) u.chan_fl1[c] = fl1[c], u.chan_fl2[c] = fl2[c];
+  for (long long e = 0; e < nevt; ++e) {
+    double m[4][4];
+    for (int i = 0; i < 4; ++i)
+      for (int c = 0; c < 4; ++c) m[i][c] = p[(e * 4 + i) * 4 + c];
+    event_scale<4>(u, m, x1[e], x2[e], as[e], lumi[e]);
   }
   return 0;
 }

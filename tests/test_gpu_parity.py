@@ -582,3 +582,82 @@ def test_pair_cuts_extension(mf):
     assert v1.last_me_events < v0.last_me_events
     with pytest.raises(ValueError):
         mf.phasespace.PhaseSpaceGenerator(6, 13e3, masses).register_cut("dr", particle=4, min_val=0.4)
+
+
+# ------------------------------------------------------------------------------ PDFs
+@pytest.fixture(scope="module")
+def toy_pdf(tmp_path_factory):
+    """A synthetic lhagrid1 set (no real grid is available offline), loaded by the product and by the oracle."""
+    from madflow_b200 import pdf as mpdf
+    from oracle import pdf as opdf
+
+    d = str(tmp_path_factory.mktemp("lhapdf"))
+    opdf.write_toy_set(d)
+    return mpdf.mkPDF("ToyPDF/0", dirname=d), opdf.GridPDF.from_set("ToyPDF/0", d)
+
+
+def test_pdf_kernels_vs_oracle(mf, toy_pdf):
+    """mf_pdf_xfxq2 / mf_pdf_alphasq2 (pdfflow's xfxQ2 / alphasQ2) against the oracle: cell interiors, knots,
+    the subgrid threshold, frozen edges."""
+    pd, og = toy_pdf
+    rng = np.random.default_rng(3)
+    n = 200_000
+    x = 10 ** rng.uniform(-7.5, 0.0, n)
+    q2 = 10 ** rng.uniform(0.0, 8.5, n)
+    sg = og.subgrids[1]
+    x[:60], q2[:60] = sg["x"], sg["q2"][3]
+    q2[60:70] = 4.75**2
+    pids = [21, 2, -1, 5, -5]
+    out = cpu(pd.xfxQ2(pids, x, q2))
+    assert out.shape == (n, 5)
+    ref = og.xfxQ2(pids, x, q2)
+    assert np.max(np.abs(out - ref) / np.max(np.abs(ref), axis=0)) < 1e-13
+    np.testing.assert_array_equal(out[:60], sg["xf"][:, 3, [pd.column(p) for p in pids]])
+    np.testing.assert_allclose(cpu(pd.xfxQ2_allpid(x[:1000], q2[:1000])), og.xfxQ2(og.pids, x[:1000], q2[:1000]), rtol=1e-11, atol=1e-13)
+    assert cpu(pd.xfxQ2([21], x[:7], q2[:7])).shape == (7,)          # squeezed like pdfflow's
+    qa = 10 ** rng.uniform(-0.5, 9.0, n)
+    qa[:13] = og.as_q2
+    np.testing.assert_allclose(cpu(pd.alphasQ2(qa)), og.alphasQ2(qa), rtol=1e-13)
+    np.testing.assert_allclose(cpu(pd.alphasQ(np.sqrt(qa[:100]))), og.alphasQ2(qa[:100]), rtol=1e-12)
+
+
+@pytest.mark.parametrize("variant", ["thread", "hp"])
+@pytest.mark.parametrize("name,k,nev,fixed", [("1_gg_ttx", 0, 40000, None), ("1_gg_ttx", 0, 40000, 91.46),
+                                              ("1_gg_ttxg", 1, 20000, None)])
+def test_fused_integrand_with_pdf(mf, toy_pdf, name, k, nev, fixed, variant):
+    """The integrand of madflow_exec.py:422-470 WITH the parton luminosity and the set's alpha_s (dynamic scale
+    and `-q` fixed scale): fused kernel == separate C-ABI calls == oracle cross_section on the same Philox points."""
+    from madflow_b200 import procgen, process_ir
+
+    pd, og = toy_pdf
+    ir = process_ir.gg_ttx_pinned() if k == 0 else procgen.generate_ir(k)
+    masses = [MT, MT] + [0.0] * k
+    m, model = mf.matrix.get_process(name)
+    _select(mf, m, variant)
+    fi = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=masses, pt_cut=30.0, lab_frame=True,
+                                     running=fixed is None, pdf=pd, fixed_scale=fixed)
+    v1 = mf.vegas.VegasFlow(fi.n_dim, nev, seed=4)
+    v1.compile(fi)
+    r1 = v1.run_iteration()
+    v2 = mf.vegas.VegasFlow(fi.n_dim, nev, seed=4)
+    v2.compile(fi.python_integrand())
+    r2 = v2.run_iteration()
+    assert abs(r1[0] / r2[0] - 1) < 1e-10 and abs(r1[1] / r2[1] - 1) < 1e-8
+    if fixed is None:
+        a_fn, pf = og.alphasQ2, (lambda a: sm_params(alpha_s=a))
+    else:
+        a0 = float(np.float32(og.alphasQ2([fixed**2])[0]))   # Model.freeze_alpha_s rounds through float32 (parameters.py:53)
+        assert fi.alpha_s == a0
+        a_fn, pf = None, (lambda a: sm_params(alpha_s=a0))
+    xs = ovegas.make_cross_section(ir, pf, 13e3, masses, pt_cut=30.0, lab_frame=True, alpha_s_fn=a_fn, pdf=og,
+                                   fixed_q2=fixed**2 if fixed else None)
+    ov = ovegas.Vegas(fi.n_dim, nev, seed=4)
+    ov.compile(xs)
+    r0 = ov.run_iteration()
+    assert abs(r1[0] / r0[0] - 1) < 1e-10 and abs(r1[1] / r0[1] - 1) < 1e-8
+    np.testing.assert_allclose(cpu(v1.divisions), ov.grid, rtol=1e-6, atol=1e-11)
+    # the luminosity changes the answer: the same run without the table differs
+    fi0 = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=masses, pt_cut=30.0, lab_frame=True, running=fixed is None)
+    v0 = mf.vegas.VegasFlow(fi.n_dim, nev, seed=4)
+    v0.compile(fi0)
+    assert abs(v0.run_iteration()[0] / r1[0] - 1) > 0.1

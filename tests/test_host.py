@@ -167,8 +167,54 @@ def test_madflow_cli_arguments_and_process_names():
     assert args.events_per_iteration == int(1e6) and args.massive_particles == 2 and args.histograms and args.no_pdf
     assert process_library_name(args.madgraph_process) == "1_gg_ttxgg"
     assert process_library_name("g g > t t~") == "1_gg_ttx"
-    with pytest.raises(SystemExit):
-        madflow_main(["--dry_run"])           # PDFs are refused, not approximated
+    assert madflow_main(["--dry_run"]) == (None, None, None)   # like the reference, a dry run stops before the PDF
+    with pytest.raises(SystemExit, match="NNPDF31_nnlo_as_0118"):
+        madflow_main(["-i", "2"])             # a missing PDF set is refused, not approximated
     with pytest.raises(SystemExit):
         madflow_main(["--no_pdf", "--dry_run", "--madgraph_process", "u u~ > t t~"])   # no such library
     assert madflow_main(["--no_pdf", "--dry_run", "--madgraph_process", "g g > t t~ g"]) == (None, None, None)
+
+
+def test_pdf_set_reader_and_table(tmp_path):
+    """madflow_b200.pdf: lhagrid1 reader, the packed table of csrc/pdf.cuh, pdfflow's mkPDF conventions, errors."""
+    from madflow_b200 import pdf as mpdf
+    from oracle import pdf as opdf
+
+    opdf.write_toy_set(str(tmp_path))
+    p = mpdf.mkPDF("ToyPDF/0", dirname=str(tmp_path))
+    assert p.flavor_scheme == [-5, -4, -3, -2, -1, 1, 2, 3, 4, 5, 21] and p.column(0) == p.column(21) == 10
+    assert p.has_alphas and p.q2min == pytest.approx(1.65**2) and p.q2max == pytest.approx(1e8) and p.nmembers == 1
+    T = p._host_table
+    nsub, nfl, nas = int(T[0]), int(T[1]), int(T[2])
+    assert (nsub, nfl, nas) == (2, 11, 2)
+    og = opdf.GridPDF.from_set("ToyPDF/0", str(tmp_path))
+    for s_, sg in enumerate(og.subgrids):
+        nx, nq, ox, olx, oq, olq, oxf, q2min = T[8 + 8 * s_: 16 + 8 * s_]
+        nx, nq, ox, olx, oq, olq, oxf = int(nx), int(nq), int(ox), int(olx), int(oq), int(olq), int(oxf)
+        np.testing.assert_array_equal(T[ox:ox + nx], sg["x"])
+        np.testing.assert_array_equal(T[olx:olx + nx], np.log(sg["x"]))
+        np.testing.assert_array_equal(T[oq:oq + nq], sg["q2"])
+        np.testing.assert_array_equal(T[oxf:oxf + nx * nq * nfl].reshape(nx, nq, nfl), sg["xf"])
+        assert q2min == sg["q2"][0]
+    assert T[3] == og.as_q2[0] and T[6] == og.as_q2[-1] and T[7] == og.as_vals[-1]
+    os.environ["LHAPDF_DATA_PATH"] = str(tmp_path)
+    try:
+        assert mpdf.mkPDF("ToyPDF").member == 0
+    finally:
+        del os.environ["LHAPDF_DATA_PATH"]
+    with pytest.raises(mpdf.PDFError, match="not found"):
+        mpdf.mkPDF("NoSuchSet/0", dirname=str(tmp_path))
+    with pytest.raises(mpdf.PDFError, match="not found"):
+        mpdf.mkPDF("ToyPDF/3", dirname=str(tmp_path))
+    with pytest.raises(mpdf.PDFError, match="flavour 6"):
+        p.column(6)
+
+    class M:
+        initial_states, mirror_initial_states = [(1, -1), (2, -2)], True
+
+    assert mpdf.initial_state_channels(M, p) == ([5, 6, 4, 3], [4, 3, 5, 6])   # madflow_exec.py:141-155
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU implementation"):
+            p.xfxQ2([21], [0.1], [1e4])    # nothing but the CUDA kernels behind the product API

@@ -87,3 +87,56 @@ def test_device_vegas_map_on_host(hc):
     np.testing.assert_array_equal(bins, kr)
     np.testing.assert_allclose(x, xr, rtol=1e-15)
     np.testing.assert_allclose(w, wr, rtol=1e-14)
+
+
+def test_device_pdf_on_host(hc, tmp_path):
+    """csrc/pdf.cuh (log-bicubic x f(x, Q2), alpha_s table, luminosity + scale of an event) executed on the CPU
+    against oracle/pdf.py on a synthetic lhagrid1 set: knots, cell interiors, subgrid thresholds, frozen edges."""
+    from madflow_b200 import pdf as mpdf
+    from oracle import pdf as opdf
+
+    opdf.write_toy_set(str(tmp_path))
+    og = opdf.GridPDF.from_set("ToyPDF/0", str(tmp_path))
+    pd = mpdf.mkPDF("ToyPDF/0", dirname=str(tmp_path))
+    T = np.ascontiguousarray(pd._host_table)
+    lib = hc.core()
+    rng = np.random.default_rng(3)
+    n = 4000
+    x = 10 ** rng.uniform(-7.5, 0.0, n)            # below xmin: frozen
+    q2 = 10 ** rng.uniform(0.0, 8.5, n)            # below q2min / above q2max: frozen
+    sg = og.subgrids[1]
+    x[:60], q2[:60] = sg["x"], sg["q2"][3]         # on knots
+    q2[60:70] = 4.75 ** 2                          # on the subgrid threshold
+    x[70:80], q2[70:80] = 1.0, 1e4                 # upper corner
+    pids = [21, 2, -1, 5]
+    cols = np.array([pd.column(p) for p in pids], dtype=np.int32)
+    out = np.empty((n, len(pids)))
+    lib.hc_pdf_xfx(hc._dp(T), cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(pids), hc._dp(x), hc._dp(q2),
+                   ctypes.c_longlong(n), hc._dp(out))
+    ref = og.xfxQ2(pids, x, q2)
+    scale = np.max(np.abs(ref), axis=0)
+    assert np.max(np.abs(out - ref) / scale) < 1e-13
+    np.testing.assert_array_equal(out[:60], sg["xf"][:, 3, cols])   # knots exactly
+    qa = 10 ** rng.uniform(-0.5, 9.0, n)
+    qa[:13] = og.as_q2
+    a = np.empty(n)
+    lib.hc_pdf_alphas(hc._dp(T), hc._dp(qa), ctypes.c_longlong(n), hc._dp(a))
+    np.testing.assert_allclose(a, og.alphasQ2(qa), rtol=1e-13)
+    # scale + alpha_s + luminosity of an event, g g and q q~ (+ mirrored) channels
+    xr = rng.random((500, 10))
+    p, w, x1, x2 = ops.ramboflow(xr, 4, 13e3, [MT, MT], xfactor="converged")
+    lab = np.ascontiguousarray(ops.boost_to_lab(p, x1, x2))
+    q2e = (np.sum(ops.mt(lab[:, 2:4]), axis=-1) / 2.0) ** 2
+    ini = [(1, -1), (2, -2), (-1, 1), (-2, 2)]
+    f1 = np.array([pd.column(a_) for a_, _ in ini], dtype=np.int8)
+    f2 = np.array([pd.column(b_) for _, b_ in ini], dtype=np.int8)
+    as_, lumi = np.empty(500), np.empty(500)
+    for fixed in (0.0, 91.46 ** 2):
+        lib.hc_event_scale(hc._dp(T), 2, ctypes.c_double(0.118), ctypes.c_double(1.0), ctypes.c_double(0.0),
+                           ctypes.c_double(fixed), len(ini), f1.ctypes.data_as(ctypes.POINTER(ctypes.c_byte)),
+                           f2.ctypes.data_as(ctypes.POINTER(ctypes.c_byte)), hc._dp(lab), hc._dp(x1), hc._dp(x2),
+                           ctypes.c_longlong(500), hc._dp(as_), hc._dp(lumi))
+        qq = np.full(500, fixed) if fixed else q2e
+        p1, p2 = og.xfxQ2([a_ for a_, _ in ini], x1, qq), og.xfxQ2([b_ for _, b_ in ini], x2, qq)
+        np.testing.assert_allclose(lumi, np.sum(p1 * p2, axis=1) / x1 / x2, rtol=1e-12)
+        np.testing.assert_allclose(as_, og.alphasQ2(qq), rtol=1e-12)

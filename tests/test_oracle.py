@@ -244,3 +244,46 @@ def test_vegas_map_weight_is_jacobian():
     x, k, w = ovegas.map_to_grid(u, grid)
     assert abs(np.mean(w) - 1.0) < 0.02          # E[jacobian] = volume of the unit cube
     assert np.all((x >= 0) & (x <= 1)) and k.min() >= 0 and k.max() <= 49
+
+
+def test_pdf_interpolation_properties(tmp_path):
+    """oracle/pdf.py (LHAPDF log-bicubic + AlphaS_Ipol; pdfflow and every real grid are absent, so parity is
+    unpinned): the knots are reproduced exactly, a quadratic in (log x, log Q2) on uniform log grids is
+    reproduced to rounding, the interpolant is continuous across cells, a threshold value belongs to the upper
+    subgrid, the synthetic shapes are recovered to the accuracy of the coarse grid."""
+    from oracle import pdf as opdf
+
+    opdf.write_toy_set(str(tmp_path))
+    g = opdf.GridPDF.from_set("ToyPDF/0", str(tmp_path))
+    assert g.pids == [-5, -4, -3, -2, -1, 1, 2, 3, 4, 5, 21] and len(g.subgrids) == 2
+    for sg in g.subgrids:
+        X, Q2 = np.meshgrid(sg["x"], sg["q2"][:-1], indexing="ij")
+        got = g.xfxQ2([21, -3], X.ravel(), Q2.ravel())
+        ref = sg["xf"][:, :-1][:, :, [10, 2]].reshape(-1, 2)
+        np.testing.assert_array_equal(got, ref)
+    # the threshold Q = 4.75 is the first knot of the upper subgrid
+    lo, hi = g.subgrids
+    np.testing.assert_array_equal(g.xfxQ2([21], hi["x"], np.full(60, 4.75**2))[:, 0], hi["xf"][:, 0, 10])
+    # quadratic polynomial in (log x, log Q2) on uniform log grids: exact
+    lx, lq = np.linspace(-9.0, 0.0, 19), np.linspace(1.0, 12.0, 12)
+    poly = lambda a, b: 1.0 + 0.3 * a - 0.05 * a * a + 0.2 * b + 0.01 * b * b + 0.02 * a * b
+    sub = dict(x=np.exp(lx), q2=np.exp(lq), pids=[21], xf=poly(lx[:, None], lq[None, :])[:, :, None])
+    gq = opdf.GridPDF({"AlphaS_Qs": [], "AlphaS_Vals": []}, [sub])
+    rng = np.random.default_rng(0)
+    a, b = rng.uniform(-8.5, -0.5, 2000), rng.uniform(2.0, 11.0, 2000)   # away from the one-sided edge cells
+    np.testing.assert_allclose(gq.xfxQ2([21], np.exp(a), np.exp(b))[:, 0], poly(a, b), rtol=1e-12)
+    # continuity across a cell boundary in x and in Q2
+    xk, qk = hi["x"][20], hi["q2"][4]
+    eps = 1e-9
+    v = g.xfxQ2([21], [xk * (1 - eps), xk * (1 + eps), 1e-3, 1e-3], [1e4, 1e4, qk * (1 - eps), qk * (1 + eps)])[:, 0]
+    assert abs(v[0] / v[1] - 1) < 1e-7 and abs(v[2] / v[3] - 1) < 1e-7
+    x = 10 ** rng.uniform(-4, -0.3, 1000)
+    q2 = 10 ** rng.uniform(np.log10(30.0), 7, 1000)
+    shape = 3.0 * x**-0.25 * (1 - x) ** 5 * (1 + 0.3 * np.log(np.sqrt(q2) / 1.65))
+    np.testing.assert_allclose(g.xfxQ2([0], x, q2)[:, 0], shape, rtol=5e-4)   # pid 0 = gluon
+    # alpha_s: knots exact (the upper subgrid owns the threshold), monotonic, frozen above, power law below
+    np.testing.assert_allclose(g.alphasQ2(g.as_q2[[0, 1, 2, 4, 8, 12]]), g.as_vals[[0, 1, 2, 4, 8, 12]], rtol=1e-15)
+    aa = g.alphasQ2(10 ** np.linspace(0.5, 7.9, 400))
+    assert np.all(np.diff(aa) < 0)
+    assert g.alphasQ2([1e9])[0] == g.as_vals[-1] and g.alphasQ2([1.0])[0] > g.as_vals[0]
+    assert abs(g.alphasQ2([91.1876**2])[0] - 0.118) < 1e-12
