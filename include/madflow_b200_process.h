@@ -110,10 +110,18 @@ typedef struct mfp_integrand_args {
   int32_t nchannels;
   int8_t chan_fl1[MFP_MAX_CHANNELS], chan_fl2[MFP_MAX_CHANNELS];
   double fixed_q2;          /* > 0: muF^2 = muR^2 fixed (madflow -q, :376-386); else q2 = (sum mT/2)^2    */
+  /* several subprocesses on the same events (`p p > ...`: ret += luminosity_i * smatrix_i, :444-455): every
+   * library runs generation + matrix element into its own workspace with skip_accumulate = 1, then
+   * mf_vegas_accumulate_sum (madflow_b200.h) sums the terms per event.  Helicity-parallel flavour only.    */
+  int32_t skip_accumulate;
 } mfp_integrand_args;
 
 /* recommended persistent grid size for the current device (multiple of the SM count)          */
 int mfp_integrand_blocks(void);
+/* Fix the grid size mfp_integrand_blocks() reports for the helicity-parallel flavour (0 = back to automatic).
+ * The event buffer is cut into 4 segments per block, so libraries that evaluate different subprocesses on the
+ * SAME events (skip_accumulate, below) must agree on it: slot i then holds the same event in all of them.   */
+int mfp_set_integrand_blocks(int nblocks);
 /* bytes of device scratch mfp_integrand needs for a call generating `nevents` events (0 for the
  * one-event-per-thread flavour, whose single kernel keeps everything on chip)                   */
 int64_t mfp_integrand_workspace(int64_t nevents);
@@ -124,7 +132,7 @@ int mfp_integrand(const mfp_integrand_args* args, void* stream);
 
 /* The events of the LAST mfp_integrand call on this workspace (helicity-parallel flavour): the slots
  * that reached the matrix element, grouped in segments; slots of weight 0 are padding.  The integrand value
- * of slot i is d_me[i] * d_weight[i].  What the reference passes to its LHE writer from inside the integrand
+ * of slot i is d_me[i] * d_weight[i] (the weight includes the parton luminosity).  What the reference passes to its LHE writer from inside the integrand
  * (scripts/madflow_exec.py:462-464: all_ps and weight * ret).  Returns -2 for the one-event-per-thread
  * flavour, whose single kernel keeps the events on chip.                                                   */
 typedef struct mfp_event_view {
@@ -133,6 +141,7 @@ typedef struct mfp_event_view {
   const double* d_me;       /* (capacity) |M|^2                                                             */
   const double* d_alpha_s;  /* (capacity) alpha_s of the event                                              */
   int64_t capacity;
+  const uint8_t* d_bins;    /* (ndim, capacity) VEGAS bin of every dimension                                */
 } mfp_event_view;
 int mfp_integrand_events(void* d_workspace, int64_t nevents, mfp_event_view* out);
 

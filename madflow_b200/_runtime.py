@@ -67,13 +67,13 @@ class mfp_integrand_args(ctypes.Structure):
         ("d_workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
         ("d_pdf", ctypes.c_void_p), ("nchannels", ctypes.c_int32),
         ("chan_fl1", ctypes.c_int8 * MFP_MAX_CHANNELS), ("chan_fl2", ctypes.c_int8 * MFP_MAX_CHANNELS),
-        ("fixed_q2", ctypes.c_double),
+        ("fixed_q2", ctypes.c_double), ("skip_accumulate", ctypes.c_int32),
     ]
 
 
 class mfp_event_view(ctypes.Structure):
     _fields_ = [("d_mom", ctypes.c_void_p), ("d_weight", ctypes.c_void_p), ("d_me", ctypes.c_void_p),
-                ("d_alpha_s", ctypes.c_void_p), ("capacity", ctypes.c_int64)]
+                ("d_alpha_s", ctypes.c_void_p), ("capacity", ctypes.c_int64), ("d_bins", ctypes.c_void_p)]
 
 
 def _require_cuda():
@@ -185,6 +185,10 @@ class ProcessLib:
     def integrand_blocks(self):
         _require_cuda()
         return int(self.lib.mfp_integrand_blocks())
+
+    def set_integrand_blocks(self, nblocks):
+        """Fix the grid size / event-buffer segmentation of the helicity-parallel integrand (0 = automatic)."""
+        self._check(self.lib.mfp_set_integrand_blocks(int(nblocks)))
 
     def integrand_workspace(self, nevents):
         self.lib.mfp_integrand_workspace.restype = ctypes.c_int64

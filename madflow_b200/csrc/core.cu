@@ -424,6 +424,19 @@ int mf_vegas_accumulate(const double* d_f, const double* d_xjac, const uint8_t* 
   return check_launch("accumulate_kernel");
 }
 
+int mf_vegas_accumulate_sum(int nterms, const double* const* d_f, const double* const* d_w, const uint8_t* d_bins,
+                            int64_t nevt, int ndim, int with_hist, double* d_partial, int nblocks, void* stream) {
+  if (ndim < 1 || ndim > MF_MAX_DIM) return fail_msg("mf_vegas_accumulate_sum: 1 <= ndim <= 32");
+  if (nterms < 1 || nterms > ACC_MAX_TERMS) return fail_msg("mf_vegas_accumulate_sum: 1 <= nterms <= 8");
+  if (nblocks < 1) return fail_msg("mf_vegas_accumulate_sum: nblocks < 1");
+  AccTerms t;
+  t.n = nterms;
+  for (int i = 0; i < ACC_MAX_TERMS; ++i) t.f[i] = i < nterms ? d_f[i] : nullptr, t.w[i] = i < nterms ? d_w[i] : nullptr;
+  const size_t smem = (ndim * VEGAS_BINS + 24) * sizeof(double);
+  accumulate_sum_kernel<<<nblocks, ACC_BLOCK, smem, (cudaStream_t)stream>>>(t, d_bins, nevt, ndim, with_hist, d_partial);
+  return check_launch("accumulate_sum_kernel");
+}
+
 int mf_vegas_reduce(const double* d_partial, int nblocks, int ndim, int add, double* d_sums, void* stream) {
   const int len = VEGAS_HEADER + ndim * VEGAS_BINS;
   vegas_reduce_kernel<<<(len + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_partial, nblocks, len, add, d_sums);

@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(GEN_BLOCK) ps_generate_kernel(const GenArgs a)
 }
 
 constexpr int ACC_BLOCK = 256;
-// t = f * xjac; per block: [sum t, sum t^2, #(t != 0), 0] + histogram of t^2 over (dimension, bin)
-__global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const double* f, const double* xjac,
-                                                               const unsigned char* bins, long long nevt, int ndim,
-                                                               int with_hist, double* partial) {
+// t = value(e) = f * xjac; per block: [sum t, sum t^2, #(t != 0), 0] + histogram of t^2 over (dimension, bin)
+template <class Value>
+__device__ __forceinline__ void accumulate_block(Value value, const unsigned char* bins, long long nevt, int ndim,
+                                                 int with_hist, double* partial) {
   extern __shared__ double shist[];  // ndim*50, then 3*8 for the reduction
   double* red = shist + ndim * VEGAS_BINS;
   for (int i = threadIdx.x; i < ndim * VEGAS_BINS; i += blockDim.x) shist[i] = 0.0;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const double* f, 
   double s1 = 0.0, s2 = 0.0, cnt = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
-    const double t = f[e] * xjac[e];
+    const double t = value(e);
     const double t2 = t * t;
     s1 += t;
     s2 += t2;
@@ -163,6 +163,32 @@ __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const double* f, 
     out[0] = a, out[1] = b, out[2] = c, out[3] = 0.0;
   }
   for (int i = threadIdx.x; i < ndim * VEGAS_BINS; i += blockDim.x) out[VEGAS_HEADER + i] = shist[i];
+}
+
+__global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const double* f, const double* xjac,
+                                                               const unsigned char* bins, long long nevt, int ndim,
+                                                               int with_hist, double* partial) {
+  accumulate_block([=](long long e) { return f[e] * xjac[e]; }, bins, nevt, ndim, with_hist, partial);
+}
+
+// several subprocesses on the same events (madflow_exec.py:444-455: ret += luminosity_i * smatrix_i):
+// t = sum_i f_i * w_i with w_i = xjac * phase-space weight * luminosity_i
+constexpr int ACC_MAX_TERMS = 8;
+struct AccTerms {
+  int n;
+  const double* f[ACC_MAX_TERMS];
+  const double* w[ACC_MAX_TERMS];
+};
+__global__ void __launch_bounds__(ACC_BLOCK) accumulate_sum_kernel(const AccTerms terms, const unsigned char* bins,
+                                                                   long long nevt, int ndim, int with_hist,
+                                                                   double* partial) {
+  accumulate_block(
+      [=](long long e) {
+        double t = 0.0;
+        for (int i = 0; i < terms.n; ++i) t += terms.f[i][e] * terms.w[i][e];
+        return t;
+      },
+      bins, nevt, ndim, with_hist, partial);
 }
 
 // carve the caller's workspace into the event buffer; returns bytes needed (buf may be null)

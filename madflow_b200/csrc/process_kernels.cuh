@@ -302,6 +302,8 @@ int prepare_integrand_args(const mfp_integrand_args* u, IntegrandArgs& a) {
   if (u->ncuts < 0 || u->ncuts > MFP_MAX_CUTS) return fail_msg("mfp_integrand: too many cuts");
   if (u->nblocks <= 0) return fail_msg("mfp_integrand: nblocks must come from mfp_integrand_blocks()");
   if (!u->d_grid || !u->d_partial) return fail_msg("mfp_integrand: null grid or partial buffer");
+  if (u->skip_accumulate && !u->d_workspace)
+    return fail_msg("mfp_integrand: skip_accumulate needs the event buffer of the helicity-parallel flavour");
   if (u->alpha_mode < 0 || u->alpha_mode > 2) return fail_msg("mfp_integrand: alpha_mode must be 0, 1 or 2");
   if (u->alpha_mode == 2 && !u->d_pdf) return fail_msg("mfp_integrand: alpha_mode 2 needs the PDF table (d_pdf)");
   if (u->d_pdf && (u->nchannels <= 0 || u->nchannels > MFP_MAX_CHANNELS))
@@ -328,6 +330,7 @@ int prepare_integrand_args(const mfp_integrand_args* u, IntegrandArgs& a) {
 
 template <class P>
 int launch_integrand(const mfp_integrand_args* u, cudaStream_t st) {
+  if (u->skip_accumulate) return fail_msg("mfp_integrand: skip_accumulate needs the helicity-parallel flavour");
   IntegrandArgs a;
   if (int rc = prepare_integrand_args<P>(u, a)) return rc;
   cudaError_t e = cudaFuncSetAttribute(integrand_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -728,8 +728,13 @@ int launch_smatrix_hp(const double* d_p, int layout, long long nevt, const doubl
   return 0;
 }
 
+// grid size override (mfp_set_integrand_blocks): libraries that work on the same events must cut their event
+// buffers into the same segments
+static int g_blocks_override = 0;
+
 template <class P>
 int integrand_blocks_hp() {
+  if (g_blocks_override > 0) return g_blocks_override;
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -756,6 +761,7 @@ int integrand_events_hp(void* d_workspace, long long nevents, mfp_event_view* ou
   EventBuffer b;
   event_buffer_layout(nevents, hp_segments<P>(integrand_blocks_hp<P>()), P::NEXT, NDIM, d_workspace, &b);
   out->d_mom = b.mom, out->d_weight = b.w, out->d_me = b.me, out->d_alpha_s = b.as, out->capacity = b.cap;
+  out->d_bins = b.bins;
   return 0;
 }
 
@@ -791,6 +797,7 @@ int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("smatrix_kernel_hp launch", e);
 
+  if (u->skip_accumulate) return 0;  // the caller sums several subprocesses (mf_vegas_accumulate_sum)
   accumulate_kernel<<<u->nblocks, ACC_BLOCK, (NDIM * VEGAS_BINS + 24) * sizeof(double), st>>>(
       g.buf.me, g.buf.w, g.buf.bins, g.buf.cap, NDIM, u->accumulate_hist, u->d_partial);
   e = cudaGetLastError();
@@ -860,6 +867,11 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
     return 0;                                                                                                  \
   }                                                                                                            \
   int mfp_get_variant(void) { return mf::use_hp<P>() ? 2 : 1; }                                                \
+  int mfp_set_integrand_blocks(int nblocks) {                                                                  \
+    if (nblocks < 0) return mf::fail_msg("mfp_set_integrand_blocks: 0 = automatic, > 0 = grid size");          \
+    mf::g_blocks_override = nblocks;                                                                           \
+    return 0;                                                                                                  \
+  }                                                                                                            \
   int mfp_smatrix(const double* d_p, int layout, int64_t nevt, const double* par, const double* d_coup,        \
                   int64_t cs, double sqh, double* d_out, void* st) {                                           \
     return mf::dispatch_smatrix<P>(d_p, layout, nevt, par, d_coup, cs, sqh, d_out, -1, (cudaStream_t)st);      \

@@ -35,13 +35,15 @@ def alpha_s_one_loop(q2, alpha_mz=0.118, mz2=MZ * MZ, b0=None):
 
 class FusedIntegrand:
     def __init__(self, matrix, model, sqrts=13e3, masses=None, pt_cut=None, cuts=None, lab_frame=True,
-                 alpha_s=None, running=False, alpha_mz=0.118, mz=MZ, nf=5, pdf=None, fixed_scale=None):
+                 alpha_s=None, running=False, alpha_mz=0.118, mz=MZ, nf=5, pdf=None, fixed_scale=None,
+                 initial_states=None, mirror_initial_states=None):
         """alpha_s: frozen value (default: 0.118 as `madflow --no_pdf -q`, madflow_exec.py:379-380);
         running=True: q2 = (sum mT/2)^2 per event (madflow_exec.py:428-431) with one-loop alpha_s.
         pdf: a madflow_b200.pdf.PDF -- the event weight gets the parton luminosity of the process's initial
         states at muF^2 = q2 (madflow_exec.py:410-417, 450-454) and, with running=True, alpha_s comes from the
         set's table (`pdf.alphasQ2`, :431); fixed_scale (GeV): muF = muR fixed and alpha_s frozen at
-        `pdf.alphasQ2(fixed_scale^2)` (`madflow -q`, :376-386)."""
+        `pdf.alphasQ2(fixed_scale^2)` (`madflow -q`, :376-386).  initial_states / mirror_initial_states: the
+        flavour pairs of the luminosity when they differ from the ones the process library recorded."""
         self.matrix, self.model = matrix, model
         self._lib = matrix._lib
         n = int(matrix.nexternal)
@@ -66,7 +68,11 @@ class FusedIntegrand:
         if pdf is not None:
             from .pdf import initial_state_channels
 
-            self.channels = initial_state_channels(matrix, pdf)
+            self.channels = initial_state_channels(matrix, pdf, initial_states, mirror_initial_states)
+            self.initial_pairs = [tuple(int(f) for f in pr) for pr in
+                                  (initial_states if initial_states is not None else matrix.initial_states)]
+            if matrix.mirror_initial_states if mirror_initial_states is None else mirror_initial_states:
+                self.initial_pairs += [(b, a) for a, b in list(self.initial_pairs)]
             if not 0 < len(self.channels[0]) <= rt.MFP_MAX_CHANNELS:
                 raise ValueError(f"{len(self.channels[0])} initial-state channels (1..{rt.MFP_MAX_CHANNELS} supported): "
                                  "does the process know its initial_states?")
@@ -119,8 +125,10 @@ class FusedIntegrand:
                 a.chan_fl1[i], a.chan_fl2[i] = c1, c2
         return a
 
-    def launch(self, divisions, seed, iteration, first_event, nevents, inv_total, partial, nblocks, train):
+    def launch(self, divisions, seed, iteration, first_event, nevents, inv_total, partial, nblocks, train,
+               skip_accumulate=False):
         a = self._args()
+        a.skip_accumulate = int(bool(skip_accumulate))
         a.d_grid = divisions.data_ptr()
         a.seed, a.iteration, a.first_event, a.nevents = int(seed), int(iteration), int(first_event), int(nevents)
         a.inv_total_events = float(inv_total)
@@ -163,9 +171,7 @@ class FusedIntegrand:
 
         pdf = self.pdf
         if pdf is not None:
-            ini = [tuple(int(f) for f in pr) for pr in self.matrix.initial_states]
-            if self.matrix.mirror_initial_states:
-                ini += [(b, a) for a, b in ini]
+            ini = self.initial_pairs
             had1, had2 = [a for a, _ in ini], [b for _, b in ini]
 
         def cross_section(xrand, n_dim=None, weight=None):
@@ -193,6 +199,88 @@ class FusedIntegrand:
                 out = torch.zeros(xrand.shape[0], dtype=torch.float64, device=ret.device)
                 out[idx[:, 0].long()] = ret
                 return out
+            return ret
+
+        return cross_section
+
+
+class MultiProcessIntegrand:
+    """Several subprocesses of one hadronic process on the same events -- `p p > t t~` = g g > t t~ and
+    q q~ > t t~ -- summed per event, each weighted by its own parton luminosity (the loop over `matrices` in the
+    reference's cross_section, scripts/madflow_exec.py:444-455).
+
+    Every subprocess runs the generation and matrix-element stages of its own library on the same Philox
+    counters, grid and cuts, so slot i of every event buffer holds the same event; one accumulation kernel then
+    forms t = sum_p |M|^2_p * w_p (w_p = xjac * phase-space weight * luminosity_p) and the VEGAS sums of t."""
+
+    def __init__(self, integrands):
+        self.parts = list(integrands)
+        if not self.parts:
+            raise ValueError("at least one subprocess")
+        first = self.parts[0]
+        for fi in self.parts:
+            if (fi.nexternal, fi.sqrts, fi.masses, fi.cuts, fi.lab_frame) != (first.nexternal, first.sqrts, first.masses,
+                                                                               first.cuts, first.lab_frame):
+                raise ValueError("the subprocesses must share the phase space (particles, masses, cuts, frame)")
+            if fi.matrix.variant != "hp":
+                fi.matrix.set_variant("hp")   # the kernel pipeline that keeps the events in device memory
+        if len(self.parts) > 8:
+            raise ValueError("at most 8 subprocesses (mf_vegas_accumulate_sum)")
+        self.n_dim, self.nexternal = first.n_dim, first.nexternal
+        self.max_events_per_launch = min(fi.max_events_per_launch for fi in self.parts)
+        self._common_blocks = None
+        self.event_sink = None   # madflow_b200.events.EventSink: sees the momenta and the summed integrand value
+
+    def nblocks(self):
+        """One grid size for all subprocess libraries: it fixes how the event buffers are cut into segments, and
+        slot i must hold the same event in every buffer."""
+        if self._common_blocks is None:
+            for fi in self.parts:
+                fi._lib.set_integrand_blocks(0)
+            self._common_blocks = min(fi.nblocks() for fi in self.parts)
+        for fi in self.parts:
+            fi._lib.set_integrand_blocks(self._common_blocks)
+        return self._common_blocks
+
+    def launch(self, divisions, seed, iteration, first_event, nevents, inv_total, partial, nblocks, train):
+        views = []
+        nblocks = self.nblocks()
+        for fi in self.parts:
+            fi.launch(divisions, seed, iteration, first_event, nevents, inv_total, partial, nblocks, train,
+                      skip_accumulate=True)
+            views.append(fi._lib.integrand_events(fi._ws.data_ptr(), nevents))
+        cap = int(views[0].capacity)
+        if any(int(v.capacity) != cap for v in views):
+            raise rt.MadflowB200Error("the subprocess libraries lay out their event buffers differently")
+        n = len(views)
+        fptr = (ctypes.c_void_p * n)(*[v.d_me for v in views])
+        wptr = (ctypes.c_void_p * n)(*[v.d_weight for v in views])
+        lib = rt.core()
+        rt.check(lib, lib.mf_vegas_accumulate_sum(n, fptr, wptr, ctypes.c_void_p(views[0].d_bins), ctypes.c_int64(cap),
+                                                  self.n_dim, int(bool(train)), rt.ptr(partial), int(nblocks),
+                                                  rt.stream_ptr()))
+        if self.event_sink is not None:
+            # what the reference hands its LHE writer: all_ps and the summed ret * weight (madflow_exec.py:462-464)
+            evs = [fi.events(nevents) for fi in self.parts]
+            total = evs[0][2] * evs[0][1]
+            for mom, w, me, _ in evs[1:]:
+                total = total + me * w
+            self.event_sink.consume(evs[0][0], None, total, None, first_event)
+
+    def release(self):
+        """Give the libraries their own grid sizes back (the override is per library, not per integrand)."""
+        for fi in self.parts:
+            fi._lib.set_integrand_blocks(0)
+        self._common_blocks = None
+
+    def python_integrand(self):
+        """The same sum from the separate API calls, as the reference assembles it."""
+        parts = [fi.python_integrand() for fi in self.parts]
+
+        def cross_section(xrand, n_dim=None, weight=None):
+            ret = parts[0](xrand, n_dim=n_dim, weight=weight)
+            for f in parts[1:]:
+                ret = ret + f(xrand, n_dim=n_dim, weight=weight)
             return ret
 
         return cross_section

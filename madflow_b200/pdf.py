@@ -216,12 +216,12 @@ def mkPDF(fname, dirname=None):
                    "LHAPDF_DATA_PATH), or run with --no_pdf")
 
 
-def initial_state_channels(matrix, pdf):
+def initial_state_channels(matrix, pdf, initial_states=None, mirror=None):
     """The flavour pairs whose luminosities are summed for one subprocess: `initial_states` plus, when
     `mirror_initial_states`, the same pairs with the hadrons exchanged (madflow_exec.py:141-155, 446-454),
-    as columns of the PDF table."""
-    initials = [tuple(int(f) for f in pair) for pair in matrix.initial_states]
+    as columns of the PDF table.  `initial_states` / `mirror` override what the process library recorded."""
+    initials = [tuple(int(f) for f in pair) for pair in (initial_states if initial_states is not None else matrix.initial_states)]
     pairs = list(initials)
-    if getattr(matrix, "mirror_initial_states", False):
+    if (getattr(matrix, "mirror_initial_states", False) if mirror is None else mirror):
         pairs += [(b, a) for a, b in initials]
     return [pdf.column(a) for a, _ in pairs], [pdf.column(b) for _, b in pairs]

@@ -1,4 +1,4 @@
-"""Built-in tree-level process generator for  g g > t t~ + k g  (k = 0..3), QCD only.
+"""Built-in tree-level process generator for  g g > t t~ + k g  (k = 0..3) and  q q~ > t t~, QCD only.
 
 Why it exists: the IR of a process (process_ir.py) is what MG5_aMC computes and hands to
 madflow's exporter -- the diagrams, the HELAS call list, the JAMP coefficients and the colour
@@ -517,6 +517,49 @@ def generate_ir(n_final_gluons, name=None, root="centroid"):
     return ir
 
 
+def qqbar_ttx_ir(pp=True, name="1_uux_ttx"):
+    """IR of  q q~ > t t~  (one s-channel gluon), the second subprocess of madflow's default `p p > t t~`
+    (MG5 writes it as matrix_1_uux_ttx with all light flavours in `initial_states`; `mirror_initial_states`
+    because either proton may supply the quark: PyOut_exporter.py:186-191, madflow_exec.py:141-155).
+    MG5 itself is absent, so like every generated process this is restated from the Feynman rules and checked
+    by a closed form (tests/test_procgen.py): parity unpinned with respect to MG5's own output.
+
+      legs    0 = q (incoming fermion, ixxxxx nsf +1), 1 = q~ (oxxxxx nsf -1), 2 = t, 3 = t~
+      colour  T^a_{..} T^a_{..} = 1/2 (delta delta - 1/N delta delta): two colour flows with JAMPs
+              (1/2, -1/6) x amp and colour matrix [[9, 3], [3, 9]]  (sum = 2 = Tr(T^a T^b)^2 x 8 ... = (N^2-1)/4)
+      average 4 spin states x 9 colours"""
+    hel_states = [[1, -1], [-1, 1], [-1, 1], [1, -1]]   # antiparticle-like legs listed reversed, as for t~ in g g > t t~
+    flavours = [[2, -2], [4, -4], [1, -1], [3, -3]] if pp else [[2, -2]]
+    return {
+        "name": name,
+        "process": "u u~ > t t~ WEIGHTED<=2 @1",
+        "nexternal": 4, "ninitial": 2, "ndiags": 1, "ncomb": 16, "nwavefuncs": 5,
+        "helicities": [list(h) for h in itertools.product(*hel_states)],
+        "denominator": 36,
+        "params": ["mdl_MT", "mdl_WT"],
+        "couplings": ["GC_11"],
+        "initial_states": flavours, "mirror_initial_states": bool(pp),
+        "pdg": [2, -2, 6, -6],
+        "masses": ["ZERO", "ZERO", "mdl_MT", "mdl_MT"],
+        "calls": [
+            {"op": "ixxxxx", "out": 0, "leg": 0, "mass": "ZERO", "nsf": +1},
+            {"op": "oxxxxx", "out": 1, "leg": 1, "mass": "ZERO", "nsf": -1},
+            {"op": "oxxxxx", "out": 2, "leg": 2, "mass": "mdl_MT", "nsf": +1},
+            {"op": "ixxxxx", "out": 3, "leg": 3, "mass": "mdl_MT", "nsf": -1},
+            {"op": "FFV1P0_3", "out": 4, "in": [0, 1], "coup": "GC_11", "mass": "ZERO", "width": "ZERO"},
+            {"op": "FFV1_0", "amp": 0, "in": [3, 2, 4], "coup": "GC_11"},
+        ],
+        "jamp": [[(0, 0.5, 0.0)], [(0, -1.0 / 6.0, 0.0)]],
+        "color_num": [[9, 3], [3, 9]],
+        "color_denom": [1, 1],
+    }
+
+
+# `p p > ...` processes of the command line: the subprocess libraries whose luminosity-weighted matrix elements
+# are summed (madflow_exec.py:444-455)
+MULTI_PROCESSES = {"p p > t t~": ["1_gg_ttx", "1_uux_ttx"]}
+
+
 def builtin_irs():
     """Processes compiled into the package besides the pinned g g > t t~."""
-    return [generate_ir(1), generate_ir(2), generate_ir(3)]
+    return [generate_ir(1), generate_ir(2), generate_ir(3), qqbar_ttx_ir()]

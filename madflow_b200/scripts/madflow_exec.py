@@ -28,10 +28,22 @@ DEFAULT_PDF = "NNPDF31_nnlo_as_0118"
 
 
 def process_library_name(madgraph_process):
-    """'g g > t t~ g' -> '1_gg_ttxg' (MG5's shell_string for process number 1, PyOut_exporter.py:138)."""
+    """'g g > t t~ g' -> '1_gg_ttxg' (MG5's shell_string for process number 1, PyOut_exporter.py:138); the light
+    q q~ > t t~ processes share the library MG5 names after the first flavour, 1_uux_ttx."""
     ini, fin = madgraph_process.split(">")
+    if "".join(ini.split()) in ("dd~", "ss~", "cc~") and "".join(fin.split()) == "tt~":
+        return "1_uux_ttx"
     shell = lambda side: "".join(side.split()).replace("~", "x")
     return f"1_{shell(ini)}_{shell(fin)}"
+
+
+def subprocess_libraries(madgraph_process):
+    """The process libraries behind a process string: one, or for the hadronic processes the generator knows
+    (`p p > t t~`) the subprocesses whose luminosity-weighted matrix elements are summed (madflow_exec.py:444-455)."""
+    from madflow_b200.procgen import MULTI_PROCESSES
+
+    key = " ".join(madgraph_process.split())
+    return list(MULTI_PROCESSES.get(key, [process_library_name(madgraph_process)]))
 
 
 def build_parser():
@@ -82,14 +94,16 @@ def madflow_main(args=None, quick_return=False):
     from madflow_b200 import vegas as mfv
     from madflow_b200.lhe_writer import LheWriter
 
-    name = process_library_name(args.madgraph_process)
-    if name not in mfm.available_processes():
-        raise SystemExit(f"process '{args.madgraph_process}' ({name}) has no compiled process library; available: "
-                         f"{mfm.available_processes()} (export it through the pyout plugin's CUDA backend)")
+    names = subprocess_libraries(args.madgraph_process)
+    name = names[0]
+    for nm in names:
+        if nm not in mfm.available_processes():
+            raise SystemExit(f"process '{args.madgraph_process}' ({nm}) has no compiled process library; available: "
+                             f"{mfm.available_processes()} (export it through the pyout plugin's CUDA backend)")
     output_path = args.output if args.output is not None else Path(tempfile.mkdtemp(prefix="mad_"))
     output_path.mkdir(parents=True, exist_ok=True)
     if args.dry_run:
-        logger.info("Process %s -> library %s; dry run, nothing executed", args.madgraph_process, name)
+        logger.info("Process %s -> libraries %s; dry run, nothing executed", args.madgraph_process, names)
         return None, None, None
 
     pdf = None
@@ -131,9 +145,19 @@ def madflow_main(args=None, quick_return=False):
         light = [i for i in range(2, nparticles) if masses[i - 2] == 0.0]
         cuts = [("dr", (i, j), args.dr_cut, None) for a, i in enumerate(light) for j in light[a + 1:]]
         logger.info("Applying Delta R > %.2f to the pairs %s", args.dr_cut, [c[1] for c in cuts])
-    fi = mfi.FusedIntegrand(matrix, model, sqrts=13e3, masses=masses, pt_cut=args.pt_cut, cuts=cuts, lab_frame=True,
-                            running=args.fixed_scale is None, alpha_s=0.118 if pdf is None else None, pdf=pdf,
-                            fixed_scale=args.fixed_scale if pdf is not None else None)
+    # a single-flavour process string against the all-flavour q q~ library of `p p`: only that flavour's luminosity
+    one_flavour = {"u u~ > t t~": 2, "d d~ > t t~": 1, "s s~ > t t~": 3, "c c~ > t t~": 4}.get(" ".join(args.madgraph_process.split()))
+
+    def integrand_of(mat, mod):
+        return mfi.FusedIntegrand(mat, mod, sqrts=13e3, masses=masses, pt_cut=args.pt_cut, cuts=cuts, lab_frame=True,
+                                  running=args.fixed_scale is None, alpha_s=0.118 if pdf is None else None, pdf=pdf,
+                                  fixed_scale=args.fixed_scale if pdf is not None else None,
+                                  initial_states=[(one_flavour, -one_flavour)] if one_flavour else None,
+                                  mirror_initial_states=False if one_flavour else None)
+
+    fi = integrand_of(matrix, model)
+    if len(names) > 1:   # one event sample, the subprocesses summed per event
+        fi = mfi.MultiProcessIntegrand([fi] + [integrand_of(*mfm.get_process(nm)) for nm in names[1:]])
     if args.events_per_device:
         fi.max_events_per_launch = args.events_per_device
     if nparticles >= 5 and args.frozen_iter == 0:

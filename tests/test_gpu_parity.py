@@ -661,3 +661,79 @@ def test_fused_integrand_with_pdf(mf, toy_pdf, name, k, nev, fixed, variant):
     v0 = mf.vegas.VegasFlow(fi.n_dim, nev, seed=4)
     v0.compile(fi0)
     assert abs(v0.run_iteration()[0] / r1[0] - 1) > 0.1
+
+
+# ------------------------------------------------------------------------------ p p > t t~
+def test_qqbar_ttx_smatrix_vs_oracle_and_closed_form(mf):
+    """q q~ > t t~, both kernel flavours: per-event |M|^2 vs the oracle (1e-12) and the textbook closed form."""
+    from madflow_b200 import procgen
+
+    ir = procgen.qqbar_ttx_ir()
+    x = np.random.default_rng(12).random((50_000, 10))
+    p, w, x1, x2 = ops.ramboflow(x, 4, 13e3, [MT, MT], xfactor="converged")
+    lab = ops.boost_to_lab(p, x1, x2)
+    a_s = 0.09 + 0.05 * np.random.default_rng(13).random(lab.shape[0])
+    op = sm_params(alpha_s=a_s)
+    ref = omatrix.smatrix(ir, lab, op)
+    m, model = mf.matrix.get_process("1_uux_ttx")
+    assert m.initial_states == [(2, -2), (4, -4), (1, -1), (3, -3)] and m.mirror_initial_states
+    for variant in ("thread", "hp"):
+        _select(mf, m, variant)
+        out = cpu(m.smatrix(lab, *model.evaluate(a_s)))
+        assert np.max(np.abs(out / ref - 1)) < REL_ME
+    m.set_variant("default")
+    dot = lambda a, b: a[:, 0] * b[:, 0] - np.sum(a[:, 1:] * b[:, 1:], axis=1)
+    s = dot(p[:, 0] + p[:, 1], p[:, 0] + p[:, 1])
+    t = dot(p[:, 0] - p[:, 2], p[:, 0] - p[:, 2])
+    u = dot(p[:, 0] - p[:, 3], p[:, 0] - p[:, 3])
+    g4 = (4 * np.pi * a_s) ** 2
+    exact = 4 * g4 / 9 * ((MT**2 - t) ** 2 + (MT**2 - u) ** 2 + 2 * MT**2 * s) / s**2
+    com = cpu(m.smatrix(p, *model.evaluate(a_s)))
+    np.testing.assert_allclose(com, exact, rtol=1e-9)   # SQH is float32-rounded in the reference constants: none here (no gluon legs)
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_multi_process_integrand_pp_ttx(mf, toy_pdf, train):
+    """`p p > t t~` = g g > t t~ + q q~ > t t~ on the same events, each with its own parton luminosity
+    (madflow_exec.py:444-455): pipeline + mf_vegas_accumulate_sum == separate C-ABI calls == oracle."""
+    from madflow_b200 import procgen, process_ir
+
+    pd, og = toy_pdf
+    nev = 60_000
+    parts = []
+    for name in procgen.MULTI_PROCESSES["p p > t t~"]:
+        m, model = mf.matrix.get_process(name)
+        parts.append(mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT], pt_cut=30.0, lab_frame=True,
+                                                 running=True, pdf=pd))
+    multi = mf.integrand.MultiProcessIntegrand(parts)
+    try:
+        v1 = mf.vegas.VegasFlow(10, nev, seed=4, train=train)
+        v1.compile(multi)
+        r1 = v1.run_iteration()
+        v2 = mf.vegas.VegasFlow(10, nev, seed=4, train=train)
+        v2.compile(multi.python_integrand())
+        r2 = v2.run_iteration()
+        assert abs(r1[0] / r2[0] - 1) < 1e-10 and abs(r1[1] / r2[1] - 1) < 1e-8
+        assert v1.last_me_events == v2.last_me_events and 0 < v1.last_me_events < nev
+        irs = [process_ir.gg_ttx_pinned(), procgen.qqbar_ttx_ir()]
+        xss = [ovegas.make_cross_section(ir, lambda a: sm_params(alpha_s=a), 13e3, [MT, MT], pt_cut=30.0, lab_frame=True,
+                                         alpha_s_fn=og.alphasQ2, pdf=og) for ir in irs]
+        ov = ovegas.Vegas(10, nev, seed=4)
+        if not train:
+            ov.freeze_grid()
+        ov.compile(lambda x, **kw: xss[0](x) + xss[1](x))
+        r0 = ov.run_iteration()
+        assert abs(r1[0] / r0[0] - 1) < 1e-10 and abs(r1[1] / r0[1] - 1) < 1e-8
+        np.testing.assert_allclose(cpu(v1.divisions), ov.grid, rtol=1e-6, atol=1e-11)
+        # each subprocess alone, through its own fused pipeline: the two add up to the sum
+        singles = []
+        for fi in parts:
+            fi._lib.set_integrand_blocks(0)
+            v = mf.vegas.VegasFlow(10, nev, seed=4, train=False)
+            v.compile(fi)
+            singles.append(v.run_iteration()[0])
+        assert abs(sum(singles) / r1[0] - 1) < 1e-10 and min(singles) / r1[0] > 1e-3
+    finally:
+        multi.release()
+        for fi in parts:
+            fi.matrix.set_variant("default")

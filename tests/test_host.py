@@ -167,11 +167,15 @@ def test_madflow_cli_arguments_and_process_names():
     assert args.events_per_iteration == int(1e6) and args.massive_particles == 2 and args.histograms and args.no_pdf
     assert process_library_name(args.madgraph_process) == "1_gg_ttxgg"
     assert process_library_name("g g > t t~") == "1_gg_ttx"
+    from madflow_b200.scripts.madflow_exec import subprocess_libraries
+
+    assert subprocess_libraries("p p  > t t~") == ["1_gg_ttx", "1_uux_ttx"] and subprocess_libraries("g g > t t~ g") == ["1_gg_ttxg"]
+    assert madflow_main(["--dry_run", "--madgraph_process", "p p > t t~"]) == (None, None, None)
     assert madflow_main(["--dry_run"]) == (None, None, None)   # like the reference, a dry run stops before the PDF
     with pytest.raises(SystemExit, match="NNPDF31_nnlo_as_0118"):
         madflow_main(["-i", "2"])             # a missing PDF set is refused, not approximated
     with pytest.raises(SystemExit):
-        madflow_main(["--no_pdf", "--dry_run", "--madgraph_process", "u u~ > t t~"])   # no such library
+        madflow_main(["--no_pdf", "--dry_run", "--madgraph_process", "e+ e- > t t~"])   # no such library
     assert madflow_main(["--no_pdf", "--dry_run", "--madgraph_process", "g g > t t~ g"]) == (None, None, None)
 
 
@@ -218,3 +222,28 @@ def test_pdf_set_reader_and_table(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU implementation"):
             p.xfxQ2([21], [0.1], [1e4])    # nothing but the CUDA kernels behind the product API
+
+
+def test_ctypes_structs_match_the_c_headers(tmp_path):
+    """The ctypes mirrors of mfp_integrand_args / mfp_event_view / mfp_info have the C compiler's layout."""
+    import shutil
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from madflow_b200 import _runtime as rt
+
+    fields = {"mfp_integrand_args": ["d_grid", "nevents", "masses", "cuts", "par", "alpha_mode", "sqh", "d_partial",
+                                     "d_workspace", "d_pdf", "nchannels", "chan_fl1", "chan_fl2", "fixed_q2", "skip_accumulate"],
+              "mfp_event_view": ["d_mom", "capacity", "d_bins"], "mfp_info": ["name", "ndim", "denominator", "flops_per_event"]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/madflow_b200_process.h"', "int main(void) {"]
+    for st, fl in fields.items():
+        src.append(f'  printf("%zu", sizeof({st}));')
+        src += [f'  printf(" %zu", offsetof({st}, {f}));' for f in fl]
+        src.append('  printf("\\n");')
+    src += ["  return 0;", "}"]
+    (tmp_path / "layout.c").write_text("\n".join(src))
+    subprocess.run(["gcc", str(tmp_path / "layout.c"), "-o", str(tmp_path / "layout")], check=True)
+    lines = subprocess.run([str(tmp_path / "layout")], check=True, capture_output=True, text=True).stdout.split("\n")
+    for (st, fl), line in zip(fields.items(), lines):
+        cls = getattr(rt, st)
+        assert [int(v) for v in line.split()] == [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f in fl], st

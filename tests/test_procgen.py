@@ -136,3 +136,46 @@ def test_helicity_parallel_data_flow_on_host(irs, k):
     row = 5
     one = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, only_comb=row, hp=True)
     np.testing.assert_allclose(one, omatrix.matrix(ir, p, ir["helicities"][row], params), rtol=1e-11)
+
+
+def _mandelstam(p):
+    dot = lambda a, b: a[:, 0] * b[:, 0] - np.sum(a[:, 1:] * b[:, 1:], axis=1)
+    s = dot(p[:, 0] + p[:, 1], p[:, 0] + p[:, 1])
+    t = dot(p[:, 0] - p[:, 2], p[:, 0] - p[:, 2])
+    u = dot(p[:, 0] - p[:, 3], p[:, 0] - p[:, 3])
+    return s, t, u
+
+
+def test_qqbar_ttx_closed_form():
+    """q q~ > t t~, the second subprocess of `p p > t t~`: the textbook result
+    sum |M|^2 / 36 = (4 g^4 / 9) [(m^2 - t)^2 + (m^2 - u)^2 + 2 m^2 s] / s^2  (no top propagator: any width)."""
+    ir = procgen.qqbar_ttx_ir()
+    assert process_ir.validate(ir)
+    assert ir["initial_states"] == [[2, -2], [4, -4], [1, -1], [3, -3]] and ir["mirror_initial_states"]
+    assert procgen.qqbar_ttx_ir(pp=False)["initial_states"] == [[2, -2]]
+    c = np.array(ir["color_num"], dtype=float) / np.array(ir["color_denom"], dtype=float)[:, None]
+    j = np.array([t[0][1] for t in ir["jamp"]])
+    assert j @ c @ j == pytest.approx(2.0)          # sum over colours of |T^a_ij T^a_kl|^2 = (N^2 - 1) / 4
+    p = _points(0, n=500, seed=5)
+    s, t, u = _mandelstam(p)
+    exact = 4 * G**4 / 9 * ((MT**2 - t) ** 2 + (MT**2 - u) ** 2 + 2 * MT**2 * s) / s**2
+    np.testing.assert_allclose(omatrix.smatrix(ir, p, sm_params(), EXACT), exact, rtol=1e-11)
+    assert codegen.flops_per_event(ir) == 16 * (4 * 30 + 176 + 108 + 4 + 40 + 4) + 17
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+def test_generated_cuda_source_on_host_qqbar_ttx():
+    """The emitted code of q q~ > t t~ (one event per thread and helicity-parallel), executed on the CPU."""
+    import hostcheck as hc
+
+    ir = procgen.qqbar_ttx_ir()
+    lib = hc.process(ir)
+    p = _points(0, n=200, seed=7)
+    a_s = 0.09 + 0.05 * np.random.default_rng(9).random(200)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    ref = omatrix.smatrix(ir, p, params)
+    np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF), ref, rtol=1e-12)
+    np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True), ref, rtol=1e-12)
+    one = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, only_comb=6, hp=True)
+    np.testing.assert_allclose(one, omatrix.matrix(ir, p, ir["helicities"][6], params), rtol=1e-11, atol=1e-300)
