@@ -1,0 +1,53 @@
+#!/usr/bin/env python3
+"""Cost of the parton luminosity and of the multi-subprocess sum in the fused integrand:
+python tools/time_pdf.py [nevents].  Uses the synthetic lhagrid1 set of oracle/pdf.py (no real grid offline).
+Prints matrix-element events/s of one VEGAS iteration (CUDA events) with and without the PDF table."""
+import os
+import sys
+import tempfile
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from madflow_b200 import integrand, matrix, pdf as mpdf, vegas
+from oracle import pdf as opdf
+
+nev = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+d = tempfile.mkdtemp()
+opdf.write_toy_set(d)
+pd = mpdf.mkPDF("ToyPDF/0", dirname=d)
+MT = 173.0
+
+
+def run(label, fi, ndim):
+    v = vegas.VegasFlow(ndim, nev, seed=4)
+    v.compile(fi)
+    v.run_iteration()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 3
+    for _ in range(reps):
+        r = v.run_iteration()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{label:44s} {v.last_me_events / ms * 1e3:12.4g} ME events/s  {nev / ms * 1e3:12.4g} generated/s  {ms:8.2f} ms  "
+          f"sigma {r[0]:.6g} +/- {r[1]:.3g}", flush=True)
+
+
+for name, k, variant in (("1_gg_ttx", 0, "thread"), ("1_gg_ttx", 0, "hp"), ("1_gg_ttxg", 1, "hp")):
+    m, model = matrix.get_process(name)
+    m.set_variant(variant)
+    masses = [MT, MT] + [0.0] * k
+    for label, p in (("no_pdf, one-loop alpha_s", None), ("toy PDF luminosity + alpha_s table", pd)):
+        fi = integrand.FusedIntegrand(m, model, sqrts=13e3, masses=masses, pt_cut=30.0, running=True, pdf=p)
+        run(f"{name} [{variant}] {label}", fi, fi.n_dim)
+    m.set_variant("default")
+parts = []
+for name in ("1_gg_ttx", "1_uux_ttx"):
+    m, model = matrix.get_process(name)
+    parts.append(integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT], pt_cut=30.0, running=True, pdf=pd))
+multi = integrand.MultiProcessIntegrand(parts)
+run("p p > t t~ (g g + q q~, toy PDF)", multi, 10)
+multi.release()
