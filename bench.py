@@ -94,7 +94,7 @@ def cpu_integrand(proc, wl):
 
         ir = process_ir.gg_ttx_pinned()
     return CpuIntegrand(ir, 13e3, wl["masses"], wl["pt_cut"], True, wl["running"], alpha_s=0.118,
-                        b0=mfi.one_loop_b0(), mz2=mfi.MZ**2)
+                        b0=mfi.one_loop_b0(), mz2=mfi.MZ**2, pdf_spec=wl.get("pdf"), pdf_dir=wl.get("pdf_dir"))
 
 
 def time_cpu(cpu, target_s=12.0):
@@ -152,12 +152,20 @@ def main():
     ap.add_argument("--events", type=int, default=None, help="generated events per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="default", choices=["default", "thread", "hp"])
+    ap.add_argument("--pdf", default=None, help="LHAPDF set (member 0) for the parton luminosity and alpha_s, as madflow "
+                    "without --no_pdf; needs the set on disk (--pdf_dir / LHAPDF_DATA_PATH).  Default: --no_pdf")
+    ap.add_argument("--pdf_dir", default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     proc = args.process or default_process()
     wl = dict(WORKLOADS[proc])
     if args.events:
         wl["events"] = args.events
+    if args.pdf:   # BASELINE config 2 names the PDF; no grid exists offline, so this is opt-in
+        wl["pdf"], wl["pdf_dir"] = args.pdf + "/0", args.pdf_dir
+        wl["running"] = True
+        wl["label"] = (wl["label"].split(", --no_pdf")[0] + f", PDF {args.pdf} (luminosity + alpha_s of the set at "
+                       "q2 = (sum mT/2)^2), pt>30 cuts")
 
     if args.impl == "reference":
         run_reference(args, wl, proc)
@@ -187,8 +195,13 @@ def main():
 
     m, model = mfm.get_process(proc)
     m.set_variant(args.variant)
+    pdf = None
+    if wl.get("pdf"):
+        from madflow_b200.pdf import mkPDF
+
+        pdf = mkPDF(wl["pdf"], dirname=wl["pdf_dir"])
     fi = mfi.FusedIntegrand(m, model, sqrts=13e3, masses=wl["masses"], pt_cut=wl["pt_cut"], lab_frame=True,
-                            running=wl["running"])
+                            running=wl["running"], pdf=pdf)
     n_per_gpu = wl["events"]
     vegas = mfv.VegasFlow(fi.n_dim, n_per_gpu * world, seed=4)
     vegas.compile(fi)

@@ -15,7 +15,7 @@ import numpy as np
 _state = {}
 
 
-def _init(ir_json, sqrts, masses, pt_cut, lab, running, alpha_s, b0, mz2):
+def _init(ir_json, sqrts, masses, pt_cut, lab, running, alpha_s, b0, mz2, pdf_spec=None, pdf_dir=None):
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
     from oracle import model, vegas
@@ -29,7 +29,15 @@ def _init(ir_json, sqrts, masses, pt_cut, lab, running, alpha_s, b0, mz2):
         return dict(c, mdl_MT=173.0, mdl_WT=1.4915000200271606)
 
     a_fn = (lambda q2: alpha_s / (1 + alpha_s * b0 * np.log(q2 / mz2))) if running else None
-    _state["xs"] = vegas.make_cross_section(ir, params, sqrts, masses, pt_cut=pt_cut, lab_frame=lab, alpha_s_fn=a_fn)
+    grid = None
+    if pdf_spec:   # luminosity and (when running) alpha_s from the LHAPDF set, as madflow does without --no_pdf
+        from oracle import pdf as opdf
+
+        grid = opdf.GridPDF.from_set(pdf_spec, pdf_dir)
+        if running and len(grid.as_q2):
+            a_fn = grid.alphasQ2
+    _state["xs"] = vegas.make_cross_section(ir, params, sqrts, masses, pt_cut=pt_cut, lab_frame=lab, alpha_s_fn=a_fn,
+                                            pdf=grid)
     _state["ndim"] = 4 * (ir["nexternal"] - 2) + 2
 
 
@@ -48,9 +56,10 @@ def _work(job):
 class CpuIntegrand:
     """Pool of workers evaluating the oracle's cross_section on event chunks."""
 
-    def __init__(self, ir, sqrts, masses, pt_cut, lab, running, alpha_s=0.118, b0=0.0, mz2=1.0, cores=None):
+    def __init__(self, ir, sqrts, masses, pt_cut, lab, running, alpha_s=0.118, b0=0.0, mz2=1.0, cores=None,
+                 pdf_spec=None, pdf_dir=None):
         self.cores = cores or os.cpu_count() or 1
-        args = (json.dumps(ir), sqrts, masses, pt_cut, lab, running, alpha_s, b0, mz2)
+        args = (json.dumps(ir), sqrts, masses, pt_cut, lab, running, alpha_s, b0, mz2, pdf_spec, pdf_dir)
         self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_init, initargs=args)
 
     def step(self, n_events, iteration=0, seed=4, chunk=None):
