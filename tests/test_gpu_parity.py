@@ -737,3 +737,44 @@ def test_multi_process_integrand_pp_ttx(mf, toy_pdf, train):
         multi.release()
         for fi in parts:
             fi.matrix.set_variant("default")
+
+
+# ------------------------------------------------------------------------------ command line
+def test_madflow_command_line_end_to_end(mf, toy_pdf, tmp_path):
+    """`madflow` (scripts/madflow_exec.py:243-530) end to end: g g > t t~ --no_pdf against a direct VegasFlow run, and
+    the reference's default kind of run -- p p > t t~ with a PDF set, warm-up + frozen iterations, --histograms."""
+    import gzip
+    import json
+
+    from madflow_b200.scripts.madflow_exec import madflow_main
+
+    pd, _ = toy_pdf
+    try:
+        args, (res, err), folder = madflow_main(["--no_pdf", "-c", "-i", "4", "--events_per_iteration", "200000",
+                                                 "--madgraph_process", "g g > t t~", "-o", str(tmp_path / "a")])
+        assert folder is None and res > 0 and err / res < 0.02
+        m, model = mf.matrix.get_process("1_gg_ttx")
+        fi = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT], pt_cut=30.0, lab_frame=True, running=True)
+        v = mf.vegas.VegasFlow(10, 200_000, seed=4)
+        v.compile(fi)
+        v.run_integration(2, log_time=False)
+        ref, referr = v.run_integration(2, log_time=False)
+        assert abs(res - ref) < 1e-9 * ref           # same seed, same schedule (2 warm-up + 2 final): the same numbers
+
+        args, (res, err), folder = madflow_main(["--pdf", "ToyPDF", "--pdf_dir", pd.dirname, "-c", "-i", "5", "-f", "2",
+                                                 "--events_per_iteration", "200000", "--histograms",
+                                                 "--madgraph_process", "p p > t t~", "-o", str(tmp_path / "b")])
+        assert res > 0 and err / res < 0.02
+        np.testing.assert_allclose(np.loadtxt(folder / "cross_err.txt"), [res, err], rtol=1e-6)
+        hists = json.loads((folder / "histograms.json").read_text())
+        pt = hists["pt_2"]
+        total = sum(pt["dsigma_pb"]) + sum(pt["underflow_overflow_pb"])
+        assert abs(total / res - 1) < 0.05            # the histogram is filled from the same (summed) event weights
+        with gzip.open(folder / "unweighted_events.lhe.gz", "rt") as fh:
+            text = fh.read()
+        assert text.count("<event>") > 10 and "</LesHouchesEvent>" in text   # the reference's closing tag (lhe_writer.py:227)
+    finally:
+        for name in ("1_gg_ttx", "1_uux_ttx"):
+            lib = mf.rt.process_lib(name)
+            lib.set_variant("default")
+            lib.set_integrand_blocks(0)

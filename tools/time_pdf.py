@@ -36,6 +36,25 @@ def run(label, fi, ndim):
           f"sigma {r[0]:.6g} +/- {r[1]:.3g}", flush=True)
 
 
+# the interpolation kernels alone (PDF.xfxQ2 / .alphasQ2): points/s and the HBM traffic they imply
+npt = 1 << 24
+g = torch.Generator("cuda").manual_seed(1)
+xs = 10 ** (-4.0 * torch.rand(npt, dtype=torch.float64, device="cuda", generator=g))
+q2s = 10 ** (2.0 + 5.0 * torch.rand(npt, dtype=torch.float64, device="cuda", generator=g))
+for label, fn, nout in (("xfxQ2, 1 flavour", lambda: pd.xfxQ2([21], xs, q2s), 1), ("xfxQ2, 5 flavours", lambda: pd.xfxQ2([21, 1, 2, -1, -2], xs, q2s), 5),
+                        ("xfxQ2, 11 flavours", lambda: pd.xfxQ2_allpid(xs, q2s), 11), ("alphasQ2", lambda: pd.alphasQ2(q2s), 1)):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    nin = 1 if label == "alphasQ2" else 2
+    print(f"{label:44s} {npt / ms * 1e3:12.4g} points/s  {ms:8.3f} ms  {(nin + nout) * 8 * npt / ms / 1e6:8.1f} GB/s of x, q2 in + values out", flush=True)
+
 for name, k, variant in (("1_gg_ttx", 0, "thread"), ("1_gg_ttx", 0, "hp"), ("1_gg_ttxg", 1, "hp")):
     m, model = matrix.get_process(name)
     m.set_variant(variant)
