@@ -555,11 +555,126 @@ def qqbar_ttx_ir(pp=True, name="1_uux_ttx"):
     }
 
 
+# ------------------------------------------------------------------------------------------------
+# two quark lines: q q~ > t t~ g and its crossings
+LIGHT_LINE_KINDS = ("uux_ttxg", "gu_ttxu", "gux_ttxux")
+
+
+def _su3():
+    """Generators T^a = lambda^a / 2 and structure constants f^{abc} of SU(3), numerically."""
+    import numpy as np
+
+    lam = np.zeros((8, 3, 3), dtype=complex)
+    lam[0][0, 1] = lam[0][1, 0] = 1
+    lam[1][0, 1], lam[1][1, 0] = -1j, 1j
+    lam[2][0, 0], lam[2][1, 1] = 1, -1
+    lam[3][0, 2] = lam[3][2, 0] = 1
+    lam[4][0, 2], lam[4][2, 0] = -1j, 1j
+    lam[5][1, 2] = lam[5][2, 1] = 1
+    lam[6][1, 2], lam[6][2, 1] = -1j, 1j
+    lam[7] = np.diag([1, 1, -2]) / math.sqrt(3)
+    T = lam / 2
+    f = np.zeros((8, 8, 8))
+    for a in range(8):
+        for b in range(8):
+            comm = T[a] @ T[b] - T[b] @ T[a]          # [T^a, T^b] = i f^{abc} T^c,  Tr(T^c T^d) = delta/2
+            for c in range(8):
+                f[a, b, c] = (-2j * np.trace(comm @ T[c])).real
+    return T, f
+
+
+def light_line_ttxg_ir(kind="uux_ttxg"):
+    """IR of the five-point processes with a light quark line, the subprocesses of `p p > t t~ j` besides
+    g g > t t~ g:   "uux_ttxg"  q q~ > t t~ g,   "gu_ttxu"  g q > t t~ q,   "gux_ttxux"  g q~ > t t~ q~
+    (MG5's names for the first flavour; `initial_states` lists all light flavours, `mirror_initial_states`
+    because either proton may supply either parton -- PyOut_exporter.py:186-191, madflow_exec.py:141-155).
+
+    Five diagrams -- the gluon attached to the top line (2), to the light line (2), to the exchanged gluon (1).  The
+    three processes are crossings of one amplitude: only the external wavefunctions differ (which leg is the
+    fermion-flow-in end `I` of the light line, which the flow-out end `O`, which the gluon `G`).  Colour: the tensor
+    of every diagram (generators and structure constants of SU(3) written out numerically) is projected on the four
+    colour flows  T^a_{t I} d_{O tb},  d_{t I} T^a_{O tb},  T^a_{t tb} d_{O I},  d_{t tb} T^a_{O I};  the colour matrix
+    is the Gram matrix of the flows.  MG5's own output is not in the reference tree: parity unpinned; checked by BRST
+    invariance of every colour flow, by the explicit colour sum and on the generated CUDA code (tests/test_procgen.py)."""
+    import numpy as np
+
+    roles = {   # leg -> (wavefunction call, nsf); I / O = ends of the light line, G = the gluon
+        "uux_ttxg": dict(I=(0, "ixxxxx", +1), O=(1, "oxxxxx", -1), G=(4, "vxxxxx", +1), pdg=[2, -2, 6, -6, 21],
+                         initial=[[2, -2], [4, -4], [1, -1], [3, -3]], colour_avg=9, process="u u~ > t t~ g"),
+        "gu_ttxu": dict(G=(0, "vxxxxx", -1), I=(1, "ixxxxx", +1), O=(4, "oxxxxx", +1), pdg=[21, 2, 6, -6, 2],
+                        initial=[[21, 2], [21, 4], [21, 1], [21, 3]], colour_avg=24, process="g u > t t~ u"),
+        "gux_ttxux": dict(G=(0, "vxxxxx", -1), O=(1, "oxxxxx", -1), I=(4, "ixxxxx", -1), pdg=[21, -2, 6, -6, -2],
+                          initial=[[21, -2], [21, -4], [21, -1], [21, -3]], colour_avg=24, process="g u~ > t t~ u~"),
+    }[kind]
+    ext = {2: ("oxxxxx", +1, "mdl_MT"), 3: ("ixxxxx", -1, "mdl_MT")}
+    for key in "IOG":
+        leg, op, nsf = roles[key]
+        ext[leg] = (op, nsf, "ZERO")
+    calls = [{"op": ext[leg][0], "out": leg, "leg": leg, "mass": ext[leg][2], "nsf": ext[leg][1]} for leg in range(5)]
+    I_, O_, G_, T_, TB_ = roles["I"][0], roles["O"][0], roles["G"][0], 2, 3
+    top = dict(coup="GC_11", mass="mdl_MT", width="mdl_WT")
+    light = dict(coup="GC_11", mass="ZERO", width="ZERO")
+    calls += [
+        dict(op="FFV1P0_3", out=5, **{"in": [I_, O_]}, **light),              # gluon from the light line
+        dict(op="FFV1_1", out=6, **{"in": [T_, G_]}, **top),
+        dict(op="FFV1_0", amp=0, **{"in": [TB_, 6, 5]}, coup="GC_11"),        # gluon radiated off the t
+        dict(op="FFV1_2", out=6, **{"in": [TB_, G_]}, **top),
+        dict(op="FFV1_0", amp=1, **{"in": [6, T_, 5]}, coup="GC_11"),         # ... off the t~
+        dict(op="FFV1P0_3", out=7, **{"in": [TB_, T_]}, **light),             # gluon from the top line
+        dict(op="FFV1_2", out=6, **{"in": [I_, G_]}, **light),
+        dict(op="FFV1_0", amp=2, **{"in": [6, O_, 7]}, coup="GC_11"),         # ... off the I end of the light line
+        dict(op="FFV1_1", out=6, **{"in": [O_, G_]}, **light),
+        dict(op="FFV1_0", amp=3, **{"in": [I_, 6, 7]}, coup="GC_11"),         # ... off the O end
+        dict(op="VVV1_0", amp=4, **{"in": [7, 5, G_]}, coup="GC_10"),         # ... off the exchanged gluon
+    ]
+    # colour tensors [t, tb, O, I, a]: a fermion line contributes (T T ..)_{out end, in end}, radiation ordered from the
+    # outgoing end; the three-gluon vertex f^{123} in the order of the VVV1_0 arguments
+    T, f = _su3()
+    d3 = np.eye(3)
+    TT = np.einsum("aij,bjk->abik", T, T)
+    diagrams = [np.einsum("abik,bol->ikola", TT, T), np.einsum("baik,bol->ikola", TT, T),
+                np.einsum("bik,baol->ikola", T, TT), np.einsum("bik,abol->ikola", T, TT),
+                np.einsum("bca,bik,col->ikola", f, T, T)]
+    flows = [np.einsum("ail,ok->ikola", T, d3), np.einsum("il,aok->ikola", d3, T),
+             np.einsum("aik,ol->ikola", T, d3), np.einsum("ik,aol->ikola", d3, T)]
+    B = np.stack([b.reshape(-1) for b in flows], axis=1)
+    jamp = [[] for _ in flows]
+    for d_idx, tensor in enumerate(diagrams):
+        coef, *_ = np.linalg.lstsq(B, tensor.reshape(-1), rcond=None)
+        assert np.allclose(B @ coef, tensor.reshape(-1), atol=1e-12), "the colour flows do not span this diagram"
+        for k_, c in enumerate(coef):
+            re = Fraction(float(c.real)).limit_denominator(36)
+            im = Fraction(float(c.imag)).limit_denominator(36)
+            assert abs(complex(re, im) - c) < 1e-12
+            if re or im:
+                jamp[k_].append((d_idx, -float(re), -float(im)))   # overall sign as in generate_ir
+    gram = (B.conj().T @ B).real
+    rows = [[Fraction(float(v)).limit_denominator(36) for v in row] for row in gram]
+    assert np.allclose([[float(v) for v in row] for row in rows], gram, atol=1e-12) and np.allclose(gram, gram.T)
+    nums, dens = integer_rows(rows)
+    hel_states = [[-1, 1]] * 5
+    for leg, (op, nsf, _) in ext.items():
+        if (op == "ixxxxx") == (leg >= 2):   # antiparticle-like legs (incoming fermion, outgoing antifermion) listed reversed
+            hel_states[leg] = [1, -1]
+    return {
+        "name": "1_" + kind, "process": roles["process"] + " WEIGHTED<=3 @1",
+        "nexternal": 5, "ninitial": 2, "ndiags": 5, "ncomb": 32, "nwavefuncs": 8,
+        "helicities": [list(h) for h in itertools.product(*hel_states)],
+        "denominator": 4 * roles["colour_avg"],
+        "params": ["mdl_MT", "mdl_WT"], "couplings": ["GC_10", "GC_11"],
+        "initial_states": roles["initial"], "mirror_initial_states": True,
+        "pdg": roles["pdg"], "masses": ["ZERO", "ZERO", "mdl_MT", "mdl_MT", "ZERO"],
+        "calls": calls, "jamp": jamp, "color_num": nums, "color_denom": dens,
+    }
+
+
 # `p p > ...` processes of the command line: the subprocess libraries whose luminosity-weighted matrix elements
 # are summed (madflow_exec.py:444-455)
-MULTI_PROCESSES = {"p p > t t~": ["1_gg_ttx", "1_uux_ttx"]}
+MULTI_PROCESSES = {"p p > t t~": ["1_gg_ttx", "1_uux_ttx"],
+                   "p p > t t~ g": ["1_gg_ttxg", "1_uux_ttxg"],
+                   "p p > t t~ j": ["1_gg_ttxg", "1_gu_ttxu", "1_gux_ttxux", "1_uux_ttxg"]}
 
 
 def builtin_irs():
     """Processes compiled into the package besides the pinned g g > t t~."""
-    return [generate_ir(1), generate_ir(2), generate_ir(3), qqbar_ttx_ir()]
+    return [generate_ir(1), generate_ir(2), generate_ir(3), qqbar_ttx_ir()] + [light_line_ttxg_ir(k) for k in LIGHT_LINE_KINDS]

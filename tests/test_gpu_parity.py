@@ -778,3 +778,54 @@ def test_madflow_command_line_end_to_end(mf, toy_pdf, tmp_path):
             lib = mf.rt.process_lib(name)
             lib.set_variant("default")
             lib.set_integrand_blocks(0)
+
+
+# ------------------------------------------------------------------------------ p p > t t~ j
+def test_light_line_processes_and_pp_ttxj(mf, toy_pdf):
+    """q q~ > t t~ g, g q > t t~ q, g q~ > t t~ q~: per-event |M|^2 vs the oracle in both kernel flavours (1e-12), and
+    `p p > t t~ j` = the four subprocesses on the same events with their luminosities == separate calls == oracle."""
+    from madflow_b200 import procgen
+
+    pd, og = toy_pdf
+    x = np.random.default_rng(21).random((20_000, 14))
+    p, w, x1, x2 = ops.ramboflow(x, 5, 13e3, [MT, MT, 0.0], xfactor="converged")
+    lab = ops.boost_to_lab(p, x1, x2)
+    a_s = 0.09 + 0.05 * np.random.default_rng(22).random(lab.shape[0])
+    irs = {}
+    for kind in procgen.LIGHT_LINE_KINDS:
+        ir = irs["1_" + kind] = procgen.light_line_ttxg_ir(kind)
+        ref = omatrix.smatrix(ir, lab, sm_params(alpha_s=a_s))
+        m, model = mf.matrix.get_process("1_" + kind)
+        for variant in ("thread", "hp"):
+            _select(mf, m, variant)
+            out = cpu(m.smatrix(lab, *model.evaluate(a_s)))
+            assert np.max(np.abs(out / ref - 1)) < REL_ME, (kind, variant)
+        m.set_variant("default")
+    irs["1_gg_ttxg"] = procgen.generate_ir(1)
+    names = procgen.MULTI_PROCESSES["p p > t t~ j"]
+    nev = 30_000
+    parts = []
+    for name in names:
+        m, model = mf.matrix.get_process(name)
+        parts.append(mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT, 0.0], pt_cut=30.0, lab_frame=True,
+                                                 running=True, pdf=pd))
+    multi = mf.integrand.MultiProcessIntegrand(parts)
+    try:
+        v1 = mf.vegas.VegasFlow(14, nev, seed=4)
+        v1.compile(multi)
+        r1 = v1.run_iteration()
+        v2 = mf.vegas.VegasFlow(14, nev, seed=4)
+        v2.compile(multi.python_integrand())
+        r2 = v2.run_iteration()
+        assert abs(r1[0] / r2[0] - 1) < 1e-10 and abs(r1[1] / r2[1] - 1) < 1e-8
+        xss = [ovegas.make_cross_section(irs[nm], lambda a: sm_params(alpha_s=a), 13e3, [MT, MT, 0.0], pt_cut=30.0,
+                                         lab_frame=True, alpha_s_fn=og.alphasQ2, pdf=og) for nm in names]
+        ov = ovegas.Vegas(14, nev, seed=4)
+        ov.compile(lambda xr, **kw: sum(xs(xr) for xs in xss))
+        r0 = ov.run_iteration()
+        assert abs(r1[0] / r0[0] - 1) < 1e-10 and abs(r1[1] / r0[1] - 1) < 1e-8
+        np.testing.assert_allclose(cpu(v1.divisions), ov.grid, rtol=1e-6, atol=1e-11)
+    finally:
+        multi.release()
+        for fi in parts:
+            fi.matrix.set_variant("default")

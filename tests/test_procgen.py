@@ -179,3 +179,68 @@ def test_generated_cuda_source_on_host_qqbar_ttx():
     np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True), ref, rtol=1e-12)
     one = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, only_comb=6, hp=True)
     np.testing.assert_allclose(one, omatrix.matrix(ir, p, ir["helicities"][6], params), rtol=1e-11, atol=1e-300)
+
+
+@pytest.mark.parametrize("kind", procgen.LIGHT_LINE_KINDS)
+def test_light_line_five_point_processes(kind):
+    """q q~ > t t~ g, g q > t t~ q, g q~ > t t~ q~ (the subprocesses of `p p > t t~ j` besides g g > t t~ g): BRST
+    invariance of every colour flow for every helicity (Gamma_t = 0), the JAMP / colour-matrix form against the
+    explicit sum over the colours of all five external partons, crossing-independent colour data."""
+    ir = procgen.light_line_ttxg_ir(kind)
+    assert process_ir.validate(ir)
+    assert ir["ncomb"] == 32 and ir["ndiags"] == 5 and len(ir["jamp"]) == 4 and ir["mirror_initial_states"]
+    assert ir["denominator"] == (36 if kind == "uux_ttxg" else 96)
+    assert ir["color_num"] == [[12, 0, 4, 4], [0, 12, 4, 4], [4, 4, 12, 0], [4, 4, 0, 12]] and ir["color_denom"] == [1] * 4
+    p = _points(1, n=12, seed=2)
+    params = dict(sm_params(), mdl_WT=0.0)
+    gl = [c["leg"] for c in ir["calls"] if c["op"] == "vxxxxx"][0]
+    nonzero = 0
+    for hel in ir["helicities"]:
+        phys = np.max(np.abs(omatrix.matrix(ir, p, hel, params, EXACT, return_jamp=True)))
+        if phys == 0.0:
+            continue          # the light quark line conserves helicity
+        nonzero += 1
+        h = list(hel)
+        h[gl] = 4             # BRST polarisation (wavefunctions_flow.py:146-152)
+        assert np.max(np.abs(omatrix.matrix(ir, p, h, params, EXACT, return_jamp=True))) < 1e-11 * phys
+    assert nonzero == 16
+    # explicit colour sum: sum over (t, t~, O, I, a) of |sum_d tensor_d amp_d|^2 with the SU(3) matrices written out
+    T, f = procgen._su3()
+    TT = np.einsum("aij,bjk->abik", T, T)
+    tensors = [np.einsum("abik,bol->ikola", TT, T), np.einsum("baik,bol->ikola", TT, T),
+               np.einsum("bik,baol->ikola", T, TT), np.einsum("bik,abol->ikola", T, TT),
+               np.einsum("bca,bik,col->ikola", f, T, T)]
+    from oracle import aloha, helas
+
+    hel = next(h for h in ir["helicities"] if np.max(np.abs(omatrix.matrix(ir, p, h, sm_params(), EXACT, return_jamp=True))) > 0)
+    w, amp = {}, {}
+    ext = {"vxxxxx": helas.vxxxxx, "ixxxxx": helas.ixxxxx, "oxxxxx": helas.oxxxxx}
+    pr = sm_params()
+    val = lambda name: 0.0 if name == "ZERO" else pr[name]
+    for c in ir["calls"]:
+        if "leg" in c:
+            w[c["out"]] = ext[c["op"]](p[:, c["leg"]], val(c["mass"]), hel[c["leg"]], c["nsf"], EXACT)
+        elif "amp" in c:
+            amp[c["amp"]] = aloha.ROUTINES[c["op"]](*[w[i] for i in c["in"]], pr[c["coup"]])
+        else:
+            w[c["out"]] = aloha.ROUTINES[c["op"]](*[w[i] for i in c["in"]], pr[c["coup"]], val(c["mass"]), val(c["width"]))
+    full = sum(t[..., None] * amp[d] for d, t in enumerate(tensors))          # (3,3,3,3,8,nevt)
+    explicit = np.sum(np.abs(full) ** 2, axis=(0, 1, 2, 3, 4))
+    np.testing.assert_allclose(omatrix.matrix(ir, p, hel, pr, EXACT), explicit, rtol=1e-12)
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+@pytest.mark.parametrize("kind", procgen.LIGHT_LINE_KINDS)
+def test_generated_cuda_source_on_host_light_line(kind):
+    """The emitted code of the light-line five-point processes (both kernel flavours), executed on the CPU."""
+    import hostcheck as hc
+
+    ir = procgen.light_line_ttxg_ir(kind)
+    lib = hc.process(ir)
+    p = _points(1, n=60, seed=7)
+    a_s = 0.09 + 0.05 * np.random.default_rng(9).random(60)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    ref = omatrix.smatrix(ir, p, params)
+    np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF), ref, rtol=1e-12)
+    np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True), ref, rtol=1e-12)
