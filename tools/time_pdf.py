@@ -70,3 +70,10 @@ for name in ("1_gg_ttx", "1_uux_ttx"):
 multi = integrand.MultiProcessIntegrand(parts)
 run("p p > t t~ (g g + q q~, toy PDF)", multi, 10)
 multi.release()
+parts = []
+for name in ("1_gg_ttxg", "1_gu_ttxu", "1_gux_ttxux", "1_uux_ttxg"):
+    m, model = matrix.get_process(name)
+    parts.append(integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT, 0.0], pt_cut=30.0, running=True, pdf=pd))
+multi = integrand.MultiProcessIntegrand(parts)
+run("p p > t t~ j (4 subprocesses, toy PDF)", multi, 14)
+multi.release()
