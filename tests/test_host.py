@@ -250,3 +250,28 @@ def test_ctypes_structs_match_the_c_headers(tmp_path):
     for (st, fl), line in zip(fields.items(), lines):
         cls = getattr(rt, st)
         assert [int(v) for v in line.split()] == [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f in fl], st
+
+
+def test_pdf_set_variants(tmp_path):
+    """Sets with one subgrid, without an alpha_s table, malformed files: reader, table header, loud errors."""
+    from madflow_b200 import pdf as mpdf
+    from oracle import pdf as opdf
+
+    opdf.write_toy_set(str(tmp_path), name="OneGrid", q_knots=((1.65, 3.0, 10.0, 100.0, 1000.0),))
+    p = mpdf.mkPDF("OneGrid/0", dirname=str(tmp_path))
+    assert len(p.subgrids) == 1 and int(p._host_table[0]) == 1 and p.q2max == pytest.approx(1e6)
+    # strip the alpha_s table: the set still gives PDFs, alphasQ2 is refused, the table header says "no alpha_s"
+    info = tmp_path / "OneGrid" / "OneGrid.info"
+    info.write_text("\n".join(ln for ln in info.read_text().splitlines() if not ln.startswith("AlphaS_Qs") and not ln.startswith("AlphaS_Vals")))
+    q = mpdf.mkPDF("OneGrid/0", dirname=str(tmp_path))
+    assert not q.has_alphas and int(q._host_table[2]) == 0
+    with pytest.raises(mpdf.PDFError, match="AlphaS"):
+        q.alphasQ2([100.0])
+    # too few knots for the bicubic interpolation, and a file that is not lhagrid1
+    opdf.write_toy_set(str(tmp_path), name="Coarse", q_knots=((2.0, 10.0, 100.0),))
+    with pytest.raises(mpdf.PDFError, match="4 knots"):
+        mpdf.mkPDF("Coarse/0", dirname=str(tmp_path))
+    bad = tmp_path / "Coarse" / "Coarse_0000.dat"
+    bad.write_text("PdfType: central\nFormat: lhagrid2\n---\n")
+    with pytest.raises(mpdf.PDFError, match="lhagrid1"):
+        mpdf.mkPDF("Coarse/0", dirname=str(tmp_path))

@@ -140,3 +140,31 @@ def test_device_pdf_on_host(hc, tmp_path):
         p1, p2 = og.xfxQ2([a_ for a_, _ in ini], x1, qq), og.xfxQ2([b_ for _, b_ in ini], x2, qq)
         np.testing.assert_allclose(lumi, np.sum(p1 * p2, axis=1) / x1 / x2, rtol=1e-12)
         np.testing.assert_allclose(as_, og.alphasQ2(qq), rtol=1e-12)
+
+
+def test_device_pdf_single_subgrid_on_host(hc, tmp_path):
+    """csrc/pdf.cuh on a set with ONE subgrid (no thresholds) and a 5-knot alpha_s table without repeated Q."""
+    from madflow_b200 import pdf as mpdf
+    from oracle import pdf as opdf
+
+    opdf.write_toy_set(str(tmp_path), name="OneGrid", q_knots=((1.65, 3.0, 10.0, 100.0, 1000.0),))
+    info = tmp_path / "OneGrid" / "OneGrid.info"
+    lines = [ln for ln in info.read_text().splitlines() if not ln.startswith("AlphaS_")]
+    lines += ["AlphaS_Qs: [2.0, 5.0, 20.0, 91.1876, 1000.0]", "AlphaS_Vals: [0.30, 0.21, 0.15, 0.118, 0.088]"]
+    info.write_text("\n".join(lines) + "\n")
+    og = opdf.GridPDF.from_set("OneGrid/0", str(tmp_path))
+    T = np.ascontiguousarray(mpdf.mkPDF("OneGrid/0", dirname=str(tmp_path))._host_table)
+    lib = hc.core()
+    rng = np.random.default_rng(5)
+    n = 2000
+    x, q2 = 10 ** rng.uniform(-7.0, 0.0, n), 10 ** rng.uniform(0.3, 6.2, n)
+    cols = np.arange(11, dtype=np.int32)
+    out = np.empty((n, 11))
+    lib.hc_pdf_xfx(hc._dp(T), cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 11, hc._dp(x), hc._dp(q2), ctypes.c_longlong(n),
+                   hc._dp(out))
+    ref = og.xfxQ2(og.pids, x, q2)
+    assert np.max(np.abs(out - ref) / np.max(np.abs(ref), axis=0)) < 1e-13
+    qa = 10 ** rng.uniform(0.0, 7.0, n)
+    a = np.empty(n)
+    lib.hc_pdf_alphas(hc._dp(T), hc._dp(qa), ctypes.c_longlong(n), hc._dp(a))
+    np.testing.assert_allclose(a, og.alphasQ2(qa), rtol=1e-13)

@@ -244,3 +244,25 @@ def test_generated_cuda_source_on_host_light_line(kind):
     ref = omatrix.smatrix(ir, p, params)
     np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF), ref, rtol=1e-12)
     np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True), ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_colour_matrix_against_explicit_su3(irs, k):
+    """The colour matrix of g g > t t~ + k g (exact Fierz reduction in procgen._trace_value) against the Gram matrix
+    of the colour strings (T^a1 .. T^an)_{ij} built from the Gell-Mann matrices: an independent numerical check."""
+    T, _ = procgen._su3()
+    ir = irs[k]
+    ng = 2 + k
+    letters = "abcd"[:ng]
+    strings = []
+    for word in ir["color_basis"]:
+        # tensor [i, j, a_leg...] with the adjoint axes in the order of the gluon legs (0, 1, 4, 5, ...)
+        legs = sorted(word)
+        m = T[:, :, :]   # (a, i, j)
+        expr_in = ",".join(f"{letters[legs.index(g)]}{'ijklm'[q]}{'ijklm'[q + 1]}" for q, g in enumerate(word))
+        tensor = np.einsum(f"{expr_in}->i{'ijklm'[ng]}{letters}", *([m] * ng))
+        strings.append(tensor.reshape(-1))
+    B = np.stack(strings, axis=1)
+    gram = (B.conj().T @ B).real
+    cm = np.array(ir["color_num"], dtype=float) / np.array(ir["color_denom"], dtype=float)[:, None]
+    np.testing.assert_allclose(gram, cm, rtol=1e-12, atol=1e-12)
