@@ -32,6 +32,14 @@ def build_core(verbose=False):
     return out
 
 
+def build_named(name, verbose=False):
+    """Compile one process of the light-line generator (procgen_lines.PROCESSES) that is not built by default,
+    e.g. build_named("1_uux_ttxgg"); afterwards matrix.get_process(name) and the `madflow` command find it."""
+    from . import procgen_lines
+
+    return codegen.build_process(procgen_lines.process_ir(name), verbose=verbose)
+
+
 def build_all(verbose=False):
     libs = [build_core(verbose)]
     for ir in builtin_irs():
@@ -40,5 +48,6 @@ def build_all(verbose=False):
 
 
 if __name__ == "__main__":
-    for lib in build_all("-v" in sys.argv):
+    names = [a for a in sys.argv[1:] if not a.startswith("-")]
+    for lib in ([build_named(n, "-v" in sys.argv) for n in names] if names else build_all("-v" in sys.argv)):
         print(lib)

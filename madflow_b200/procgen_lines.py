@@ -1,0 +1,280 @@
+"""Tree-level QCD processes with the top line, ONE light quark line and up to two extra gluons, in any crossing:
+
+    q q~ > t t~ (g (g)),   g q > t t~ q (g),   g q~ > t t~ q~ (g),   g g > t t~ q q~,  ...
+
+the light-quark subprocesses of `p p > t t~ + jets` (reference: the subprocess loop of
+scripts/madflow_exec.py:444-455 over what MG5_aMC generates).  MG5 is absent, so like madflow_b200.procgen this
+module restates the Feynman rules in the conventions of the pinned ALOHA routines -- "parity unpinned" with respect
+to MG5's own output, checked by BRST invariance of every colour flow, against the hand-built five-point IRs of
+procgen.light_line_ttxg_ir and on the generated CUDA code executed on the host (tests/test_procgen.py).
+
+Differences to procgen.Generator (which stays untouched: the compiled g g > t t~ + n g libraries depend on it):
+  * colour is NUMERIC: every current carries the colour tensor of its sub-diagram (axes = the external legs below it
+    + its own open index), vertices contract explicit SU(3) generators / structure constants, and the amplitudes'
+    tensors are projected on the colour-flow basis  (T..)_{t I}(T..)_{O t~}  and  (T..)_{t t~}(T..)_{O I}  (I / O = the
+    fermion-flow-in / -out end of the light line) by least squares; the colour matrix is the basis' Gram matrix;
+  * every diagram is closed at the vertex of the external t~ (FFV1_0 amplitudes only), which enumerates each diagram
+    exactly once without the centroid bookkeeping; currents therefore grow to n-1 legs.
+"""
+import itertools
+import math
+from fractions import Fraction
+
+import numpy as np
+
+from .procgen import _partitions, _su3, integer_rows
+
+QUARTIC = {1: ((1, 2), (3, 4)), 3: ((1, 3), (2, 4)), 4: ((1, 4), (2, 3))}   # f^{e,p,q} f^{r,s,e}, UFO models/sm
+
+
+class Node:
+    __slots__ = ("kind", "legs", "op", "children", "ct", "uid", "topo")
+
+    def __init__(self, kind, legs, op, children, ct, topo):
+        self.kind, self.legs, self.op, self.children, self.ct, self.topo = kind, frozenset(legs), op, children, ct, topo
+        self.uid = None
+
+
+class LineGenerator:
+    """legs: list of roles per external leg, in MG5's leg order (incoming first):
+         "g"   gluon
+         "to"  t  (outgoing fermion: oxxxxx, the top string's row index)     "ti"  t~ (ixxxxx, its column index)
+         "lo"  fermion-flow-out end of the light line (incoming q~ or outgoing q: oxxxxx)
+         "li"  fermion-flow-in end (incoming q or outgoing q~: ixxxxx)"""
+
+    OPEN = 40   # einsum axis labels must stay below 52: legs 0..7, children's open indices 20+q, strings 30+
+
+    def __init__(self, roles, ninitial=2):
+        self.roles, self.n, self.ninitial = list(roles), len(roles), ninitial
+        assert sorted(r for r in roles if r != "g") == ["li", "lo", "ti", "to"], "one top line and one light line"
+        self.T, self.f = _su3()
+        self.leg_of = {r: k for k, r in enumerate(roles) if r != "g"}
+        self.dim = [8 if r == "g" else 3 for r in roles]
+        self._memo = {}
+        self.externals = {}
+        for leg, r in enumerate(roles):
+            kind = {"g": "g", "to": "o_t", "ti": "i_t", "lo": "o_l", "li": "i_l"}[r]
+            op = {"g": "vxxxxx", "to": "oxxxxx", "lo": "oxxxxx", "ti": "ixxxxx", "li": "ixxxxx"}[r]
+            self.externals[leg] = Node(kind, [leg], op, (), np.eye(self.dim[leg]), f"x{leg}")
+
+    # ---- colour tensors: axes = sorted external legs + the open index (last)
+    def _contract(self, vertex, vaxes, nodes, out_open):
+        """einsum of the vertex tensor (axes `vaxes`: internal labels 20+q for child q's open index, OPEN for the new one)
+        with the children's colour tensors."""
+        ops = [vertex, list(vaxes)]
+        legs = set()
+        for q, nd in enumerate(nodes):
+            ops += [nd.ct, sorted(nd.legs) + [20 + q]]
+            legs |= nd.legs
+        out = sorted(legs) + ([self.OPEN] if out_open else [])
+        return np.einsum(*ops, out)
+
+    def admissible(self, legs, kind):
+        s = set(legs)
+        has = {r: self.leg_of[r] in s for r in ("to", "ti", "lo", "li")}
+        top_whole, top_none = has["to"] and has["ti"], not has["to"] and not has["ti"]
+        light_whole, light_none = has["lo"] and has["li"], not has["lo"] and not has["li"]
+        if kind == "g":
+            return (top_whole or top_none) and (light_whole or light_none)
+        if kind in ("o_t", "i_t"):
+            return has["to" if kind == "o_t" else "ti"] and not has["ti" if kind == "o_t" else "to"] and (light_whole or light_none)
+        return has["lo" if kind == "o_l" else "li"] and not has["li" if kind == "o_l" else "lo"] and (top_whole or top_none)
+
+    def currents(self, legs, kind):
+        legs = frozenset(legs)
+        key = (legs, kind)
+        if key in self._memo:
+            return self._memo[key]
+        out = []
+        if len(legs) == 1:
+            (leg,) = legs
+            nd = self.externals[leg]
+            out = [nd] if nd.kind == kind else []
+        elif self.admissible(legs, kind):
+            s = tuple(sorted(legs))
+            T, f = self.T, self.f
+            if kind in ("o_t", "o_l"):       # FFV1_1(o, g): string (.. T^a)_{row, open}
+                for a, b in self._splits2(s):
+                    for o in self.currents(a, kind):
+                        for g in self.currents(b, "g"):
+                            ct = self._contract(T, [21, 20, self.OPEN], (o, g), True)
+                            out.append(Node(kind, legs, "FFV1_1", (o, g), ct, f"F1({o.topo},{g.topo})"))
+            elif kind in ("i_t", "i_l"):     # FFV1_2(i, g): string (T^a ..)_{open, column}
+                for a, b in self._splits2(s):
+                    for i in self.currents(a, kind):
+                        for g in self.currents(b, "g"):
+                            ct = self._contract(T, [21, self.OPEN, 20], (i, g), True)
+                            out.append(Node(kind, legs, "FFV1_2", (i, g), ct, f"F2({i.topo},{g.topo})"))
+            else:
+                for a, b in self._splits2(s):
+                    for line in ("t", "l"):  # FFV1P0_3(i, o): T^a_{o's open, i's open}
+                        for i in self.currents(a, "i_" + line):
+                            for o in self.currents(b, "o_" + line):
+                                ct = self._contract(T, [self.OPEN, 21, 20], (i, o), True)
+                                out.append(Node("g", legs, "FFV1P0_3", (i, o), ct, f"J({i.topo},{o.topo})"))
+                for part in _partitions(s, 2):
+                    for x in self.currents(part[0], "g"):
+                        for y in self.currents(part[1], "g"):   # VVV1P0_1(V2, V3) -> leg 1: f^{1,2,3}
+                            ct = self._contract(f, [self.OPEN, 20, 21], (x, y), True)
+                            out.append(Node("g", legs, "VVV1P0_1", (x, y), ct, f"V({x.topo},{y.topo})"))
+                for part in _partitions(s, 3):
+                    for x in self.currents(part[0], "g"):
+                        for y in self.currents(part[1], "g"):
+                            for z in self.currents(part[2], "g"):
+                                for kind4, ((p, q), (r, s_)) in QUARTIC.items():
+                                    lab = {1: self.OPEN, 2: 20, 3: 21, 4: 22}
+                                    ff = np.einsum("epq,rse->pqrs", f, f)
+                                    ct = self._contract(ff, [lab[p], lab[q], lab[r], lab[s_]], (x, y, z), True)
+                                    out.append(Node("g", legs, f"VVVV{kind4}P0_1", (x, y, z), ct,
+                                                    f"W{kind4}({x.topo},{y.topo},{z.topo})"))
+        self._memo[key] = out
+        return out
+
+    @staticmethod
+    def _splits2(s):
+        """ordered splits of s into two non-empty parts (both orders)"""
+        for part in _partitions(s, 2):
+            yield part[0], part[1]
+            yield part[1], part[0]
+
+    def amplitudes(self):
+        """FFV1_0(t~, o_t(A), g(B)) over all splits of the other legs: every diagram exactly once."""
+        tb = self.leg_of["ti"]
+        rest = tuple(l for l in range(self.n) if l != tb)
+        amps = []
+        for a, b in self._splits2(rest):
+            for o in self.currents(a, "o_t"):
+                for g in self.currents(b, "g"):
+                    # (o string)_{t, m} T^a_{m, m'} delta_{m', t~}
+                    ct = self._contract(self.T, [21, 20, 22], (o, g, self.externals[tb]), False)
+                    amps.append(("FFV1_0", (self.externals[tb], o, g), ct, f"A({o.topo},{g.topo})"))
+        return amps
+
+    # ---- colour flows
+    def colour_flows(self):
+        """Basis tensors over all external legs (sorted): type A (T^s1)_{t, I} (T^s2)_{O, t~}, type B (T^s1)_{t, t~} (T^s2)_{O, I}
+        over all ordered distributions of the gluons on the two strings."""
+        gl = [l for l, r in enumerate(self.roles) if r == "g"]
+        to, ti, lo, li = (self.leg_of[r] for r in ("to", "ti", "lo", "li"))
+        flows, names = [], []
+        for typ, (c1, c2) in (("A", (li, ti)), ("B", (ti, li))):
+            for j in range(len(gl) + 1):
+                for first in itertools.permutations(gl, j):
+                    rem = [g for g in gl if g not in first]
+                    for second in itertools.permutations(rem):
+                        t1 = self._string(first, to, c1)
+                        t2 = self._string(second, lo, c2)
+                        ops = [t1[0], t1[1], t2[0], t2[1], list(range(self.n))]
+                        flows.append(np.einsum(*ops).reshape(-1))
+                        names.append((typ, first, tuple(second)))
+        return np.stack(flows, axis=1), names
+
+    def _string(self, gluons, row, col):
+        """(T^{g1} T^{g2} ..)_{row, col} as (tensor, axis labels)"""
+        m, axes, cur = np.eye(3), [row, 30], 30
+        for q, g in enumerate(gluons):
+            m = np.einsum(m, axes, self.T, [g, cur, cur + 1], [a for a in axes if a != cur] + [g, cur + 1])
+            axes = [a for a in axes if a != cur] + [g, cur + 1]
+            cur += 1
+        m = np.einsum(m, axes, np.eye(3), [cur, col], [a for a in axes if a != cur] + [col])
+        return m, [a for a in axes if a != cur] + [col]
+
+
+def _rational(c, what):
+    re, im = Fraction(float(c.real)).limit_denominator(216), Fraction(float(c.imag)).limit_denominator(216)
+    assert abs(complex(re, im) - c) < 1e-10, f"{what}: {c} is not a small rational"
+    return re, im
+
+
+def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial=2):
+    """IR of the process whose external legs have the given roles (see LineGenerator)."""
+    gen = LineGenerator(roles, ninitial)
+    n = gen.n
+    amps = gen.amplitudes()
+    B, flow_names = gen.colour_flows()
+    # schedule: externals, then per amplitude the currents it needs (each wavefunction keeps its own slot)
+    calls, order = [], []
+    uid = itertools.count()
+
+    def visit(nd):
+        if nd.uid is not None:
+            return
+        for ch in nd.children:
+            visit(ch)
+        nd.uid = next(uid)
+        order.append(nd)
+
+    def emit(nd):
+        line = "t" if nd.kind.endswith("_t") else ("l" if nd.kind.endswith("_l") else "g")
+        mass, width = ("mdl_MT", "mdl_WT") if line == "t" else ("ZERO", "ZERO")
+        if not nd.children:
+            (leg,) = nd.legs
+            role = roles[leg]
+            incoming = leg < ninitial
+            nsf = {"g": -1 if incoming else 1, "to": 1, "ti": -1, "lo": -1 if incoming else 1, "li": 1 if incoming else -1}[role]
+            calls.append({"op": nd.op, "out": nd.uid, "leg": leg, "mass": mass if role in ("to", "ti") else "ZERO", "nsf": nsf})
+        else:
+            coup = {"FFV1": "GC_11", "VVV1": "GC_10", "VVVV": "GC_12"}[nd.op[:4]]
+            calls.append({"op": nd.op, "out": nd.uid, "in": [c.uid for c in nd.children], "coup": coup, "mass": mass, "width": width})
+
+    for leg in range(n):
+        visit(gen.externals[leg])
+    for nd in order:
+        emit(nd)
+    jamp = [[] for _ in flow_names]
+    for a_idx, (op, children, ct, topo) in enumerate(amps):
+        before = len(order)
+        for ch in children:
+            visit(ch)
+        for nd in order[before:]:
+            emit(nd)
+        calls.append({"op": op, "amp": a_idx, "in": [c.uid for c in children], "coup": "GC_11"})
+        coef, *_ = np.linalg.lstsq(B, ct.reshape(-1), rcond=None)
+        assert np.allclose(B @ coef, ct.reshape(-1), atol=1e-10), f"the colour flows do not span {topo}"
+        for k_, c in enumerate(coef):
+            re, im = _rational(c, topo)
+            if re or im:
+                jamp[k_].append((a_idx, -float(re), -float(im)))
+    gram = (B.conj().T @ B).real
+    rows = [[_rational(complex(v), "colour matrix")[0] for v in row] for row in gram]
+    nums, dens = integer_rows(rows)
+    hel_states = []
+    for leg, role in enumerate(roles):
+        anti_like = (role in ("ti", "li")) == (leg >= ninitial)   # incoming fermion / outgoing antifermion: listed reversed
+        hel_states.append([1, -1] if role != "g" and anti_like else [-1, 1])
+    colour_avg = 1
+    for leg in range(ninitial):
+        colour_avg *= 8 if roles[leg] == "g" else 3
+    nfinal_gluons = sum(1 for leg in range(ninitial, n) if roles[leg] == "g")
+    topos = {t.replace("W1", "W").replace("W3", "W").replace("W4", "W") for _, _, _, t in amps}
+    return {
+        "name": name, "process": process, "nexternal": n, "ninitial": ninitial, "ndiags": len(topos), "ncomb": 2**n,
+        "nwavefuncs": len(order), "helicities": [list(h) for h in itertools.product(*hel_states)],
+        "denominator": 4 * colour_avg * math.factorial(nfinal_gluons),
+        "params": ["mdl_MT", "mdl_WT"], "couplings": sorted({c["coup"] for c in calls if "coup" in c}),
+        "initial_states": initial_states, "mirror_initial_states": bool(mirror), "pdg": pdg,
+        "masses": ["mdl_MT" if r in ("to", "ti") else "ZERO" for r in roles],
+        "calls": calls, "jamp": jamp, "color_num": nums, "color_denom": dens,
+        "color_basis": [[t, list(a), list(b)] for t, a, b in flow_names],
+    }
+
+
+LIGHT = [2, 4, 1, 3]   # u, c, d, s in MG5's order
+
+PROCESSES = {   # name -> (roles, process string, pdg of the first flavour, initial states of all light flavours)
+    "1_uux_ttx": (["li", "lo", "to", "ti"], "u u~ > t t~", [2, -2, 6, -6], [[q, -q] for q in LIGHT]),
+    "1_uux_ttxg": (["li", "lo", "to", "ti", "g"], "u u~ > t t~ g", [2, -2, 6, -6, 21], [[q, -q] for q in LIGHT]),
+    "1_gu_ttxu": (["g", "li", "to", "ti", "lo"], "g u > t t~ u", [21, 2, 6, -6, 2], [[21, q] for q in LIGHT]),
+    "1_gux_ttxux": (["g", "lo", "to", "ti", "li"], "g u~ > t t~ u~", [21, -2, 6, -6, -2], [[21, -q] for q in LIGHT]),
+    "1_uux_ttxgg": (["li", "lo", "to", "ti", "g", "g"], "u u~ > t t~ g g", [2, -2, 6, -6, 21, 21], [[q, -q] for q in LIGHT]),
+    "1_gu_ttxug": (["g", "li", "to", "ti", "lo", "g"], "g u > t t~ u g", [21, 2, 6, -6, 2, 21], [[21, q] for q in LIGHT]),
+    "1_gux_ttxuxg": (["g", "lo", "to", "ti", "li", "g"], "g u~ > t t~ u~ g", [21, -2, 6, -6, -2, 21], [[21, -q] for q in LIGHT]),
+    "1_gg_ttxuux": (["g", "g", "to", "ti", "lo", "li"], "g g > t t~ u u~", [21, 21, 6, -6, 2, -2], [[21, 21]]),
+}
+
+
+def process_ir(name):
+    roles, proc, pdg, initial = PROCESSES[name]
+    mirror = initial != [[21, 21]]
+    n = len(roles)
+    return generate_ir(roles, name, f"{proc} WEIGHTED<={n - 2} @1", pdg, initial, mirror)

@@ -98,8 +98,11 @@ def madflow_main(args=None, quick_return=False):
     name = names[0]
     for nm in names:
         if nm not in mfm.available_processes():
+            from madflow_b200 import procgen_lines
+
+            hint = (f"; it can be generated: python -m madflow_b200.build {nm}" if nm in procgen_lines.PROCESSES else "")
             raise SystemExit(f"process '{args.madgraph_process}' ({nm}) has no compiled process library; available: "
-                             f"{mfm.available_processes()} (export it through the pyout plugin's CUDA backend)")
+                             f"{mfm.available_processes()} (export it through the pyout plugin's CUDA backend{hint})")
     output_path = args.output if args.output is not None else Path(tempfile.mkdtemp(prefix="mad_"))
     output_path.mkdir(parents=True, exist_ok=True)
     if args.dry_run:

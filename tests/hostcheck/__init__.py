@@ -36,11 +36,26 @@ def core():
     return ctypes.CDLL(out)
 
 
+_names = None
+
+
+def _builtin_names():
+    global _names
+    if _names is None:
+        from madflow_b200 import build
+
+        _names = {b["name"] for b in build.builtin_irs()}
+    return _names
+
+
 def process(ir):
     from madflow_b200 import codegen
 
     os.makedirs(codegen.GENDIR, exist_ok=True)
-    src = os.path.join(codegen.GENDIR, f"proc_{ir['name']}.cu")
+    os.makedirs(BUILD, exist_ok=True)
+    builtin = ir["name"] in _builtin_names()
+    # processes that are not compiled into the package keep their emitted source with the other test artefacts
+    src = os.path.join(codegen.GENDIR if builtin else BUILD, f"proc_{ir['name']}.cu")
     text = codegen.emit_process_source(ir)
     if not os.path.exists(src) or open(src).read() != text:
         open(src, "w").write(text)

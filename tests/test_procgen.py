@@ -266,3 +266,74 @@ def test_colour_matrix_against_explicit_su3(irs, k):
     gram = (B.conj().T @ B).real
     cm = np.array(ir["color_num"], dtype=float) / np.array(ir["color_denom"], dtype=float)[:, None]
     np.testing.assert_allclose(gram, cm, rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------ general light-line generator
+def test_line_generator_reproduces_the_hand_built_processes():
+    """procgen_lines (numeric colour, every diagram closed at the t~ vertex) against the hand-built q q~ > t t~ and
+    five-point IRs: different call lists, same |M|^2."""
+    from madflow_b200 import procgen_lines as pl
+
+    p4, p5 = _points(0, n=40, seed=4), _points(1, n=20, seed=4)
+    a = omatrix.smatrix(pl.process_ir("1_uux_ttx"), p4, sm_params(), EXACT)
+    np.testing.assert_allclose(a, omatrix.smatrix(procgen.qqbar_ttx_ir(), p4, sm_params(), EXACT), rtol=1e-13)
+    for kind in procgen.LIGHT_LINE_KINDS:
+        ir = pl.process_ir("1_" + kind)
+        assert process_ir.validate(ir) and ir["ndiags"] == 5 and len(ir["jamp"]) == 4
+        ref = procgen.light_line_ttxg_ir(kind)
+        assert ir["denominator"] == ref["denominator"] and ir["initial_states"] == ref["initial_states"]
+        np.testing.assert_allclose(omatrix.smatrix(ir, p5, sm_params(), EXACT), omatrix.smatrix(ref, p5, sm_params(), EXACT), rtol=2e-12)
+
+
+@pytest.mark.parametrize("name", ["1_uux_ttxgg", "1_gu_ttxug", "1_gux_ttxuxg", "1_gg_ttxuux"])
+def test_line_generator_six_point_processes(name):
+    """q q~ > t t~ g g and its crossings (36 diagrams, 12 colour flows): BRST invariance of every colour flow for every
+    gluon (Gamma_t = 0), Bose symmetry of identical gluons, positive |M|^2."""
+    from madflow_b200 import procgen_lines as pl
+
+    ir = pl.process_ir(name)
+    assert process_ir.validate(ir)
+    assert (ir["ndiags"], len(ir["jamp"]), ir["ncomb"]) == (36, 12, 64)
+    assert ir["denominator"] == {"1_uux_ttxgg": 72, "1_gu_ttxug": 96, "1_gux_ttxuxg": 96, "1_gg_ttxuux": 256}[name]
+    c = np.array(ir["color_num"], dtype=float) / np.array(ir["color_denom"], dtype=float)[:, None]
+    assert np.allclose(c, c.T) and np.min(np.linalg.eigvalsh(c)) > -1e-10
+    p = _points(2, n=5, seed=6)
+    params = dict(sm_params(), mdl_WT=0.0)
+    gluons = [cl["leg"] for cl in ir["calls"] if cl["op"] == "vxxxxx"]
+    checked = 0
+    for hel in ir["helicities"][::5]:
+        phys = np.max(np.abs(omatrix.matrix(ir, p, hel, params, EXACT, return_jamp=True)))
+        if phys == 0.0:
+            continue
+        checked += 1
+        for gl in gluons:
+            h = list(hel)
+            h[gl] = 4
+            assert np.max(np.abs(omatrix.matrix(ir, p, h, params, EXACT, return_jamp=True))) < 1e-11 * phys
+    assert checked >= 5
+    me = omatrix.smatrix(ir, p, sm_params())
+    assert np.all(me > 0)
+    same = [g_ for g_ in gluons if (g_ < 2) == (gluons[0] < 2)]
+    if len(same) == 2:   # two gluons on the same side of the process: exchanging their momenta changes nothing
+        q = p.copy()
+        q[:, same] = q[:, same[::-1]]
+        np.testing.assert_allclose(omatrix.smatrix(ir, q, sm_params()), me, rtol=1e-11)
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+@pytest.mark.parametrize("name", ["1_uux_ttxgg", "1_gg_ttxuux"])
+def test_generated_cuda_source_on_host_line_generator(name):
+    """The helicity-parallel tables and code emitted for a six-point light-line process, executed on the CPU."""
+    import hostcheck as hc
+    from madflow_b200 import procgen_lines as pl
+
+    ir = pl.process_ir(name)
+    lib = hc.process(ir)
+    p = _points(2, n=4, seed=8)
+    a_s = 0.09 + 0.05 * np.random.default_rng(3).random(4)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    ref = omatrix.smatrix(ir, p, params)
+    np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True), ref, rtol=1e-12)
+    one = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, only_comb=9, hp=True)
+    np.testing.assert_allclose(one, omatrix.matrix(ir, p, ir["helicities"][9], params), rtol=1e-11, atol=1e-300)
