@@ -46,7 +46,9 @@ class LineGenerator:
 
     def __init__(self, roles, ninitial=2):
         self.roles, self.n, self.ninitial = list(roles), len(roles), ninitial
-        assert sorted(r for r in roles if r != "g") == ["li", "lo", "ti", "to"], "one top line and one light line"
+        quarks = sorted(r for r in roles if r != "g")
+        assert quarks in (["li", "lo", "ti", "to"], ["ti", "to"]), "the top line and at most one light line"
+        self.has_light = "lo" in quarks
         self.T, self.f = _su3()
         self.leg_of = {r: k for k, r in enumerate(roles) if r != "g"}
         self.dim = [8 if r == "g" else 3 for r in roles]
@@ -71,7 +73,7 @@ class LineGenerator:
 
     def admissible(self, legs, kind):
         s = set(legs)
-        has = {r: self.leg_of[r] in s for r in ("to", "ti", "lo", "li")}
+        has = {r: self.leg_of.get(r, -1) in s for r in ("to", "ti", "lo", "li")}
         top_whole, top_none = has["to"] and has["ti"], not has["to"] and not has["ti"]
         light_whole, light_none = has["lo"] and has["li"], not has["lo"] and not has["li"]
         if kind == "g":
@@ -107,7 +109,7 @@ class LineGenerator:
                             out.append(Node(kind, legs, "FFV1_2", (i, g), ct, f"F2({i.topo},{g.topo})"))
             else:
                 for a, b in self._splits2(s):
-                    for line in ("t", "l"):  # FFV1P0_3(i, o): T^a_{o's open, i's open}
+                    for line in ("t", "l") if self.has_light else ("t",):  # FFV1P0_3(i, o): T^a_{o's open, i's open}
                         for i in self.currents(a, "i_" + line):
                             for o in self.currents(b, "o_" + line):
                                 ct = self._contract(T, [self.OPEN, 21, 20], (i, o), True)
@@ -155,8 +157,14 @@ class LineGenerator:
         """Basis tensors over all external legs (sorted): type A (T^s1)_{t, I} (T^s2)_{O, t~}, type B (T^s1)_{t, t~} (T^s2)_{O, I}
         over all ordered distributions of the gluons on the two strings."""
         gl = [l for l, r in enumerate(self.roles) if r == "g"]
-        to, ti, lo, li = (self.leg_of[r] for r in ("to", "ti", "lo", "li"))
         flows, names = [], []
+        if not self.has_light:   # one string (T^s)_{t, t~} per ordering of the gluons: the basis of procgen.generate_ir
+            for perm in itertools.permutations(gl):
+                t1 = self._string(perm, self.leg_of["to"], self.leg_of["ti"])
+                flows.append(np.einsum(t1[0], t1[1], list(range(self.n))).reshape(-1))
+                names.append(("T", perm, ()))
+            return np.stack(flows, axis=1), names
+        to, ti, lo, li = (self.leg_of[r] for r in ("to", "ti", "lo", "li"))
         for typ, (c1, c2) in (("A", (li, ti)), ("B", (ti, li))):
             for j in range(len(gl) + 1):
                 for first in itertools.permutations(gl, j):
@@ -242,6 +250,9 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
     for leg, role in enumerate(roles):
         anti_like = (role in ("ti", "li")) == (leg >= ninitial)   # incoming fermion / outgoing antifermion: listed reversed
         hel_states.append([1, -1] if role != "g" and anti_like else [-1, 1])
+    if np.linalg.matrix_rank(B) < B.shape[1]:
+        # dependent flows (large multiplicities at N = 3): least squares would pick an arbitrary decomposition
+        raise ValueError("the colour flows of this process are linearly dependent: use an exact colour algebra (procgen.generate_ir)")
     colour_avg = 1
     for leg in range(ninitial):
         colour_avg *= 8 if roles[leg] == "g" else 3
@@ -270,6 +281,10 @@ PROCESSES = {   # name -> (roles, process string, pdg of the first flavour, init
     "1_gu_ttxug": (["g", "li", "to", "ti", "lo", "g"], "g u > t t~ u g", [21, 2, 6, -6, 2, 21], [[21, q] for q in LIGHT]),
     "1_gux_ttxuxg": (["g", "lo", "to", "ti", "li", "g"], "g u~ > t t~ u~ g", [21, -2, 6, -6, -2, 21], [[21, -q] for q in LIGHT]),
     "1_gg_ttxuux": (["g", "g", "to", "ti", "lo", "li"], "g g > t t~ u u~", [21, 21, 6, -6, 2, -2], [[21, 21]]),
+    # no light line: an independent derivation of the built-in processes (cross-check only, see the tests)
+    "1_gg_ttx": (["g", "g", "to", "ti"], "g g > t t~", [21, 21, 6, -6], [[21, 21]]),
+    "1_gg_ttxg": (["g", "g", "to", "ti", "g"], "g g > t t~ g", [21, 21, 6, -6, 21], [[21, 21]]),
+    "1_gg_ttxgg": (["g", "g", "to", "ti", "g", "g"], "g g > t t~ g g", [21, 21, 6, -6, 21, 21], [[21, 21]]),
 }
 
 
