@@ -228,6 +228,14 @@ def hp_config(ir, key):
     return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 21, "SCRATCH": 512, "MINBLOCKS": 2}[key]
 
 
+def hp_chain(ir):
+    """Amplitude tiles that accumulate in the tensor-core accumulators: amplitudes of one batch with the same colour
+    signature (up to +-1, +-i) and the same split of the legs between pair object and wavefunction are stored ONCE
+    (1 = on; MADFLOW_B200_HP_CHAIN overrides).  Default off until measured on the GPU (plan for round 2)."""
+    env = os.environ.get("MADFLOW_B200_HP_CHAIN")
+    return int(env) if env else 0
+
+
 def hp_passes(ir):
     """Helicity passes: with more than 64 helicity combinations the amplitude / JAMP / colour phases run
     once per helicity of the last external leg (64 combinations per pass), so that the JAMPs of a pass
@@ -411,9 +419,33 @@ def emit_hp(ir):
 
     # tensor-core tiles: amplitude(variant of Q, variant of x) = sum_k Q_k x_k is an (nvq x 4)(4 x nvx)
     # complex product; one work item = 8 variants of Q (rows) x 8 variants of x (columns)
-    irow, trow, brow = [], [], []
+    irow, trow, brow, urow = [], [], [], []
     ncolor = len(ir["jamp"])
     NJ = -(-ncolor // NCG)
+    # rows of the amplitude buffer: one per amplitude, or (hp_chain) one per chain of amplitudes that the tile phase
+    # adds up: [(index into amp_rows, phase relative to the first member), ...]
+    chain_on = bool(hp_chain(ir)) and len(used) > HP_UNROLL_MAX_AMPS
+    PHASE_CODE = {1: 0, -1: 1, 1j: 2, -1j: 3}
+
+    def first_coef(k):
+        t = by_amp[amp_rows[k]["am"]["call"]["amp"]]
+        return complex(t[0][1], t[0][2])
+
+    batch_rows = []
+    for cur_pairs, cur_amps in batches:
+        rows, index = [], {}
+        for k in cur_amps:
+            r = amp_rows[k]
+            key = (r["sig"], wfs[r["x"]]["legs"], pairs[r["pair"]]["legs"]) if chain_on else ("own", k)
+            if key in index:
+                ph = first_coef(k) / first_coef(rows[index[key]][0][0])
+                if ph in PHASE_CODE:
+                    rows[index[key]].append((k, ph))
+                    continue
+                key = ("own", k)
+            index[key] = len(rows)
+            rows.append([(k, 1)])
+        batch_rows.append(rows)
     for p in range(NPASS):
         for bi, (cur_pairs, cur_amps) in enumerate(batches):
             ib, tb = len(irow), len(trow)
@@ -423,8 +455,9 @@ def emit_hp(ir):
                 for v in vrange(pr["legs"], pr["nv"], p):
                     iv = [pext(v, m) for m in masks]
                     irow.append(f"{{{pi}, {v}, {{{iv[0]}, {iv[1]}, {iv[2]}}}, 0}}")
-            for slot, k in enumerate(cur_amps):
-                r = amp_rows[k]
+            ub = len(urow)
+            for slot, row in enumerate(batch_rows[bi]):
+                r = amp_rows[row[0][0]]
                 xw, pr = wfs[r["x"]], pairs[r["pair"]]
                 assert not set(xw["legs"]) & set(pr["legs"]) and len(xw["legs"]) + len(pr["legs"]) == n
                 qr, xr = vrange(pr["legs"], pr["nv"], p), vrange(xw["legs"], xw["nv"], p)
@@ -433,9 +466,16 @@ def emit_hp(ir):
                         qv, xv = min(8, qr.stop - q0), min(8, xr.stop - x0)
                         rowh = [spread(pr["legs"], q0 + i) if i < qv else 0 for i in range(8)]
                         colh = [spread(xw["legs"], x0 + i) if i < xv else 0 for i in range(8)]
-                        trow.append(f"{{{pr['off']}, {xw['off'] + 2}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
-                                    f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
-            brow.append(f"{{{ib}, {len(irow)}, {tb}, {len(trow)}}}")
+                        urow.append(f"{{{len(trow)}u, {len(row)}u}}")
+                        for mi, (km, ph) in enumerate(row):   # the members of a chain: same geometry, own objects
+                            mx, mp = wfs[amp_rows[km]["x"]], pairs[amp_rows[km]["pair"]]
+                            assert (mx["legs"], mp["legs"], mx["nv"], mp["nv"]) == (xw["legs"], pr["legs"], xw["nv"], pr["nv"])
+                            # flags: 1 = adds to the tile before it, 2 = the next tile adds to it, phase code << 2
+                            flags = (1 if mi else 0) | (2 if mi + 1 < len(row) else 0) | PHASE_CODE[ph] << 2
+                            trow.append(f"{{{mp['off']}, {mx['off'] + 2}, {mp['nv']}, {mx['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, {flags}, "
+                                        f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
+            # with chains the warps take UNITS (chains of tiles, d_units) instead of single tiles
+            brow.append(f"{{{ib}, {len(irow)}, {ub if chain_on else tb}, {len(urow) if chain_on else len(trow)}}}")
     # JAMP code per (batch, colour group).  Amplitudes of a batch that feed the same colours of the group with the
     # same coefficients up to a common phase (+-1, +-i) are summed first and the sum is applied once:
     #   J_c += k_c (A_0 + p_1 A_1 + ...)   instead of   J_c += k_c A_0; J_c += k_c p_1 A_1; ...
@@ -452,7 +492,8 @@ def emit_hp(ir):
     for bi, (cur_pairs, cur_amps) in enumerate(batches):
         for cg in range(NCG):
             groups = {}   # signature within the colour group -> [(slot, phase relative to the group's first amplitude)]
-            for slot, k in enumerate(cur_amps):
+            for slot, row in enumerate(batch_rows[bi]):
+                k = row[0][0]   # the first member of a chain carries its JAMP coefficients
                 terms = [(j - cg * NJ, complex(re, im)) for j, re, im in by_amp[amp_rows[k]["am"]["call"]["amp"]] if j // NJ == cg]
                 if not terms:
                     continue
@@ -479,6 +520,8 @@ def emit_hp(ir):
     tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0, {0, 0, 0}, 0}", const=False)
     tables += "\n" + both("mf::HpTile", "tiles", max(len(trow), 1), ",\n  ".join(trow) if trow else "{0}", const=len(trow) * 32 <= 24576)
     tables += "\n" + both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}")
+    if chain_on:
+        tables += "\n" + both("uint2", "units", max(len(urow), 1), ", ".join(urow) if urow else "{0u, 0u}", const=False)
 
     A = ["    switch (cg) {"]
     for cg in range(NCG):
@@ -537,7 +580,7 @@ def emit_hp(ir):
         nbatch=len(batches), npairs=len(pairs), nitems_pair=len(irow), ntiles=len(trow), ncg=1 if unroll else NCG, jamp_terms=jamp_terms,
         npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
         colour_denom=float(den[0]),
-        nb=max(len(b_[1]) for b_ in batches) if batches else 1,
+        nb=max(len(rows) for rows in batch_rows) if batch_rows else 1, chain=1 if chain_on else 0,
         scratch=max(max((pairs[pi]["off"] + 4 * pairs[pi]["nv"] for pi in b_[0]), default=0) for b_ in batches) if batches else 0)
 
 
@@ -615,6 +658,10 @@ def emit_process_source(ir, block=None, minblocks=None):
 
     hp_tables, hp_jamp, hp_colour, hp_unrolled, hp = emit_hp(ir)
     hp_unroll = 'true' if hp['unroll'] else 'false'
+    # only emitted when chains are on, so that the default sources stay as they were measured
+    hp_chain_members = ("\n  // chains of tiles accumulate in the tensor-core accumulators (hp_mma_chains); the warps take units = chains\n"
+                        "  static constexpr bool HP_CHAIN = true;\n"
+                        "  MF_DEV static uint2 unit(int i) { return MF_TAB(units)[i]; }") if hp['chain'] else ""
     hp_scratch_n = 0 if hp['unroll'] else hp['scratch']
     hp_nb = 0 if hp['unroll'] else hp['nb']
     hp_ncg = hp['ncg']
@@ -680,7 +727,7 @@ struct Proc {{
   static constexpr int HP_THREADS = HP_E * HP_NHP * HP_NCG;                // threads per block
   // tile descriptors per warp and trip (x HP_E tiles in flight): 2 tiles in flight measured best -- more only adds
   // padded tiles at the end of a batch (g g > t t~ g g: 17.7e6 events/s with 2, 16.5e6 with 4, 14.5e6 with 8)
-  static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 2)) // hp_e)};
+  static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 2)) // hp_e)};{hp_chain_members}
   // colour contraction: 0 in-thread, 1 generated code over colour groups, 2 tensor cores, 3 CUDA-core loop
   // (2 and 3 read the block-symmetrised matrix d_cfsym and JAMP planes of HP_PLANE doubles per colour)
   static constexpr int HP_COLOUR = {hp['cmode']}, HP_NCP = {hp['ncp']}, HP_PLANE = HP_NHP + 4;

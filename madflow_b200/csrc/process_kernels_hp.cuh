@@ -32,6 +32,8 @@
 // of one component (current / pair-object phases) and the tensor-core fragment (2 variants x 4 components
 // per quarter warp).
 #pragma once
+#include <type_traits>
+
 #include "pipeline_kernels.cuh"
 #include "process_kernels.cuh"
 
@@ -94,9 +96,15 @@ struct alignas(16) HpTile {
   unsigned short qnv, xnv;      // component strides = helicity variants of the objects
   unsigned char q0, x0;         // first variant of the tile
   unsigned char qvalid, xvalid; // rows / columns in use (the rest is padding)
-  unsigned short slot, pad;
-  unsigned char rowh[8], colh[8];
+  unsigned short slot, flags;   // flags (chains of tiles, codegen.hp_chain): 1 = adds to the tile before it, 2 = the next
+  unsigned char rowh[8], colh[8];   // tile adds to it, bits 2-3 = phase of this member (1, -1, i, -i); 0 = a tile on its own
 };
+
+// does the process use chains of tiles (Proc::HP_CHAIN is only emitted when it does)
+template <class P, class = void>
+struct hp_has_chain : std::false_type {};
+template <class P>
+struct hp_has_chain<P, std::void_t<decltype(P::HP_CHAIN)>> : std::true_type {};
 
 struct HpBatch {   // one (helicity pass, batch): its pair-object work items and its tiles
   int item_begin, item_end, tile_begin, tile_end;
@@ -387,6 +395,66 @@ __device__ __forceinline__ void hp_mma_tiles(const HpTileWords (&tile)[NT], int 
     }
 }
 
+// Chains of tiles (codegen.hp_chain): a unit = `n` consecutive tile descriptors with the same geometry and destination
+// whose products  phase_m * Q_m . x_m  are added up in the tensor-core accumulators and stored once -- amplitudes of one
+// colour signature and one split of the legs reach the JAMP sums only through their sum.  NT units x E events in flight
+// per warp; `unit[t]` = (first tile, number of tiles), warp-uniform.
+template <class P, int NT>
+__device__ __forceinline__ void hp_mma_chains(const uint2 (&unit)[NT], int lane, unsigned evs) {
+  constexpr int E = P::HP_E;
+  constexpr unsigned EVB = P::HP_EVSTRIDE * 16u;
+  const int r = lane >> 2, k = lane & 3;
+  double cr0[NT][E], cr1[NT][E], ci0[NT][E], ci1[NT][E];
+  unsigned d0[NT], d1[NT];
+  bool s0[NT], s1[NT];
+  unsigned maxlen = 0;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    maxlen = unit[t].y > maxlen ? unit[t].y : maxlen;
+#pragma unroll
+    for (int e = 0; e < E; ++e) cr0[t][e] = cr1[t][e] = ci0[t][e] = ci1[t][e] = 0.0;
+  }
+#pragma unroll 1
+  for (unsigned m = 0; m < maxlen; ++m) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (m >= unit[t].y) continue;  // warp-uniform
+      const HpTileWords tw = hp_tile_words(P::tile(unit[t].x + m));
+      const uint4 w0 = tw.w0, w1 = tw.w1;
+      const int q = w0.x & 0xffff, x = w0.x >> 16, qnv = w0.y & 0xffff, xnv = w0.y >> 16;
+      const int q0 = w0.z & 0xff, x0 = (w0.z >> 8) & 0xff, qvalid = (w0.z >> 16) & 0xff, xvalid = w0.z >> 24;
+      const int slot = w0.w & 0xffff, ph = (w0.w >> 18) & 3;
+      const unsigned qi = evs + 16u * (P::HP_WFSIZE + q + hp_slot(k, qnv, (q0 + r) & (qnv - 1)));
+      const unsigned xi = evs + 16u * (x + hp_slot(k, xnv, (x0 + r) & (xnv - 1)));
+      if (m == 0) {  // destination and validity are the same for all members
+        const int hq = (((r & 4) ? w1.y : w1.x) >> (8 * (r & 3))) & 0xff;
+        const unsigned hc = (((k & 2) ? w1.w : w1.z) >> (16 * (k & 1))) & 0xffff;
+        d0[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::HP_NHP + hp_abuf_pos(hq | (hc & 0xff)));
+        d1[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::HP_NHP + hp_abuf_pos(hq | (hc >> 8)));
+        s0[t] = r < qvalid && 2 * k < xvalid, s1[t] = r < qvalid && 2 * k + 1 < xvalid;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const cxd qa = lds_cxd(qi + e * EVB), xb = lds_cxd(xi + e * EVB);
+        // phase * Q: 1 -> (re, im), -1 -> (-re, -im), i -> (-im, re), -i -> (im, -re)   (warp-uniform)
+        const double pre = (ph & 2) ? ((ph & 1) ? qa.im : -qa.im) : ((ph & 1) ? -qa.re : qa.re);
+        const double pim = (ph & 2) ? ((ph & 1) ? -qa.re : qa.re) : ((ph & 1) ? -qa.im : qa.im);
+        dmma_m8n8k4(cr0[t][e], cr1[t][e], pre, xb.re);
+        dmma_m8n8k4(ci0[t][e], ci1[t][e], pre, xb.im);
+        dmma_m8n8k4(cr0[t][e], cr1[t][e], -pim, xb.im);
+        dmma_m8n8k4(ci0[t][e], ci1[t][e], pim, xb.re);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (s0[t]) sts_cxd(d0[t] + e * EVB, cr0[t][e], ci0[t][e]);
+      if (s1[t]) sts_cxd(d1[t] + e * EVB, cr1[t][e], ci1[t][e]);
+    }
+}
+
 // the same tile on the CPU (tests/hostcheck): plain loops over its rows and columns
 template <class P>
 inline void hp_mma_tile_host(const HpTile* tp, const cxd* wf_e, const cxd* scratch_e, cxd* abuf_e) {
@@ -395,7 +463,11 @@ inline void hp_mma_tile_host(const HpTile* tp, const cxd* wf_e, const cxd* scrat
       cxd amp = mk(0.0, 0.0);
       for (int k = 0; k < 4; ++k)
         amp = fma_c(scratch_e[tp->q + hp_slot(k, tp->qnv, tp->q0 + r)], wf_e[tp->x + hp_slot(k, tp->xnv, tp->x0 + c)], amp);
-      abuf_e[tp->slot * P::HP_NHP + hp_abuf_pos(tp->rowh[r] | tp->colh[c])] = amp;
+      const int ph = (tp->flags >> 2) & 3;  // member of a chain: phase * amplitude, added to the members before it
+      if (ph & 2) amp = mul_i(amp);
+      if (ph & 1) amp = -amp;
+      cxd& dst = abuf_e[tp->slot * P::HP_NHP + hp_abuf_pos(tp->rowh[r] | tp->colh[c])];
+      dst = (tp->flags & 1) ? dst + amp : amp;
     }
 }
 
@@ -542,7 +614,19 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
         }
         __syncthreads();
         MF_PROF(2);
-        {
+        if constexpr (hp_has_chain<P>::value) {
+          // every warp takes MT units (chains of tiles) per trip; an index past the end repeats the batch's last unit
+          constexpr int NW = T / 32, MT = P::HP_TILES_IN_FLIGHT;
+          const unsigned evs = (unsigned)__cvta_generic_to_shared(ev);
+          const int last = bt.tile_end - 1;  // with chains the batch's tile range is its range of units
+#pragma unroll 1
+          for (int w = bt.tile_begin + warp; w < bt.tile_end; w += MT * NW) {
+            uint2 un[MT];
+#pragma unroll
+            for (int t = 0; t < MT; ++t) un[t] = P::unit(w + t * NW < last ? w + t * NW : last);
+            hp_mma_chains<P, MT>(un, lane, evs);
+          }
+        } else {
           // every warp takes MT tiles per trip; an index past the end repeats the batch's last tile
           // (same values stored twice) so that the trips stay straight-line
           constexpr int NW = T / 32, MT = P::HP_TILES_IN_FLIGHT;

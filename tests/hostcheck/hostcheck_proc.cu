@@ -74,12 +74,17 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
             mf::hp_pair<Proc>(Proc::pair_item(bt.item_begin + ii), cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS,
                               evarea.data() + ee * EVS + Proc::HP_WFSIZE);
           }
-          for (int w = 0; w < (bt.tile_end - bt.tile_begin) * E; ++w) {
-            const int ti = w / E, ee = w - ti * E;
-            cxd* a_e = evarea.data() + ee * EVS;
-            mf::hp_mma_tile_host<Proc>(Proc::tile(bt.tile_begin + ti), a_e, a_e + Proc::HP_WFSIZE,
-                                       a_e + Proc::HP_WFSIZE + Proc::HP_SCRATCH);
+          // the tiles of the batch in table order (with chains the batch holds a range of units = runs of tiles)
+          int tile_begin = bt.tile_begin, tile_end = bt.tile_end;
+          if constexpr (mf::hp_has_chain<Proc>::value) {
+            tile_begin = (int)Proc::unit(bt.tile_begin).x;
+            tile_end = (int)(Proc::unit(bt.tile_end - 1).x + Proc::unit(bt.tile_end - 1).y);
           }
+          for (int ee = 0; ee < E; ++ee)
+            for (int ti = tile_begin; ti < tile_end; ++ti) {
+              cxd* a_e = evarea.data() + ee * EVS;
+              mf::hp_mma_tile_host<Proc>(Proc::tile(ti), a_e, a_e + Proc::HP_WFSIZE, a_e + Proc::HP_WFSIZE + Proc::HP_SCRATCH);
+            }
           for (int t = 0; t < T; ++t) {
             const int e = t / (NCG * NHP), cg = (t / NHP) % NCG, h = t % NHP;
             cxd(&Jt)[NJ] = *reinterpret_cast<cxd(*)[NJ]>(&J[(size_t)t * NJ]);

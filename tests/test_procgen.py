@@ -353,3 +353,33 @@ def test_builtin_processes_against_the_independent_generator(irs, k):
     assert a["color_num"] == b["color_num"] and a["color_denom"] == b["color_denom"]
     p = _points(k, n=6, seed=12)
     np.testing.assert_allclose(omatrix.smatrix(a, p, sm_params(), EXACT), omatrix.smatrix(b, p, sm_params(), EXACT), rtol=1e-12)
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+@pytest.mark.parametrize("k", [2, 3])
+def test_tile_chains_on_host(irs, k, monkeypatch):
+    """MADFLOW_B200_HP_CHAIN=1 (default off until measured on the GPU): amplitudes of one colour signature and one
+    split of the legs are added up in the tile phase and stored once.  Tables, unit ranges, phases and the JAMP code
+    of that flavour executed on the CPU against the oracle; fewer rows of the amplitude buffer than amplitudes."""
+    import hostcheck as hc
+
+    monkeypatch.setenv("MADFLOW_B200_HP_CHAIN", "1")
+    ir = process_ir.clone(irs[k])
+    ir["name"] += "_chain"
+    info = codegen.emit_hp(ir)[4]
+    assert info["chain"] == 1
+    monkeypatch.delenv("MADFLOW_B200_HP_CHAIN")
+    plain = codegen.emit_hp(irs[k])[4]
+    assert plain["chain"] == 0 and info["ntiles"] == plain["ntiles"] and info["jamp_terms"] < plain["jamp_terms"]
+    monkeypatch.setenv("MADFLOW_B200_HP_CHAIN", "1")
+    lib = hc.process(ir)
+    npts = 2 if k == 3 else 5
+    p = _points(k, n=npts, seed=13)
+    a_s = 0.09 + 0.05 * np.random.default_rng(4).random(npts)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    ref = omatrix.smatrix(ir, p, params)
+    np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True), ref, rtol=1e-12)
+    one = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, only_comb=11, hp=True)
+    # a single (possibly helicity-suppressed) row: accurate relative to the size of the whole sum
+    assert np.max(np.abs(one - omatrix.matrix(ir, p, ir["helicities"][11], params)) / (ref * ir["denominator"])) < 1e-13
