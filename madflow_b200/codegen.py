@@ -231,7 +231,9 @@ def hp_config(ir, key):
 def hp_chain(ir):
     """Amplitude tiles that accumulate in the tensor-core accumulators: amplitudes of one batch with the same colour
     signature (up to +-1, +-i) and the same split of the legs between pair object and wavefunction are stored ONCE
-    (1 = on; MADFLOW_B200_HP_CHAIN overrides).  Default off until measured on the GPU (plan for round 2)."""
+    (1 = on; MADFLOW_B200_HP_CHAIN overrides).  The batches already keep pair objects of one kind and colour signature
+    together, which is what puts chain members into one batch (ordering by legs first was tried: not better).
+    Default off until measured on the GPU (plan for round 2)."""
     env = os.environ.get("MADFLOW_B200_HP_CHAIN")
     return int(env) if env else 0
 
@@ -581,6 +583,7 @@ def emit_hp(ir):
         npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
         colour_denom=float(den[0]),
         nb=max(len(rows) for rows in batch_rows) if batch_rows else 1, chain=1 if chain_on else 0,
+        nrows=sum(len(rows) for rows in batch_rows),
         scratch=max(max((pairs[pi]["off"] + 4 * pairs[pi]["nv"] for pi in b_[0]), default=0) for b_ in batches) if batches else 0)
 
 
