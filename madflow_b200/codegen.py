@@ -387,12 +387,23 @@ def emit_hp(ir):
         c0 = complex(t[0][1], t[0][2])
         r["sig"] = sig_id.setdefault(tuple((j, complex(re, im) / c0) for j, re, im in sorted(t)), len(sig_id))
     # ... and within a kind, pair objects whose amplitudes share a colour signature next to each other (see the JAMP code)
+    chain_rows = hp_chain(ir) and len(used) > HP_UNROLL_MAX_AMPS   # rows of the amplitude buffer = chains, not amplitudes
+
+    def row_key(k):
+        r = amp_rows[k]
+        return (r["sig"], wfs[r["x"]]["legs"], pairs[r["pair"]]["legs"])
+
+    cur_keys = set()
     for pi in sorted(by_pair, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], min(amp_rows[k]["sig"] for k in by_pair[q]), q)):
         need = 4 * pairs[pi]["nv"]
         assert need <= scratch and len(by_pair[pi]) <= NB
-        if fill + need > scratch or len(cur_amps) + len(by_pair[pi]) > NB:
+        new_keys = {row_key(k) for k in by_pair[pi]}
+        rows_after = len(cur_keys | new_keys) + 4 if chain_rows else len(cur_amps) + len(by_pair[pi])   # + 4: phases that do not chain
+        if fill + need > scratch or rows_after > NB:
             batches.append((cur_pairs, cur_amps))
             cur_pairs, cur_amps, fill = [], [], 0
+            cur_keys = set()
+        cur_keys |= new_keys
         pairs[pi]["off"] = fill
         fill += need
         cur_pairs.append(pi)
