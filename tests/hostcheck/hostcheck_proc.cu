@@ -5,6 +5,19 @@
 
 #include MF_PROC_SOURCE
 
+// range of tile descriptors of a batch (with chains of tiles the batch holds a range of units = runs of tiles);
+// templates so that Proc::unit is only named for processes that have it
+template <class P>
+static int hc_tile_begin(const mf::HpBatch& bt) {
+  if constexpr (mf::hp_has_chain<P>::value) return (int)P::unit(bt.tile_begin).x;
+  else return bt.tile_begin;
+}
+template <class P>
+static int hc_tile_end(const mf::HpBatch& bt) {
+  if constexpr (mf::hp_has_chain<P>::value) return (int)(P::unit(bt.tile_end - 1).x + P::unit(bt.tile_end - 1).y);
+  else return bt.tile_end;
+}
+
 extern "C" int hostcheck_smatrix(const double* p, long long nevt, const double* par, const double* coup,
                                  long long coup_stride, double sqh, int only_comb, double* out) {
   for (long long ev = 0; ev < nevt; ++ev) {
@@ -75,11 +88,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
                               evarea.data() + ee * EVS + Proc::HP_WFSIZE);
           }
           // the tiles of the batch in table order (with chains the batch holds a range of units = runs of tiles)
-          int tile_begin = bt.tile_begin, tile_end = bt.tile_end;
-          if constexpr (mf::hp_has_chain<Proc>::value) {
-            tile_begin = (int)Proc::unit(bt.tile_begin).x;
-            tile_end = (int)(Proc::unit(bt.tile_end - 1).x + Proc::unit(bt.tile_end - 1).y);
-          }
+          const int tile_begin = hc_tile_begin<Proc>(bt), tile_end = hc_tile_end<Proc>(bt);
           for (int ee = 0; ee < E; ++ee)
             for (int ti = tile_begin; ti < tile_end; ++ti) {
               cxd* a_e = evarea.data() + ee * EVS;
