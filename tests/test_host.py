@@ -277,3 +277,27 @@ def test_pdf_set_variants(tmp_path):
     bad.write_text("PdfType: central\nFormat: lhagrid2\n---\n")
     with pytest.raises(mpdf.PDFError, match="lhagrid1"):
         mpdf.mkPDF("Coarse/0", dirname=str(tmp_path))
+
+
+def test_on_demand_process_library(tmp_path):
+    """A light-line six-point process of procgen_lines compiles for sm_100a into a loadable C-ABI library with the
+    right metadata (no kernel is launched here; the library is built outside the package tree)."""
+    import shutil
+
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    from madflow_b200 import _runtime as rt
+    from madflow_b200 import procgen_lines
+
+    ir = procgen_lines.process_ir("1_gu_ttxug")
+    src = tmp_path / "proc.cu"
+    src.write_text(codegen.emit_process_source(ir))
+    out = codegen.compile_source(str(src), str(tmp_path / "libmfp_1_gu_ttxug.so"))
+    lib = rt.ProcessLib(out)
+    assert lib.name == "1_gu_ttxug"
+    assert (lib.info.nexternal, lib.info.ncomb, lib.info.ncolor, lib.info.ndiags, lib.info.ndim) == (6, 64, 12, 36, 18)
+    assert lib.info.denominator == 96.0 and lib.info.flops_per_event == codegen.flops_per_event(ir)
+    assert lib.coupling_names == ["GC_10", "GC_11", "GC_12"] and lib.helicities == ir["helicities"]
+    assert lib.variant == "hp"      # 96 calls: only the helicity-parallel flavour is compiled
+    for n in _declared("madflow_b200_process.h"):
+        assert hasattr(lib.lib, n), n
