@@ -13,8 +13,9 @@ Differences to procgen.Generator (which stays untouched: the compiled g g > t t~
     + its own open index), vertices contract explicit SU(3) generators / structure constants, and the amplitudes'
     tensors are projected on the colour-flow basis  (T..)_{t I}(T..)_{O t~}  and  (T..)_{t t~}(T..)_{O I}  (I / O = the
     fermion-flow-in / -out end of the light line) by least squares; the colour matrix is the basis' Gram matrix;
-  * every diagram is closed at the vertex of the external t~ (FFV1_0 amplitudes only), which enumerates each diagram
-    exactly once without the centroid bookkeeping; currents therefore grow to n-1 legs.
+  * two organisations of the same amplitude: every diagram closed at its centroid vertex (default: currents of at most
+    n/2 legs, what the helicity-parallel kernels want) or at the vertex of the external t~ (FFV1_0 amplitudes only,
+    currents of up to n-1 legs) -- they must agree, which the tests use.
 """
 import itertools
 import math
@@ -139,8 +140,13 @@ class LineGenerator:
             yield part[0], part[1]
             yield part[1], part[0]
 
-    def amplitudes(self):
-        """FFV1_0(t~, o_t(A), g(B)) over all splits of the other legs: every diagram exactly once."""
+    def amplitudes(self, root="tbar"):
+        """root="tbar": FFV1_0(t~, o_t(A), g(B)) over all splits of the other legs -- every diagram exactly once, currents
+        of up to n-1 legs.  root="centroid": every diagram closed at its centroid vertex (no branch with more than n/2
+        legs; when the centroid is an edge, the end whose heavy branch holds leg 0), as procgen.Generator does: currents of
+        at most n/2 legs, FFV1_0 / VVV1_0 / VVVV_0 amplitudes."""
+        if root == "centroid":
+            return self._amplitudes_centroid()
         tb = self.leg_of["ti"]
         rest = tuple(l for l in range(self.n) if l != tb)
         amps = []
@@ -150,6 +156,47 @@ class LineGenerator:
                     # (o string)_{t, m} T^a_{m, m'} delta_{m', t~}
                     ct = self._contract(self.T, [21, 20, 22], (o, g, self.externals[tb]), False)
                     amps.append(("FFV1_0", (self.externals[tb], o, g), ct, f"A({o.topo},{g.topo})"))
+        return amps
+
+    def _amplitudes_centroid(self):
+        n, half = self.n, self.n // 2
+        all_legs = tuple(range(n))
+        lines = [("t", "to", "ti")] + ([("l", "lo", "li")] if self.has_light else [])
+        amps = []
+
+        def allowed(parts):
+            sizes = [len(p_) for p_ in parts]
+            if max(sizes) > half:
+                return False
+            if 2 * max(sizes) == n:   # the centroid is an edge: keep the end whose heavy branch holds leg 0
+                return 0 in parts[sizes.index(max(sizes))]
+            return True
+
+        ff = {k4: np.einsum("epq,rse->pqrs", self.f, self.f) for k4 in QUARTIC}
+        for nparts in (3, 4):
+            for parts in _partitions(all_legs, nparts):
+                if not allowed(parts):
+                    continue
+                if all(self.admissible(p_, "g") for p_ in parts):
+                    for combo in itertools.product(*[self.currents(p_, "g") for p_ in parts]):
+                        if nparts == 3:
+                            ct = self._contract(self.f, [20, 21, 22], combo, False)
+                            amps.append(("VVV1_0", combo, ct, "A3(" + ",".join(x.topo for x in combo) + ")"))
+                        else:
+                            for k4, ((p, q), (r, s_)) in QUARTIC.items():
+                                lab = {1: 20, 2: 21, 3: 22, 4: 23}
+                                ct = self._contract(ff[k4], [lab[p], lab[q], lab[r], lab[s_]], combo, False)
+                                amps.append((f"VVVV{k4}_0", combo, ct, "A4(" + ",".join(x.topo for x in combo) + ")"))   # one diagram, 3 structures
+                elif nparts == 3:
+                    for line, ro, ri in lines:   # the vertex sits on this quark line: branches (i side, o side, gluon)
+                        for pi_, po_, pg_ in itertools.permutations(parts):
+                            if not (self.admissible(pi_, "i_" + line) and self.admissible(po_, "o_" + line) and self.admissible(pg_, "g")):
+                                continue
+                            for i in self.currents(pi_, "i_" + line):
+                                for o in self.currents(po_, "o_" + line):
+                                    for g in self.currents(pg_, "g"):
+                                        ct = self._contract(self.T, [22, 21, 20], (i, o, g), False)   # T^a_{o's open, i's open}
+                                        amps.append(("FFV1_0", (i, o, g), ct, f"A({i.topo},{o.topo},{g.topo})"))
         return amps
 
     # ---- colour flows
@@ -194,11 +241,11 @@ def _rational(c, what):
     return re, im
 
 
-def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial=2):
+def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial=2, root="centroid"):
     """IR of the process whose external legs have the given roles (see LineGenerator)."""
     gen = LineGenerator(roles, ninitial)
     n = gen.n
-    amps = gen.amplitudes()
+    amps = gen.amplitudes(root)
     B, flow_names = gen.colour_flows()
     # schedule: externals, then per amplitude the currents it needs (each wavefunction keeps its own slot)
     calls, order = [], []
@@ -236,7 +283,8 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
             visit(ch)
         for nd in order[before:]:
             emit(nd)
-        calls.append({"op": op, "amp": a_idx, "in": [c.uid for c in children], "coup": "GC_11"})
+        calls.append({"op": op, "amp": a_idx, "in": [c.uid for c in children],
+                      "coup": {"FFV1": "GC_11", "VVV1": "GC_10", "VVVV": "GC_12"}[op[:4]]})
         coef, *_ = np.linalg.lstsq(B, ct.reshape(-1), rcond=None)
         assert np.allclose(B @ coef, ct.reshape(-1), atol=1e-10), f"the colour flows do not span {topo}"
         for k_, c in enumerate(coef):
@@ -288,8 +336,8 @@ PROCESSES = {   # name -> (roles, process string, pdg of the first flavour, init
 }
 
 
-def process_ir(name):
+def process_ir(name, root="centroid"):
     roles, proc, pdg, initial = PROCESSES[name]
     mirror = initial != [[21, 21]]
     n = len(roles)
-    return generate_ir(roles, name, f"{proc} WEIGHTED<={n - 2} @1", pdg, initial, mirror)
+    return generate_ir(roles, name, f"{proc} WEIGHTED<={n - 2} @1", pdg, initial, mirror, root=root)

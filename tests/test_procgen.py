@@ -313,6 +313,10 @@ def test_line_generator_six_point_processes(name):
     assert checked >= 5
     me = omatrix.smatrix(ir, p, sm_params())
     assert np.all(me > 0)
+    # the other organisation of the same amplitude (every diagram closed at the t~ vertex): same |M|^2, more work
+    alt = pl.process_ir(name, root="tbar")
+    assert alt["ndiags"] == 36 and codegen.flops_per_event(alt) > codegen.flops_per_event(ir)
+    np.testing.assert_allclose(omatrix.smatrix(alt, p, sm_params()), me, rtol=1e-11)
     same = [g_ for g_ in gluons if (g_ < 2) == (gluons[0] < 2)]
     if len(same) == 2:   # two gluons on the same side of the process: exchanging their momenta changes nothing
         q = p.copy()
@@ -347,7 +351,7 @@ def test_builtin_processes_against_the_independent_generator(irs, k):
     |M|^2 with the reference's top width."""
     from madflow_b200 import procgen_lines as pl
 
-    a, b = pl.process_ir("1_gg_ttx" + "g" * k), irs[k]
+    a, b = pl.process_ir("1_gg_ttx" + "g" * k, root="tbar"), irs[k]
     assert a["ndiags"] == b["ndiags"] and a["denominator"] == b["denominator"]
     assert len([c for c in a["calls"] if "amp" in c]) == len([c for c in b["calls"] if "amp" in c])
     assert a["color_num"] == b["color_num"] and a["color_denom"] == b["color_denom"]
