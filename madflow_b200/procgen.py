@@ -674,9 +674,11 @@ MULTI_PROCESSES = {"p p > t t~": ["1_gg_ttx", "1_uux_ttx"],
                    "p p > t t~ g": ["1_gg_ttxg", "1_uux_ttxg"],
                    "p p > t t~ j": ["1_gg_ttxg", "1_gu_ttxu", "1_gux_ttxux", "1_uux_ttxg"],
                    # the light-line six-point libraries come from procgen_lines and are built on demand
-                   # (python -m madflow_b200.build 1_uux_ttxgg 1_gu_ttxug 1_gux_ttxuxg 1_gg_ttxuux); the four-quark
-                   # subprocesses of p p > t t~ j j (q q > t t~ q q, ...) are not generated
-                   "p p > t t~ g g": ["1_gg_ttxgg", "1_uux_ttxgg"]}
+                   # (python -m madflow_b200.build 1_uux_ttxgg 1_gu_ttxug ...), the four-quark ones included
+                   "p p > t t~ g g": ["1_gg_ttxgg", "1_uux_ttxgg"],
+                   "p p > t t~ j j": ["1_gg_ttxgg", "1_gg_ttxuux", "1_gu_ttxug", "1_gux_ttxuxg", "1_uux_ttxgg", "1_uu_ttxuu",
+                                      "1_ud_ttxud", "1_uxux_ttxuxux", "1_uxdx_ttxuxdx", "1_uux_ttxuux", "1_uux_ttxddx",
+                                      "1_udx_ttxudx"]}
 
 
 def builtin_irs():

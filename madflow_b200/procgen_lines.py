@@ -1,6 +1,7 @@
-"""Tree-level QCD processes with the top line, ONE light quark line and up to two extra gluons, in any crossing:
+"""Tree-level QCD processes with the top line, up to TWO light quark lines and extra gluons, in any crossing:
 
-    q q~ > t t~ (g (g)),   g q > t t~ q (g),   g q~ > t t~ q~ (g),   g g > t t~ q q~,  ...
+    q q~ > t t~ (g (g)),   g q > t t~ q (g),   g q~ > t t~ q~ (g),   g g > t t~ q q~,
+    q q' > t t~ q q',   q q > t t~ q q,   q q~ > t t~ q' q~',   q q~ > t t~ q q~,  ...
 
 the light-quark subprocesses of `p p > t t~ + jets` (reference: the subprocess loop of
 scripts/madflow_exec.py:444-455 over what MG5_aMC generates).  MG5 is absent, so like madflow_b200.procgen this
@@ -48,16 +49,18 @@ class LineGenerator:
     def __init__(self, roles, ninitial=2):
         self.roles, self.n, self.ninitial = list(roles), len(roles), ninitial
         quarks = sorted(r for r in roles if r != "g")
-        assert quarks in (["li", "lo", "ti", "to"], ["ti", "to"]), "the top line and at most one light line"
-        self.has_light = "lo" in quarks
+        self.lines = [tag for tag in "tlm" if tag + "o" in quarks]   # t = top, l / m = light lines of different flavour
+        assert "t" in self.lines and quarks == sorted(tag + end for tag in self.lines for end in "oi"), \
+            "the top line and up to two light lines, each with both ends"
+        self.has_light = len(self.lines) > 1
         self.T, self.f = _su3()
         self.leg_of = {r: k for k, r in enumerate(roles) if r != "g"}
         self.dim = [8 if r == "g" else 3 for r in roles]
         self._memo = {}
         self.externals = {}
         for leg, r in enumerate(roles):
-            kind = {"g": "g", "to": "o_t", "ti": "i_t", "lo": "o_l", "li": "i_l"}[r]
-            op = {"g": "vxxxxx", "to": "oxxxxx", "lo": "oxxxxx", "ti": "ixxxxx", "li": "ixxxxx"}[r]
+            kind = "g" if r == "g" else f"{r[1]}_{r[0]}"          # "to" -> "o_t", "li" -> "i_l"
+            op = "vxxxxx" if r == "g" else ("oxxxxx" if r[1] == "o" else "ixxxxx")
             self.externals[leg] = Node(kind, [leg], op, (), np.eye(self.dim[leg]), f"x{leg}")
 
     # ---- colour tensors: axes = sorted external legs + the open index (last)
@@ -73,15 +76,17 @@ class LineGenerator:
         return np.einsum(*ops, out)
 
     def admissible(self, legs, kind):
+        """a gluon current holds every quark line entirely or not at all; a quark current of line X holds exactly its own
+        end of X, and every other line entirely or not at all"""
         s = set(legs)
-        has = {r: self.leg_of.get(r, -1) in s for r in ("to", "ti", "lo", "li")}
-        top_whole, top_none = has["to"] and has["ti"], not has["to"] and not has["ti"]
-        light_whole, light_none = has["lo"] and has["li"], not has["lo"] and not has["li"]
-        if kind == "g":
-            return (top_whole or top_none) and (light_whole or light_none)
-        if kind in ("o_t", "i_t"):
-            return has["to" if kind == "o_t" else "ti"] and not has["ti" if kind == "o_t" else "to"] and (light_whole or light_none)
-        return has["lo" if kind == "o_l" else "li"] and not has["li" if kind == "o_l" else "lo"] and (top_whole or top_none)
+        for tag in self.lines:
+            has_o, has_i = self.leg_of[tag + "o"] in s, self.leg_of[tag + "i"] in s
+            if kind != "g" and kind[2] == tag:
+                if (has_o, has_i) != ((True, False) if kind[0] == "o" else (False, True)):
+                    return False
+            elif has_o != has_i:
+                return False
+        return True
 
     def currents(self, legs, kind):
         legs = frozenset(legs)
@@ -96,13 +101,13 @@ class LineGenerator:
         elif self.admissible(legs, kind):
             s = tuple(sorted(legs))
             T, f = self.T, self.f
-            if kind in ("o_t", "o_l"):       # FFV1_1(o, g): string (.. T^a)_{row, open}
+            if kind[0] == "o":               # FFV1_1(o, g): string (.. T^a)_{row, open}
                 for a, b in self._splits2(s):
                     for o in self.currents(a, kind):
                         for g in self.currents(b, "g"):
                             ct = self._contract(T, [21, 20, self.OPEN], (o, g), True)
                             out.append(Node(kind, legs, "FFV1_1", (o, g), ct, f"F1({o.topo},{g.topo})"))
-            elif kind in ("i_t", "i_l"):     # FFV1_2(i, g): string (T^a ..)_{open, column}
+            elif kind[0] == "i":             # FFV1_2(i, g): string (T^a ..)_{open, column}
                 for a, b in self._splits2(s):
                     for i in self.currents(a, kind):
                         for g in self.currents(b, "g"):
@@ -110,7 +115,7 @@ class LineGenerator:
                             out.append(Node(kind, legs, "FFV1_2", (i, g), ct, f"F2({i.topo},{g.topo})"))
             else:
                 for a, b in self._splits2(s):
-                    for line in ("t", "l") if self.has_light else ("t",):  # FFV1P0_3(i, o): T^a_{o's open, i's open}
+                    for line in self.lines:  # FFV1P0_3(i, o): T^a_{o's open, i's open}
                         for i in self.currents(a, "i_" + line):
                             for o in self.currents(b, "o_" + line):
                                 ct = self._contract(T, [self.OPEN, 21, 20], (i, o), True)
@@ -161,7 +166,7 @@ class LineGenerator:
     def _amplitudes_centroid(self):
         n, half = self.n, self.n // 2
         all_legs = tuple(range(n))
-        lines = [("t", "to", "ti")] + ([("l", "lo", "li")] if self.has_light else [])
+        lines = [(tag, tag + "o", tag + "i") for tag in self.lines]
         amps = []
 
         def allowed(parts):
@@ -201,27 +206,26 @@ class LineGenerator:
 
     # ---- colour flows
     def colour_flows(self):
-        """Basis tensors over all external legs (sorted): type A (T^s1)_{t, I} (T^s2)_{O, t~}, type B (T^s1)_{t, t~} (T^s2)_{O, I}
-        over all ordered distributions of the gluons on the two strings."""
+        """Basis tensors over all external legs (sorted): the outgoing-flow end of every quark line is connected to the
+        incoming-flow end of some line by a string of generators, (T^s1)_{o_1, i_pi(1)} (T^s2)_{o_2, i_pi(2)} ..., over all
+        permutations pi and all ordered distributions of the gluons on the strings.  One line: the n! strings of
+        procgen.generate_ir; two lines: (T..)_{t I}(T..)_{O t~} and (T..)_{t t~}(T..)_{O I}."""
         gl = [l for l, r in enumerate(self.roles) if r == "g"]
+        rows = [self.leg_of[tag + "o"] for tag in self.lines]
+        cols = [self.leg_of[tag + "i"] for tag in self.lines]
+        L = len(rows)
         flows, names = [], []
-        if not self.has_light:   # one string (T^s)_{t, t~} per ordering of the gluons: the basis of procgen.generate_ir
+        for pi_ in itertools.permutations(range(L)):
             for perm in itertools.permutations(gl):
-                t1 = self._string(perm, self.leg_of["to"], self.leg_of["ti"])
-                flows.append(np.einsum(t1[0], t1[1], list(range(self.n))).reshape(-1))
-                names.append(("T", perm, ()))
-            return np.stack(flows, axis=1), names
-        to, ti, lo, li = (self.leg_of[r] for r in ("to", "ti", "lo", "li"))
-        for typ, (c1, c2) in (("A", (li, ti)), ("B", (ti, li))):
-            for j in range(len(gl) + 1):
-                for first in itertools.permutations(gl, j):
-                    rem = [g for g in gl if g not in first]
-                    for second in itertools.permutations(rem):
-                        t1 = self._string(first, to, c1)
-                        t2 = self._string(second, lo, c2)
-                        ops = [t1[0], t1[1], t2[0], t2[1], list(range(self.n))]
-                        flows.append(np.einsum(*ops).reshape(-1))
-                        names.append((typ, first, tuple(second)))
+                for cuts in itertools.combinations_with_replacement(range(len(gl) + 1), L - 1):
+                    bounds = (0,) + cuts + (len(gl),)
+                    segs = [perm[bounds[q]:bounds[q + 1]] for q in range(L)]
+                    ops = []
+                    for q in range(L):
+                        t_, ax = self._string(segs[q], rows[q], cols[pi_[q]])
+                        ops += [t_, ax]
+                    flows.append(np.einsum(*ops, list(range(self.n))).reshape(-1))
+                    names.append((pi_, tuple(segs)))
         return np.stack(flows, axis=1), names
 
     def _string(self, gluons, row, col):
@@ -236,7 +240,7 @@ class LineGenerator:
 
 
 def _rational(c, what):
-    re, im = Fraction(float(c.real)).limit_denominator(216), Fraction(float(c.imag)).limit_denominator(216)
+    re, im = Fraction(float(c.real)).limit_denominator(5184), Fraction(float(c.imag)).limit_denominator(5184)
     assert abs(complex(re, im) - c) < 1e-10, f"{what}: {c} is not a small rational"
     return re, im
 
@@ -245,8 +249,21 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
     """IR of the process whose external legs have the given roles (see LineGenerator)."""
     gen = LineGenerator(roles, ninitial)
     n = gen.n
-    amps = gen.amplitudes(root)
+    amps = [(op, ch, ct, topo) for op, ch, ct, topo in gen.amplitudes(root)]
     B, flow_names = gen.colour_flows()
+    # Two light lines of the SAME flavour: the fermion-flow-in ends are indistinguishable, so the diagrams with the two
+    # lines re-paired (l: lo-mi, m: mo-li) contribute with the opposite sign (Fermi statistics).  A second generator
+    # with the roles of the two in-ends exchanged enumerates them; colour tensors carry leg labels, so they project on
+    # the same flows.
+    gens = [gen]
+    if "l" in gen.lines and "m" in gen.lines and abs(pdg[gen.leg_of["lo"]]) == abs(pdg[gen.leg_of["mo"]]):
+        swap = {"li": "mi", "mi": "li"}
+        gen2 = LineGenerator([swap.get(r, r) for r in roles], ninitial)
+        gens.append(gen2)
+        amps += [(op, ch, -ct, "X" + topo) for op, ch, ct, topo in gen2.amplitudes(root)]
+    # For N = 3 the flows become linearly dependent at large multiplicities (three quark lines + a gluon, ...): the
+    # decomposition is then not unique -- harmless for |M|^2, but the JAMPs are no longer individually gauge invariant
+    independent = np.linalg.matrix_rank(B) == B.shape[1]
     # schedule: externals, then per amplitude the currents it needs (each wavefunction keeps its own slot)
     calls, order = [], []
     uid = itertools.count()
@@ -260,20 +277,25 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
         order.append(nd)
 
     def emit(nd):
-        line = "t" if nd.kind.endswith("_t") else ("l" if nd.kind.endswith("_l") else "g")
+        line = nd.kind[-1] if nd.kind != "g" else "g"
         mass, width = ("mdl_MT", "mdl_WT") if line == "t" else ("ZERO", "ZERO")
         if not nd.children:
             (leg,) = nd.legs
             role = roles[leg]
             incoming = leg < ninitial
-            nsf = {"g": -1 if incoming else 1, "to": 1, "ti": -1, "lo": -1 if incoming else 1, "li": 1 if incoming else -1}[role]
-            calls.append({"op": nd.op, "out": nd.uid, "leg": leg, "mass": mass if role in ("to", "ti") else "ZERO", "nsf": nsf})
+            # gluon: -1 incoming, +1 outgoing; o-type end (oxxxxx): incoming antiquark -1 / outgoing quark +1; i-type end
+            # (ixxxxx): incoming quark +1 / outgoing antiquark -1
+            nsf = (-1 if incoming else 1) if role == "g" or role[1] == "o" else (1 if incoming else -1)
+            calls.append({"op": nd.op, "out": nd.uid, "leg": leg, "mass": mass, "nsf": nsf})
         else:
             coup = {"FFV1": "GC_11", "VVV1": "GC_10", "VVVV": "GC_12"}[nd.op[:4]]
             calls.append({"op": nd.op, "out": nd.uid, "in": [c.uid for c in nd.children], "coup": coup, "mass": mass, "width": width})
 
     for leg in range(n):
         visit(gen.externals[leg])
+        for other in gens[1:]:   # the same external wavefunctions (a leg's call does not depend on the pairing)
+            assert other.externals[leg].op == gen.externals[leg].op
+            other.externals[leg].uid = gen.externals[leg].uid
     for nd in order:
         emit(nd)
     jamp = [[] for _ in flow_names]
@@ -288,7 +310,10 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
         coef, *_ = np.linalg.lstsq(B, ct.reshape(-1), rcond=None)
         assert np.allclose(B @ coef, ct.reshape(-1), atol=1e-10), f"the colour flows do not span {topo}"
         for k_, c in enumerate(coef):
-            re, im = _rational(c, topo)
+            if independent:
+                re, im = _rational(c, topo)
+            else:   # any decomposition gives the same |M|^2 = c^+ (B^+ B) c; the minimum-norm one has no nice fractions
+                re, im = (0.0 if abs(c.real) < 1e-13 else float(c.real)), (0.0 if abs(c.imag) < 1e-13 else float(c.imag))
             if re or im:
                 jamp[k_].append((a_idx, -float(re), -float(im)))
     gram = (B.conj().T @ B).real
@@ -296,25 +321,26 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
     nums, dens = integer_rows(rows)
     hel_states = []
     for leg, role in enumerate(roles):
-        anti_like = (role in ("ti", "li")) == (leg >= ninitial)   # incoming fermion / outgoing antifermion: listed reversed
+        anti_like = (role != "g" and role[1] == "i") == (leg >= ninitial)   # as before for t~ and the light line
         hel_states.append([1, -1] if role != "g" and anti_like else [-1, 1])
-    if np.linalg.matrix_rank(B) < B.shape[1]:
-        # dependent flows (large multiplicities at N = 3): least squares would pick an arbitrary decomposition
-        raise ValueError("the colour flows of this process are linearly dependent: use an exact colour algebra (procgen.generate_ir)")
+
     colour_avg = 1
     for leg in range(ninitial):
         colour_avg *= 8 if roles[leg] == "g" else 3
-    nfinal_gluons = sum(1 for leg in range(ninitial, n) if roles[leg] == "g")
+    identical = 1   # identical particles in the final state
+    for code in set(pdg[ninitial:]):
+        identical *= math.factorial(pdg[ninitial:].count(code))
     topos = {t.replace("W1", "W").replace("W3", "W").replace("W4", "W") for _, _, _, t in amps}
     return {
         "name": name, "process": process, "nexternal": n, "ninitial": ninitial, "ndiags": len(topos), "ncomb": 2**n,
         "nwavefuncs": len(order), "helicities": [list(h) for h in itertools.product(*hel_states)],
-        "denominator": 4 * colour_avg * math.factorial(nfinal_gluons),
+        "denominator": 4 * colour_avg * identical,
         "params": ["mdl_MT", "mdl_WT"], "couplings": sorted({c["coup"] for c in calls if "coup" in c}),
         "initial_states": initial_states, "mirror_initial_states": bool(mirror), "pdg": pdg,
         "masses": ["mdl_MT" if r in ("to", "ti") else "ZERO" for r in roles],
         "calls": calls, "jamp": jamp, "color_num": nums, "color_denom": dens,
-        "color_basis": [[t, list(a), list(b)] for t, a, b in flow_names],
+        "color_basis": [[list(pi_), [list(sg) for sg in segs]] for pi_, segs in flow_names],
+        "color_flows_independent": bool(independent),
     }
 
 
@@ -329,6 +355,19 @@ PROCESSES = {   # name -> (roles, process string, pdg of the first flavour, init
     "1_gu_ttxug": (["g", "li", "to", "ti", "lo", "g"], "g u > t t~ u g", [21, 2, 6, -6, 2, 21], [[21, q] for q in LIGHT]),
     "1_gux_ttxuxg": (["g", "lo", "to", "ti", "li", "g"], "g u~ > t t~ u~ g", [21, -2, 6, -6, -2, 21], [[21, -q] for q in LIGHT]),
     "1_gg_ttxuux": (["g", "g", "to", "ti", "lo", "li"], "g g > t t~ u u~", [21, 21, 6, -6, 2, -2], [[21, 21]]),
+    # two light lines (the four-quark subprocesses of p p > t t~ j j); same-flavour lines get the exchange diagrams with
+    # the Fermi sign automatically.  initial_states: (parton of hadron 1, parton of hadron 2), mirrored where listed once
+    "1_uu_ttxuu": (["li", "mi", "to", "ti", "lo", "mo"], "u u > t t~ u u", [2, 2, 6, -6, 2, 2], [[q, q] for q in LIGHT]),
+    "1_ud_ttxud": (["li", "mi", "to", "ti", "lo", "mo"], "u d > t t~ u d", [2, 1, 6, -6, 2, 1],
+                   [[a, b] for k_, a in enumerate(LIGHT) for b in LIGHT[k_ + 1:]]),
+    "1_uxux_ttxuxux": (["lo", "mo", "to", "ti", "li", "mi"], "u~ u~ > t t~ u~ u~", [-2, -2, 6, -6, -2, -2], [[-q, -q] for q in LIGHT]),
+    "1_uxdx_ttxuxdx": (["lo", "mo", "to", "ti", "li", "mi"], "u~ d~ > t t~ u~ d~", [-2, -1, 6, -6, -2, -1],
+                       [[-a, -b] for k_, a in enumerate(LIGHT) for b in LIGHT[k_ + 1:]]),
+    "1_uux_ttxuux": (["li", "lo", "to", "ti", "mo", "mi"], "u u~ > t t~ u u~", [2, -2, 6, -6, 2, -2], [[q, -q] for q in LIGHT]),
+    # the final flavour differs from the initial one: three choices, counted by listing every initial state three times
+    "1_uux_ttxddx": (["li", "lo", "to", "ti", "mo", "mi"], "u u~ > t t~ d d~", [2, -2, 6, -6, 1, -1], [[q, -q] for q in LIGHT] * 3),
+    "1_udx_ttxudx": (["li", "mo", "to", "ti", "lo", "mi"], "u d~ > t t~ u d~", [2, -1, 6, -6, 2, -1],
+                     [[a, -b] for a in LIGHT for b in LIGHT if a != b]),
     # no light line: an independent derivation of the built-in processes (cross-check only, see the tests)
     "1_gg_ttx": (["g", "g", "to", "ti"], "g g > t t~", [21, 21, 6, -6], [[21, 21]]),
     "1_gg_ttxg": (["g", "g", "to", "ti", "g"], "g g > t t~ g", [21, 21, 6, -6, 21], [[21, 21]]),
@@ -338,6 +377,6 @@ PROCESSES = {   # name -> (roles, process string, pdg of the first flavour, init
 
 def process_ir(name, root="centroid"):
     roles, proc, pdg, initial = PROCESSES[name]
-    mirror = initial != [[21, 21]]
+    mirror = initial != [[21, 21]] and not all(a == b for a, b in initial)   # identical beams partons need no mirror
     n = len(roles)
     return generate_ir(roles, name, f"{proc} WEIGHTED<={n - 2} @1", pdg, initial, mirror, root=root)

@@ -387,3 +387,90 @@ def test_tile_chains_on_host(irs, k, monkeypatch):
     one = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, only_comb=11, hp=True)
     # a single (possibly helicity-suppressed) row: accurate relative to the size of the whole sum
     assert np.max(np.abs(one - omatrix.matrix(ir, p, ir["helicities"][11], params)) / (ref * ir["denominator"])) < 1e-13
+
+
+# ------------------------------------------------------------------------------ two light lines (four-quark processes)
+FOUR_QUARK = ["1_uu_ttxuu", "1_ud_ttxud", "1_uxux_ttxuxux", "1_uxdx_ttxuxdx", "1_uux_ttxuux", "1_uux_ttxddx", "1_udx_ttxudx"]
+
+
+@pytest.mark.parametrize("name", FOUR_QUARK)
+def test_four_quark_processes(name):
+    """The four-quark subprocesses of p p > t t~ j j: diagram counts (7, or 14 with the exchange diagrams of identical
+    flavours), 6 colour flows, the two organisations of the amplitude agree, charge conjugation maps q q(') onto
+    q~ q~(') with t <-> t~."""
+    from madflow_b200 import procgen_lines as pl
+
+    ir = pl.process_ir(name)
+    assert process_ir.validate(ir) and len(ir["jamp"]) == 6 and ir["color_flows_independent"]
+    same = name in ("1_uu_ttxuu", "1_uxux_ttxuxux", "1_uux_ttxuux")
+    assert ir["ndiags"] == (14 if same else 7)
+    assert ir["denominator"] == (72 if name in ("1_uu_ttxuu", "1_uxux_ttxuxux") else 36)
+    p = _points(2, n=4, seed=21)
+    me = omatrix.smatrix(ir, p, sm_params(), EXACT)
+    assert np.all(me > 0)
+    np.testing.assert_allclose(omatrix.smatrix(pl.process_ir(name, root="tbar"), p, sm_params(), EXACT), me, rtol=1e-12)
+    conj = {"1_uu_ttxuu": "1_uxux_ttxuxux", "1_ud_ttxud": "1_uxdx_ttxuxdx"}.get(name)
+    if conj:
+        q = p.copy()
+        q[:, [2, 3]] = q[:, [3, 2]]
+        np.testing.assert_allclose(omatrix.smatrix(pl.process_ir(conj), q, sm_params(), EXACT), me, rtol=1e-12)
+
+
+def test_identical_quarks_obey_fermi_statistics():
+    """u u > t t~ u u with the two outgoing quarks at the same momentum and helicity: the colour-dressed amplitude
+    sum_k JAMP_k flow_k(colours) is antisymmetric under the exchange of their colours (a '+' between the direct and the
+    exchanged diagrams would make it symmetric)."""
+    from madflow_b200 import procgen_lines as pl
+
+    ir = pl.process_ir("1_uu_ttxuu")
+    B, _ = pl.LineGenerator(pl.PROCESSES["1_uu_ttxuu"][0]).colour_flows()
+    p5 = _points(1, n=3, seed=5)
+    p = np.concatenate([p5[:, :4], p5[:, 4:5] / 2, p5[:, 4:5] / 2], axis=1)
+    checked = 0
+    for hel in ir["helicities"]:
+        if hel[4] != hel[5]:
+            continue
+        J = omatrix.matrix(ir, p, hel, sm_params(), EXACT, return_jamp=True)
+        if np.max(np.abs(J)) == 0.0:
+            continue
+        full = (B @ J).reshape(3, 3, 3, 3, 3, 3, -1)          # colours of the legs 0..5
+        assert np.max(np.abs(full + np.swapaxes(full, 4, 5))) < 1e-13 * np.max(np.abs(full))
+        checked += 1
+    assert checked >= 4
+
+
+def test_three_lines_and_a_gluon_gauge_invariance():
+    """u d > t t~ u d g (64 diagrams; 18 colour flows that are linearly dependent for N = 3, so the decomposition is the
+    minimum-norm one): |M|^2 vanishes for a BRST-polarised gluon."""
+    from madflow_b200 import procgen_lines as pl
+
+    ir = pl.generate_ir(["li", "mi", "to", "ti", "lo", "mo", "g"], "1_ud_ttxudg", "u d > t t~ u d g",
+                        [2, 1, 6, -6, 2, 1, 21], [[2, 1]], True)
+    assert ir["ndiags"] == 64 and len(ir["jamp"]) == 18 and not ir["color_flows_independent"]
+    p = _points(3, n=2, seed=9)
+    params = dict(sm_params(), mdl_WT=0.0)
+    checked = 0
+    for hel in ir["helicities"][::9]:
+        phys = np.max(np.abs(omatrix.matrix(ir, p, hel, params, EXACT)))
+        if phys == 0.0:
+            continue
+        h = list(hel)
+        h[6] = 4
+        assert np.max(np.abs(omatrix.matrix(ir, p, h, params, EXACT))) < 1e-20 * phys
+        checked += 1
+    assert checked >= 3
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+def test_generated_cuda_source_on_host_four_quark():
+    """The emitted helicity-parallel code of u u~ > t t~ u u~ (direct + exchanged diagrams), executed on the CPU."""
+    import hostcheck as hc
+    from madflow_b200 import procgen_lines as pl
+
+    ir = pl.process_ir("1_uux_ttxuux")
+    lib = hc.process(ir)
+    p = _points(2, n=6, seed=8)
+    a_s = 0.09 + 0.05 * np.random.default_rng(3).random(6)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    np.testing.assert_allclose(hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF, hp=True), omatrix.smatrix(ir, p, params), rtol=1e-12)
