@@ -225,7 +225,8 @@ class MultiProcessIntegrand:
             if fi.matrix.variant != "hp":
                 fi.matrix.set_variant("hp")   # the kernel pipeline that keeps the events in device memory
         if len(self.parts) > 8:
-            raise ValueError("at most 8 subprocesses (mf_vegas_accumulate_sum)")
+            raise ValueError(f"{len(self.parts)} subprocesses: mf_vegas_accumulate_sum takes at most 8 terms per event "
+                             "(ACC_MAX_TERMS in csrc/pipeline_kernels.cuh; p p > t t~ j j needs 12)")
         self.n_dim, self.nexternal = first.n_dim, first.nexternal
         self.max_events_per_launch = min(fi.max_events_per_launch for fi in self.parts)
         self._common_blocks = None
