@@ -264,6 +264,7 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
     # For N = 3 the flows become linearly dependent at large multiplicities (three quark lines + a gluon, ...): the
     # decomposition is then not unique -- harmless for |M|^2, but the JAMPs are no longer individually gauge invariant
     independent = np.linalg.matrix_rank(B) == B.shape[1]
+    Bpinv = np.linalg.pinv(B)   # one factorisation for all amplitudes: coefficients = pinv(B) tensor (minimum norm)
     # schedule: externals, then per amplitude the currents it needs (each wavefunction keeps its own slot)
     calls, order = [], []
     uid = itertools.count()
@@ -307,7 +308,7 @@ def generate_ir(roles, name, process, pdg, initial_states, mirror=True, ninitial
             emit(nd)
         calls.append({"op": op, "amp": a_idx, "in": [c.uid for c in children],
                       "coup": {"FFV1": "GC_11", "VVV1": "GC_10", "VVVV": "GC_12"}[op[:4]]})
-        coef, *_ = np.linalg.lstsq(B, ct.reshape(-1), rcond=None)
+        coef = Bpinv @ ct.reshape(-1)
         assert np.allclose(B @ coef, ct.reshape(-1), atol=1e-10), f"the colour flows do not span {topo}"
         for k_, c in enumerate(coef):
             if independent:
