@@ -35,6 +35,10 @@ WORKLOADS = {
     "1_gg_ttxggg": dict(label="g g > t t~ g g g LO, --no_pdf, pt>30 cuts, running g_s", masses=[MT, MT, 0.0, 0.0, 0.0],
                         pt_cut=30.0, running=True, events=1 << 18, e2e_events=1 << 16),
 }
+# the light-quark subprocesses of p p > t t~ (j): same phase space and cuts as their gluon-fusion counterparts
+WORKLOADS["1_uux_ttx"] = dict(WORKLOADS["1_gg_ttx"], label="u u~ > t t~ LO, --no_pdf, RAMBO + VEGAS, pt>30, alpha_s frozen 0.118")
+for _name, _proc in (("1_uux_ttxg", "u u~ > t t~ g"), ("1_gu_ttxu", "g u > t t~ u"), ("1_gux_ttxux", "g u~ > t t~ u~")):
+    WORKLOADS[_name] = dict(WORKLOADS["1_gg_ttxg"], label=f"{_proc} LO, --no_pdf, pt>30 cuts, alpha_s frozen")
 PREFERENCE = ["1_gg_ttxgg", "1_gg_ttxg", "1_gg_ttx"]
 
 
