@@ -177,38 +177,6 @@ HP_TYPES = {"vxxxxx": 0, "oxxxxx": 1, "ixxxxx": 2, "FFV1_1": 3, "FFV1_2": 4, "FF
             "VVVV1P0_1": 7, "VVVV3P0_1": 8, "VVVV4P0_1": 9}
 
 
-def hp_analyse(ir):
-    """Undo the slot reuse of the call list: every write creates a distinct wavefunction with the set
-    of external legs below it.  Returns (wfs, exts, items, amps, cxd per event)."""
-    cur = {}      # slot -> wavefunction id
-    wfs, exts, items, amps = [], [], [], []
-    for c in ir["calls"]:
-        if "leg" in c:
-            w = len(wfs)
-            wfs.append({"legs": (c["leg"],)})
-            cur[c["out"]] = w
-            exts.append({"call": c, "out": w})
-        elif "amp" in c:
-            amps.append({"call": c, "in": [cur[s] for s in c["in"]]})
-        else:
-            ins = [cur[s] for s in c["in"]]
-            legs = tuple(sorted(set().union(*[wfs[i]["legs"] for i in ins])))
-            assert len(legs) == sum(len(wfs[i]["legs"]) for i in ins), "children must not share legs"
-            w = len(wfs)
-            wfs.append({"legs": legs})
-            cur[c["out"]] = w
-            items.append({"call": c, "in": ins, "out": w})
-    off = 0
-    for w in wfs:
-        w["level"] = len(w["legs"])
-        w["nv"] = 1 << w["level"]
-        w["off"] = off
-        w["mask"] = sum(1 << l for l in w["legs"])
-        off += 2 + 4 * w["nv"]
-    items.sort(key=lambda it: (wfs[it["out"]]["level"], HP_TYPES[it["call"]["op"]]))
-    return wfs, exts, items, amps, off
-
-
 def hp_config(ir, key):
     """Launch shape of the helicity-parallel kernels, MADFLOW_B200_HP_<KEY> overrides (tools/build_variants.py):
       E          events per block
@@ -216,26 +184,24 @@ def hp_config(ir, key):
       NB         rows of the amplitude buffer = amplitudes per batch
       SCRATCH    shared-memory scratch for the pair objects of a batch, complex numbers per event
       MINBLOCKS  resident blocks per SM the register allocation aims at
+      PERSIST    pair objects (vertex numerators) of up to this many helicity variants are evaluated once, together
+                 with the currents of their level, and stay in shared memory; the others are evaluated batch by batch
     Defaults from measurements on B200: up to 64 helicity combinations two events per
     block and all JAMPs in one thread; beyond, one event per block (its wavefunctions fill a third of the
-    shared memory), 8 colour groups and batches of 64 amplitudes; up to 64 combinations the batch size is what
-    still lets two blocks of two events share an SM (21 rows: 14.5e6 events/s for g g > t t~ g g, 16 rows: 13.8e6)."""
+    shared memory), 8 colour groups and batches of 64 amplitudes."""
     env = os.environ.get("MADFLOW_B200_HP_" + key)
     if env:
         return int(env)
     if ir["ncomb"] > 64:
-        return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 4096, "MINBLOCKS": 1}[key]
-    return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 21, "SCRATCH": 512, "MINBLOCKS": 2}[key]
+        return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 4096, "MINBLOCKS": 1, "PERSIST": 0}[key]
+    return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 21, "SCRATCH": 512, "MINBLOCKS": 2,
+            "PERSIST": 8 if hp_use_plan(ir) else 0}[key]
 
 
-def hp_chain(ir):
-    """Amplitude tiles that accumulate in the tensor-core accumulators: amplitudes of one batch with the same colour
-    signature (up to +-1, +-i) and the same split of the legs between pair object and wavefunction are stored ONCE
-    (1 = on; MADFLOW_B200_HP_CHAIN overrides).  The batches already keep pair objects of one kind and colour signature
-    together, which is what puts chain members into one batch (ordering by legs first was tried: not better).
-    Default off until measured on the GPU (plan for round 2)."""
-    env = os.environ.get("MADFLOW_B200_HP_CHAIN")
-    return int(env) if env else 0
+def hp_use_plan(ir):
+    """Evaluate the colour-reduced plan attached to the IR (madflow_b200/recursion.py) instead of the diagram list
+    (MADFLOW_B200_HP_REDUCE=0: the diagram list, the A/B partner)."""
+    return "plan" in ir and os.environ.get("MADFLOW_B200_HP_REDUCE", "1") != "0"
 
 
 def hp_passes(ir):
@@ -259,18 +225,123 @@ def hp_colour_mode(ir, ncg):
     return "mma" if len(ir["jamp"]) >= 48 else "groups"
 
 
+# Vertex structures of the helicity-parallel kernels.  Every vertex is evaluated as a NUMERATOR in dual form: with
+# one of its lines left open (the output of a current, or the input `x` of a closing vertex),
+#   Q[k] = -i COUP (vertex contracted with the other lines)_k ,  metric signs folded in, so that  amp = sum_k x[2+k] Q[k]
+# and a current is the same numerator times its propagator (csrc/process_kernels_hp.cuh::hp_unit):
+#   ROW  (O, G):    Obar Gslash            <- FFV1_1(O, G)   | FFV1_0(x, O, G)
+#   COL  (I, G):    Gslash I               <- FFV1_2(I, G)   | FFV1_0(I, x, G)
+#   CUR  (I, O):    Obar gamma^mu I        <- FFV1P0_3(I, O) | FFV1_0(I, O, x)
+#   VVV  (V2, V3):  three-gluon vertex     <- VVV1P0_1       | VVV1_0 with the other two lines in cyclic order
+#   VVVV (3 lines): contact term           <- VVVVkP0_1      | VVVVk_0
+PT = {"ROW": 0, "COL": 1, "CUR": 2, "VVV": 3, "VVVV": 4}
+FINISH = {"none": 0, "g": 1, "o": 2, "i": 3}
+PHASE_CODE = {1: 0, -1: 1, 1j: 2, -1j: 3}
+# UFO four-gluon structures: VVVVk = sum of sign * g(pa) g(pb) over vertex positions 1..4
+QUARTIC = {"1": ((+1, (1, 4), (2, 3)), (-1, (1, 3), (2, 4))),
+           "3": ((+1, (1, 4), (2, 3)), (-1, (1, 2), (3, 4))),
+           "4": ((+1, (1, 3), (2, 4)), (-1, (1, 2), (3, 4)))}
+
+
+def _vertex_structure(op, jx, ins):
+    """(structure, inputs in the structure's order, four-gluon term codes) of vertex `op` with the line at argument
+    position jx left open (jx = None: `op` is a current routine and its output is the open line)."""
+    if op == "FFV1_1":
+        return "ROW", tuple(ins), (0, 0)
+    if op == "FFV1_2":
+        return "COL", tuple(ins), (0, 0)
+    if op == "FFV1P0_3":
+        return "CUR", tuple(ins), (0, 0)
+    if op == "VVV1P0_1":
+        return "VVV", tuple(ins), (0, 0)
+    if op == "FFV1_0":
+        full = list(ins)
+        full.insert(jx, None)
+        I, O, G = full
+        return [("ROW", (O, G)), ("COL", (I, G)), ("CUR", (I, O))][jx] + ((0, 0),)
+    if op == "VVV1_0":
+        full = list(ins)
+        full.insert(jx, None)
+        return "VVV", (full[(jx + 1) % 3], full[(jx + 2) % 3]), (0, 0)
+    assert op.startswith("VVVV"), op
+    kind = op[4]
+    if jx is None:          # VVVVkP0_1(V2, V3, V4): the output is vertex position 1
+        xpos, others = 1, [2, 3, 4]
+    else:
+        xpos, others = jx + 1, [q for q in (1, 2, 3, 4) if q != jx + 1]
+    pos = {q: others.index(q) for q in others}   # vertex position -> index into the inputs
+    enc = []
+    for sign, pa, pb in QUARTIC[kind]:
+        if xpos in pa:
+            vec, dot = [q for q in pa if q != xpos][0], pb
+        else:
+            vec, dot = [q for q in pb if q != xpos][0], pa
+        enc.append((0x40 if sign < 0 else 0) | pos[vec] << 4 | pos[dot[0]] << 2 | pos[dot[1]])
+    return "VVVV", tuple(ins), tuple(enc)
+
+
+def hp_plan_from_ir(ir):
+    """The diagram list of the IR as an evaluation plan (the format of recursion.build_plan): undo the slot reuse of
+    the call list -- every write creates a distinct wavefunction -- one single-term object per current, one
+    single-term pair object per distinct (closing vertex, inputs but the heaviest), one row per amplitude."""
+    cur = {}      # slot -> object id
+    objects, amps = [], []
+    for c in ir["calls"]:
+        if "leg" in c:
+            cur[c["out"]] = len(objects)
+            objects.append({"legs": [c["leg"]], "ext": c, "terms": []})
+        elif "amp" in c:
+            amps.append((c, [cur[s] for s in c["in"]]))
+        else:
+            ins = [cur[s] for s in c["in"]]
+            legs = sorted(set().union(*[objects[i]["legs"] for i in ins]))
+            assert len(legs) == sum(len(objects[i]["legs"]) for i in ins), "children must not share legs"
+            cur[c["out"]] = len(objects)
+            sign = -1 if c.get("coup_sign", 1) < 0 else 1
+            objects.append({"legs": legs, "ext": None, "mass": c["mass"], "width": c["width"],
+                            "terms": [{"op": c["op"], "in": ins, "coef": [sign, 0], "coup": c["coup"]}]})
+    by_amp = {}
+    for j, terms in enumerate(ir["jamp"]):
+        for k, re, im in terms:
+            by_amp.setdefault(k, []).append([j, float(re), float(im)])
+    LSTAR = ir["nexternal"] - 1 if hp_passes(ir) > 1 else None
+    pairs, pair_index, rows = [], {}, []
+    for c, ins in amps:
+        if not by_amp.get(c["amp"]):
+            continue
+        # x = the input with the most legs (with helicity passes: preferably one that does not hold the pass leg,
+        # so that the pass halves the rows and not the columns of the amplitude tiles)
+        sizes = [len(objects[w]["legs"]) for w in ins]
+        cands = [q for q in range(len(ins)) if sizes[q] == max(sizes)]
+        free = [q for q in cands if LSTAR not in objects[ins[q]]["legs"]]
+        jx = (free or cands)[0]
+        rest = [w for q, w in enumerate(ins) if q != jx]
+        sign = -1 if c.get("coup_sign", 1) < 0 else 1
+        key = (c["op"], jx, tuple(rest), c["coup"], sign)
+        if key not in pair_index:
+            pair_index[key] = len(pairs)
+            legs = sorted(set().union(*[objects[w]["legs"] for w in rest]))
+            pairs.append({"legs": legs, "terms": [{"op": c["op"], "jx": jx, "in": rest, "coef": [sign, 0], "coup": c["coup"]}]})
+        rows.append({"x": ins[jx], "pair": pair_index[key], "jamp": by_amp[c["amp"]], "amp": c["amp"]})
+    return {"objects": objects, "pairs": pairs, "rows": rows}
+
+
 def emit_hp(ir):
     """Tables + the generated amplitude/JAMP/colour code of the helicity-parallel kernels."""
-    wfs, exts, items, amps, wfsize = hp_analyse(ir)
+    reduced = hp_use_plan(ir)
+    plan = ir["plan"] if reduced else hp_plan_from_ir(ir)
     n = ir["nexternal"]
     assert ir["ncomb"] == 2**n, "the hp kernels need the full 2^n helicity table"
-    maxlevel = max(w["level"] for w in wfs)
     NH = ir["ncomb"]
     NPASS = hp_passes(ir)
     assert NPASS in (1, 2)
     NHP = NH // NPASS
     LSTAR = n - 1 if NPASS > 1 else None   # the leg whose helicity is fixed within a pass (top variant bit)
-    big = len(amps) > 400                  # tables beyond the 64 KB of constant memory live in global memory
+    big = len(plan["rows"]) > 400          # tables beyond the 64 KB of constant memory live in global memory
+    scratch = hp_config(ir, "SCRATCH")
+    NB = hp_config(ir, "NB")
+    NCG = hp_config(ir, "NCG")
+    PERSIST = hp_config(ir, "PERSIST")
 
     def pidx(name):
         return -1 if name == "ZERO" else ir["params"].index(name)
@@ -284,141 +355,95 @@ def emit_hp(ir):
         """bits of the output's variant index that make up the input's variant index (both ascending)"""
         return sum(1 << q for q, l in enumerate(out_legs) if l in in_legs)
 
-    L = []
-    L.append(both("mf::HpWf", "wf", len(wfs), ", ".join(f"{{{w['off']}u, {w['nv']}, {w['mask']}}}" for w in wfs)))
-    ext_by_leg = sorted(exts, key=lambda x: x["call"]["leg"])
-    assert [x["call"]["leg"] for x in ext_by_leg] == list(range(n))
-    L.append(both("mf::HpExt", "ext", n, ", ".join(
-        f"{{{HP_TYPES[x['call']['op']]}, {x['call']['leg']}, {x['call']['nsf']}, {pidx(x['call']['mass'])}, {x['out']}}}"
-        for x in ext_by_leg)))
-    rows = []
-    for it in items:
-        c = it["call"]
-        ins = it["in"] + [0] * (3 - len(it["in"]))
-        vm = [vmask(wfs[it["out"]]["legs"], wfs[i]["legs"]) for i in it["in"]] + [0] * (3 - len(it["in"]))
-        ioff = [wfs[i]["off"] for i in ins]
-        inv = [wfs[i]["nv"] for i in ins]
-        W = wfs[it["out"]]
-        rows.append(f"{{{HP_TYPES[c['op']]}, {len(it['in'])}, {pidx(c['mass'])}, {pidx(c['width'])}, "
-                    f"{ir['couplings'].index(c['coup'])}, {1 if c.get('coup_sign', 1) < 0 else 0}, {W['off']}, {W['nv']}, "
-                    f"{{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
-                    f"{{{vm[0]}, {vm[1]}, {vm[2]}}}}}")
-    L.append(both("mf::HpItem", "items", max(len(rows), 1), ",\n  ".join(rows) if rows else "{0}"))
-
     def pext(v, m):
-        return sum(((v >> b_) & 1) << q for q, b_ in enumerate(b2 for b2 in range(5) if m >> b2 & 1))
+        return sum(((v >> b_) & 1) << q for q, b_ in enumerate(b2 for b2 in range(8) if m >> b2 & 1))
 
-    # work items of the current phases: (current, variant, variants of the inputs), level by level
-    crow, begins = [], []
-    for lev in range(0, maxlevel + 2):
-        begins.append(len(crow))
-        for idx, it in enumerate(items):
-            W = wfs[it["out"]]
-            if W["level"] != lev:
-                continue
-            masks = [vmask(W["legs"], wfs[i]["legs"]) for i in it["in"]] + [0] * (3 - len(it["in"]))
-            for v in range(W["nv"]):
-                crow.append(f"{{{idx}, {v}, {{{pext(v, masks[0])}, {pext(v, masks[1])}, {pext(v, masks[2])}}}, 0}}")
-    L.append(both("mf::HpPairItem", "cur_items", max(len(crow), 1), ", ".join(crow) if crow else "{0, 0, {0, 0, 0}, 0}", const=False))
-    L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
-    tables = "\n".join(L)
+    def phase_of(t):
+        ph = complex(*t["coef"])
+        assert ph in PHASE_CODE, f"coefficient {ph} of a plan term is not a unit"
+        return PHASE_CODE[ph]
 
-    by_amp = {}
-    for j, terms in enumerate(ir["jamp"]):
-        for k, re, im in terms:
-            by_amp.setdefault(k, []).append((j, float(re), float(im)))
-    used = [am for am in amps if by_amp.get(am["call"]["amp"])]
-
-    # pair objects: amp = x . Q(rest of the vertex), x = the input with the most legs (with helicity passes:
-    # preferably one that does not hold the pass leg, so that the pass halves the rows and not the columns)
-    QUARTIC = {"1": ((+1, (1, 4), (2, 3)), (-1, (1, 3), (2, 4))),
-               "3": ((+1, (1, 4), (2, 3)), (-1, (1, 2), (3, 4))),
-               "4": ((+1, (1, 3), (2, 4)), (-1, (1, 2), (3, 4)))}
-    pairs, pair_index, amp_rows = [], {}, []
-    for am in used:
-        c = am["call"]
-        ins = am["in"]
-        sizes = [wfs[w]["level"] for w in ins]
-        cands = [q for q in range(len(ins)) if sizes[q] == max(sizes)]
-        free = [q for q in cands if LSTAR not in wfs[ins[q]]["legs"]]
-        jx = (free or cands)[0]
-        op = c["op"]
-        term = (0, 0)
-        if op == "FFV1_0":
-            I, O, G = ins
-            ptype, rest = [("ROW", (O, G)), ("COL", (I, G)), ("CUR", (I, O))][jx]
-        elif op == "VVV1_0":
-            ptype, rest = "VVV", (ins[(jx + 1) % 3], ins[(jx + 2) % 3])
+    # ---- wavefunctions (externals + currents) and their layout in the event area
+    wfs, exts = [], []
+    off = 0
+    for o in plan["objects"]:
+        legs = tuple(sorted(o["legs"]))
+        w = {"legs": legs, "level": len(legs), "nv": 1 << len(legs), "off": off, "mask": sum(1 << l for l in legs),
+             "ext": o["ext"], "terms": o["terms"], "mass": o.get("mass", "ZERO"), "width": o.get("width", "ZERO")}
+        off += 2 + 4 * w["nv"]
+        if o["ext"] is not None:
+            exts.append({"call": o["ext"], "out": len(wfs)})
+            w["finish"] = "none"
         else:
-            ptype = "VVVV"
-            others = [q for q in range(4) if q != jx]
-            rest = tuple(ins[q] for q in others)
-            pos = {q + 1: others.index(q) for q in others}   # vertex position -> index into `rest`
-            enc = []
-            for sign, pa, pb in QUARTIC[op[4]]:
-                if jx + 1 in pa:
-                    vec, dot = [q for q in pa if q != jx + 1][0], pb
-                else:
-                    vec, dot = [q for q in pb if q != jx + 1][0], pa
-                enc.append((0x40 if sign < 0 else 0) | pos[vec] << 4 | pos[dot[0]] << 2 | pos[dot[1]])
-            term = tuple(enc)
-        coup, neg = ir["couplings"].index(c["coup"]), 1 if c.get("coup_sign", 1) < 0 else 0
-        key = (ptype, rest, term, coup, neg)
-        if key not in pair_index:
-            legs = tuple(sorted(set().union(*[wfs[w]["legs"] for w in rest])))
-            pair_index[key] = len(pairs)
-            pairs.append(dict(type=ptype, rest=rest, term=term, coup=coup, neg=neg, legs=legs, nv=1 << len(legs)))
-        amp_rows.append(dict(am=am, x=ins[jx], pair=pair_index[key]))
+            kinds = {"FFV1_1": "o", "FFV1_2": "i"}
+            w["finish"] = kinds.get(o["terms"][0]["op"], "g")
+            assert all(kinds.get(t["op"], "g") == w["finish"] for t in o["terms"])
+        wfs.append(w)
+    maxlevel = max(w["level"] for w in wfs)
+    # ---- pair objects; the small ones (<= PERSIST variants, inputs ready) join the currents' phases and stay
+    pairs = []
+    for p in plan["pairs"]:
+        legs = tuple(sorted(p["legs"]))
+        pr = {"legs": legs, "nv": 1 << len(legs), "terms": p["terms"], "finish": "none"}
+        pr["ready"] = 1 + max(wfs[w]["level"] for t in p["terms"] for w in t["in"])
+        pr["persist"] = pr["nv"] <= PERSIST and pr["ready"] <= maxlevel
+        if pr["persist"]:
+            pr["abs_off"] = off
+            off += 4 * pr["nv"]
+        pairs.append(pr)
     assert all(pr["nv"] <= 32 for pr in pairs), "pair objects hold up to 32 helicity variants"
+    wfsize = off
 
-    # batches: a batch closes at a pair boundary when the scratch area or the amplitude buffer (HP_NB rows)
-    # would overflow; pair objects of one kind together, so that the warps of a batch run the same routine
-    scratch = hp_config(ir, "SCRATCH")
-    NB = hp_config(ir, "NB")
-    NCG = hp_config(ir, "NCG")
-    PT = {"ROW": 0, "COL": 1, "CUR": 2, "VVV": 3, "VVVV": 4}
+    by_amp = {k: r["jamp"] for k, r in enumerate(plan["rows"])}   # row index -> [(colour, re, im)]
+    amp_rows = [dict(x=r["x"], pair=r["pair"], row=k) for k, r in enumerate(plan["rows"])]
+
+    def lowered(t):
+        """a plan term as a vertex structure: (structure, inputs, four-gluon codes)"""
+        return _vertex_structure(t["op"], t.get("jx"), t["in"])
+
+    def type_key(obj):
+        return tuple(PT[lowered(t)[0]] for t in obj["terms"])
+
+    # ---- batches: a batch closes at a pair boundary when the scratch area or the amplitude buffer (HP_NB rows)
+    # would overflow; pair objects of one kind together, so that the warps of a batch run the same routines
     by_pair = {}
     for k, r in enumerate(amp_rows):
         by_pair.setdefault(r["pair"], []).append(k)
-    batches, cur_pairs, cur_amps, fill = [], [], [], 0
     sig_id = {}
-    for r in amp_rows:   # colour signature of an amplitude: its JAMP coefficients up to a common phase
-        t = by_amp[r["am"]["call"]["amp"]]
+    for r in amp_rows:   # colour signature of a row: its JAMP coefficients up to a common phase
+        t = by_amp[r["row"]]
         c0 = complex(t[0][1], t[0][2])
-        r["sig"] = sig_id.setdefault(tuple((j, complex(re, im) / c0) for j, re, im in sorted(t)), len(sig_id))
-    # ... and within a kind, pair objects whose amplitudes share a colour signature next to each other (see the JAMP code)
-    chain_rows = hp_chain(ir) and len(used) > HP_UNROLL_MAX_AMPS   # rows of the amplitude buffer = chains, not amplitudes
-
-    def row_key(k):
-        r = amp_rows[k]
-        return (r["sig"], wfs[r["x"]]["legs"], pairs[r["pair"]]["legs"])
-
-    cur_keys = set()
-    for pi in sorted(by_pair, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], min(amp_rows[k]["sig"] for k in by_pair[q]), q)):
+        r["sig"] = sig_id.setdefault(tuple((j, complex(re, im) / c0) for j, re, im in sorted(map(tuple, t))), len(sig_id))
+    batches, cur_pairs, cur_amps, fill = [], [], [], 0
+    transient = [pi for pi in by_pair if not pairs[pi]["persist"]]
+    for pi in sorted(transient, key=lambda q: (type_key(pairs[q]), pairs[q]["nv"], min(amp_rows[k]["sig"] for k in by_pair[q]), q)):
         need = 4 * pairs[pi]["nv"]
         assert need <= scratch and len(by_pair[pi]) <= NB
-        new_keys = {row_key(k) for k in by_pair[pi]}
-        rows_after = len(cur_keys | new_keys) + 4 if chain_rows else len(cur_amps) + len(by_pair[pi])   # + 4: phases that do not chain
-        if fill + need > scratch or rows_after > NB:
+        if fill + need > scratch or len(cur_amps) + len(by_pair[pi]) > NB:
             batches.append((cur_pairs, cur_amps))
             cur_pairs, cur_amps, fill = [], [], 0
-            cur_keys = set()
-        cur_keys |= new_keys
-        pairs[pi]["off"] = fill
+        pairs[pi]["abs_off"] = wfsize + fill
         fill += need
         cur_pairs.append(pi)
         cur_amps += by_pair[pi]
     if cur_amps:
         batches.append((cur_pairs, cur_amps))
-    prow = []
-    for pr in pairs:
-        rest = list(pr["rest"]) + [0] * (3 - len(pr["rest"]))
-        vm = [vmask(pr["legs"], wfs[w]["legs"]) for w in pr["rest"]] + [0] * (3 - len(pr["rest"]))
-        ioff = [wfs[w]["off"] for w in rest]
-        inv = [wfs[w]["nv"] for w in rest]
-        prow.append(f"{{{PT[pr['type']]}, {len(pr['rest'])}, {pr['coup']}, {pr['neg']}, {{{pr['term'][0]}, {pr['term'][1]}}}, "
-                    f"{pr['nv']}, {pr.get('off', 0)}, {{{ioff[0]}, {ioff[1]}, {ioff[2]}}}, {{{inv[0]}, {inv[1]}, {inv[2]}}}, "
-                    f"{{{vm[0]}, {vm[1]}, {vm[2]}}}}}")
+    # rows over persistent pair objects need no pair phase: they fill the free rows of the batches (fewer batches,
+    # fewer block barriers), the rest forms batches of its own
+    resident = [k for pi in sorted(by_pair) if pairs[pi]["persist"] for k in by_pair[pi]]
+    resident.sort(key=lambda k: (amp_rows[k]["x"], amp_rows[k]["pair"]))
+    nfull = -(-(len(resident) + sum(len(a) for _, a in batches)) // NB)       # batches needed for all rows
+    while len(batches) < nfull:
+        batches.append(([], []))
+    share = -(-(len(resident) + sum(len(a) for _, a in batches)) // max(len(batches), 1))   # even filling
+    for bp, ba in batches:
+        while resident and len(ba) < min(NB, share):
+            ba.append(resident.pop(0))
+    for bp, ba in batches:
+        while resident and len(ba) < NB:
+            ba.append(resident.pop(0))
+    assert not resident
+    batches = [b_ for b_ in batches if b_[1]]
 
     def spread(legs, v):
         """helicity-combination bits (within the pass) of variant v of an object over `legs` (ascending)"""
@@ -430,47 +455,52 @@ def emit_hp(ir):
             return range(p * nv // 2, (p + 1) * nv // 2)   # the pass leg is the highest leg = top variant bit
         return range(nv)
 
-    # tensor-core tiles: amplitude(variant of Q, variant of x) = sum_k Q_k x_k is an (nvq x 4)(4 x nvx)
+    # ---- terms, work items, units.  A unit = one (object, helicity variant): its terms are evaluated by one thread
+    # and added up; the last one applies the propagator (currents) and stores.
+    trows, irow, urow = [], [], []
+
+    def term_row(obj, t, out_off):
+        st, ins, q = lowered(t)
+        ins3 = list(ins) + [0] * (3 - len(ins))
+        vm = [vmask(obj["legs"], wfs[w]["legs"]) for w in ins] + [0] * (3 - len(ins))
+        coup = ir["couplings"].index(t["coup"])
+        return (f"{{{PT[st]}, {len(ins)}, {coup}, {phase_of(t)}, {{{q[0]}, {q[1]}}}, {obj['nv']}, {out_off}, "
+                f"{{{', '.join(str(wfs[w]['off']) for w in ins3)}}}, {{{', '.join(str(wfs[w]['nv']) for w in ins3)}}}, "
+                f"{{{vm[0]}, {vm[1]}, {vm[2]}}}, {FINISH[obj['finish']]}, {pidx(obj.get('mass', 'ZERO'))}, {pidx(obj.get('width', 'ZERO'))}}}")
+
+    def add_units(obj, out_off, variants):
+        first = len(trows)
+        masks = []
+        for t in obj["terms"]:
+            st, ins, q = lowered(t)
+            masks.append([vmask(obj["legs"], wfs[w]["legs"]) for w in ins] + [0] * (3 - len(ins)))
+            trows.append(term_row(obj, t, out_off))
+        for v in variants:
+            urow.append(f"{len(irow) | len(obj['terms']) << 24}u")
+            for ti, m in enumerate(masks):
+                irow.append(f"{{{first + ti}, {v}, {{{pext(v, m[0])}, {pext(v, m[1])}, {pext(v, m[2])}}}, 0}}")
+
+    begins = []
+    for lev in range(0, maxlevel + 2):
+        begins.append(len(urow))
+        todo = [(w, w["off"]) for w in wfs if w["ext"] is None and w["level"] == lev]
+        todo += [(pr, pr["abs_off"]) for pr in pairs if pr["persist"] and pr["ready"] == lev]
+        for obj, o_ in sorted(todo, key=lambda q: (len(q[0]["terms"]), type_key(q[0]), FINISH[q[0]["finish"]])):
+            add_units(obj, o_, range(obj["nv"]))
+
+    # ---- tensor-core tiles: amplitude(variant of Q, variant of x) = sum_k Q_k x_k is an (nvq x 4)(4 x nvx)
     # complex product; one work item = 8 variants of Q (rows) x 8 variants of x (columns)
-    irow, trow, brow, urow = [], [], [], []
+    tile_rows, brow = [], []
     ncolor = len(ir["jamp"])
     NJ = -(-ncolor // NCG)
-    # rows of the amplitude buffer: one per amplitude, or (hp_chain) one per chain of amplitudes that the tile phase
-    # adds up: [(index into amp_rows, phase relative to the first member), ...]
-    chain_on = bool(hp_chain(ir)) and len(used) > HP_UNROLL_MAX_AMPS
-    PHASE_CODE = {1: 0, -1: 1, 1j: 2, -1j: 3}
-
-    def first_coef(k):
-        t = by_amp[amp_rows[k]["am"]["call"]["amp"]]
-        return complex(t[0][1], t[0][2])
-
-    batch_rows = []
-    for cur_pairs, cur_amps in batches:
-        rows, index = [], {}
-        for k in cur_amps:
-            r = amp_rows[k]
-            key = (r["sig"], wfs[r["x"]]["legs"], pairs[r["pair"]]["legs"]) if chain_on else ("own", k)
-            if key in index:
-                ph = first_coef(k) / first_coef(rows[index[key]][0][0])
-                if ph in PHASE_CODE:
-                    rows[index[key]].append((k, ph))
-                    continue
-                key = ("own", k)
-            index[key] = len(rows)
-            rows.append([(k, 1)])
-        batch_rows.append(rows)
     for p in range(NPASS):
         for bi, (cur_pairs, cur_amps) in enumerate(batches):
-            ib, tb = len(irow), len(trow)
-            for pi in sorted(cur_pairs, key=lambda q: (PT[pairs[q]["type"]], pairs[q]["nv"], q)):
+            ub, tb = len(urow), len(tile_rows)
+            for pi in cur_pairs:
                 pr = pairs[pi]
-                masks = [vmask(pr["legs"], wfs[w]["legs"]) for w in pr["rest"]] + [0] * (3 - len(pr["rest"]))
-                for v in vrange(pr["legs"], pr["nv"], p):
-                    iv = [pext(v, m) for m in masks]
-                    irow.append(f"{{{pi}, {v}, {{{iv[0]}, {iv[1]}, {iv[2]}}}, 0}}")
-            ub = len(urow)
-            for slot, row in enumerate(batch_rows[bi]):
-                r = amp_rows[row[0][0]]
+                add_units(pr, pr["abs_off"], vrange(pr["legs"], pr["nv"], p))
+            for slot, k in enumerate(cur_amps):
+                r = amp_rows[k]
                 xw, pr = wfs[r["x"]], pairs[r["pair"]]
                 assert not set(xw["legs"]) & set(pr["legs"]) and len(xw["legs"]) + len(pr["legs"]) == n
                 qr, xr = vrange(pr["legs"], pr["nv"], p), vrange(xw["legs"], xw["nv"], p)
@@ -479,17 +509,11 @@ def emit_hp(ir):
                         qv, xv = min(8, qr.stop - q0), min(8, xr.stop - x0)
                         rowh = [spread(pr["legs"], q0 + i) if i < qv else 0 for i in range(8)]
                         colh = [spread(xw["legs"], x0 + i) if i < xv else 0 for i in range(8)]
-                        urow.append(f"{{{len(trow)}u, {len(row)}u}}")
-                        for mi, (km, ph) in enumerate(row):   # the members of a chain: same geometry, own objects
-                            mx, mp = wfs[amp_rows[km]["x"]], pairs[amp_rows[km]["pair"]]
-                            assert (mx["legs"], mp["legs"], mx["nv"], mp["nv"]) == (xw["legs"], pr["legs"], xw["nv"], pr["nv"])
-                            # flags: 1 = adds to the tile before it, 2 = the next tile adds to it, phase code << 2
-                            flags = (1 if mi else 0) | (2 if mi + 1 < len(row) else 0) | PHASE_CODE[ph] << 2
-                            trow.append(f"{{{mp['off']}, {mx['off'] + 2}, {mp['nv']}, {mx['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, {flags}, "
-                                        f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
-            # with chains the warps take UNITS (chains of tiles, d_units) instead of single tiles
-            brow.append(f"{{{ib}, {len(irow)}, {ub if chain_on else tb}, {len(urow) if chain_on else len(trow)}}}")
-    # JAMP code per (batch, colour group).  Amplitudes of a batch that feed the same colours of the group with the
+                        tile_rows.append(f"{{{pr['abs_off']}, {xw['off'] + 2}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
+                                         f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
+            brow.append(f"{{{ub}, {len(urow)}, {tb}, {len(tile_rows)}}}")
+
+    # ---- JAMP code per (batch, colour group).  Rows of a batch that feed the same colours of the group with the
     # same coefficients up to a common phase (+-1, +-i) are summed first and the sum is applied once:
     #   J_c += k_c (A_0 + p_1 A_1 + ...)   instead of   J_c += k_c A_0; J_c += k_c p_1 A_1; ...
     def phase_add(dst, ph, src):
@@ -505,14 +529,13 @@ def emit_hp(ir):
     for bi, (cur_pairs, cur_amps) in enumerate(batches):
         for cg in range(NCG):
             groups = {}   # signature within the colour group -> [(slot, phase relative to the group's first amplitude)]
-            for slot, row in enumerate(batch_rows[bi]):
-                k = row[0][0]   # the first member of a chain carries its JAMP coefficients
-                terms = [(j - cg * NJ, complex(re, im)) for j, re, im in by_amp[amp_rows[k]["am"]["call"]["amp"]] if j // NJ == cg]
+            for slot, k in enumerate(cur_amps):
+                terms = [(j - cg * NJ, complex(re, im)) for j, re, im in by_amp[k] if j // NJ == cg]
                 if not terms:
                     continue
                 unit = all(c in (1, -1, 1j, -1j) for _, c in terms)
                 c0 = terms[0][1] if unit else 1.0
-                sig = tuple((jl, c / c0) for jl, c in sorted(terms)) if unit else ("own", slot)
+                sig = tuple((jl, c / c0) for jl, c in sorted(terms, key=lambda q: q[0])) if unit else ("own", slot)
                 groups.setdefault(sig, []).append((slot, c0, terms))
             stm = []
             for sig, members in groups.items():
@@ -529,12 +552,22 @@ def emit_hp(ir):
                 stm.append("{ " + " ".join(body) + " }")
                 jamp_terms += len(members) - 1 + len(terms0)
             jamp_cases[cg].append(f"      case {bi}: {{ " + "\n        ".join(stm) + " } break;")
-    tables += "\n" + both("mf::HpPair", "pairs", max(len(prow), 1), ",\n  ".join(prow) if prow else "{0}", const=not big)
-    tables += "\n" + both("mf::HpPairItem", "pair_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0, {0, 0, 0}, 0}", const=False)
-    tables += "\n" + both("mf::HpTile", "tiles", max(len(trow), 1), ",\n  ".join(trow) if trow else "{0}", const=len(trow) * 32 <= 24576)
-    tables += "\n" + both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}")
-    if chain_on:
-        tables += "\n" + both("uint2", "units", max(len(urow), 1), ", ".join(urow) if urow else "{0u, 0u}", const=False)
+
+    # ---- tables
+    L = []
+    L.append(both("mf::HpWf", "wf", len(wfs), ", ".join(f"{{{w['off']}u, {w['nv']}, {w['mask']}}}" for w in wfs)))
+    ext_by_leg = sorted(exts, key=lambda x: x["call"]["leg"])
+    assert [x["call"]["leg"] for x in ext_by_leg] == list(range(n))
+    L.append(both("mf::HpExt", "ext", n, ", ".join(
+        f"{{{HP_TYPES[x['call']['op']]}, {x['call']['leg']}, {x['call']['nsf']}, {pidx(x['call']['mass'])}, {x['out']}}}"
+        for x in ext_by_leg)))
+    L.append(both("mf::HpTerm", "terms", max(len(trows), 1), ",\n  ".join(trows) if trows else "{0}", const=not big))
+    L.append(both("mf::HpWorkItem", "work_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0, {0, 0, 0}, 0}", const=False))
+    L.append(both("unsigned", "units", max(len(urow), 1), ", ".join(urow) if urow else "0u", const=False))
+    L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
+    L.append(both("mf::HpTile", "tiles", max(len(tile_rows), 1), ",\n  ".join(tile_rows) if tile_rows else "{0}", const=len(tile_rows) * 32 <= 24576))
+    L.append(both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}"))
+    tables = "\n".join(L)
 
     A = ["    switch (cg) {"]
     for cg in range(NCG):
@@ -546,7 +579,7 @@ def emit_hp(ir):
         A.append("      break;")
     A.append("    default: break;")
     A.append("    }")
-    unroll = len(used) <= HP_UNROLL_MAX_AMPS
+    unroll = len(plan["rows"]) <= HP_UNROLL_MAX_AMPS and not reduced
     cmode = "thread" if unroll else hp_colour_mode(ir, NCG)
     ncp = -(-ncolor // 8) * 8
     if cmode == "thread":
@@ -570,32 +603,40 @@ def emit_hp(ir):
         tables += "\n" + both("double", "cfsym", ncp * ncp, ", ".join(vals), const=False)
     else:
         tables += "\n" + both("double", "cfsym", 1, "0.0", const=False)
-    # straight-line flavour of the same phase for short amplitude lists
+    # straight-line flavour of the amplitude phase for short amplitude lists (whole vertices per helicity combination)
     U = ["    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(len(ir["jamp"]))) + ";",
          "    cxd a[6], b[6], c[6], d[6];"]
     if unroll:
-        for am in used:
-            c = am["call"]
-            for q, w in enumerate(am["in"]):
-                U.append(f"    mf::hp_load_amp<Proc>(wf_e, vtab, h, {w}, {'abcd'[q]});")
+        cur = {}
+        ids = iter(range(len(wfs)))
+        for c in ir["calls"]:      # wavefunction ids = the order of the writes, as in hp_plan_from_ir
+            if "amp" not in c:
+                cur[c["out"]] = next(ids)
+                continue
+            if not any(k == c["amp"] for terms in ir["jamp"] for k, _, _ in terms):
+                continue
+            for q, s in enumerate(c["in"]):
+                U.append(f"    mf::hp_load_amp<Proc>(wf_e, vtab, h, {cur[s]}, {'abcd'[q]});")
             op = c["op"]
             fn = f"VVVV_0<{op[4]}>" if op.startswith("VVVV") else op
-            args = ", ".join("abcd"[: len(am["in"])])
+            args = ", ".join("abcd"[: len(c["in"])])
             U.append(f"    {{ const cxd amp = mf::{fn}({args}, {_coup_expr(ir, c)});")
-            for j, re, im in by_amp[c["amp"]]:
-                U.append("      " + _jamp_update(j, re, im, "amp"))
+            for j, terms in enumerate(ir["jamp"]):
+                for k, re, im in terms:
+                    if k == c["amp"]:
+                        U.append("      " + _jamp_update(j, float(re), float(im), "amp"))
             U.append("    }")
         U.append(_emit_colour(ir))
     else:
         U.append("    return 0.0;  // not used: the amplitudes of this process run on the tensor cores")
+    nunits_cur = begins[-1]
     return tables, "\n".join(A), C, "\n".join(U), dict(
-        wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=len(items), namps=len(used), unroll=unroll,
-        nbatch=len(batches), npairs=len(pairs), nitems_pair=len(irow), ntiles=len(trow), ncg=1 if unroll else NCG, jamp_terms=jamp_terms,
-        npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
-        colour_denom=float(den[0]),
-        nb=max(len(rows) for rows in batch_rows) if batch_rows else 1, chain=1 if chain_on else 0,
-        nrows=sum(len(rows) for rows in batch_rows),
-        scratch=max(max((pairs[pi]["off"] + 4 * pairs[pi]["nv"] for pi in b_[0]), default=0) for b_ in batches) if batches else 0)
+        wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=nunits_cur, namps=len(plan["rows"]), unroll=unroll,
+        nbatch=len(batches), npairs=len(pairs), nitems_pair=len(urow) - nunits_cur, ntiles=len(tile_rows), ncg=1 if unroll else NCG,
+        jamp_terms=jamp_terms, npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
+        colour_denom=float(den[0]), reduced=reduced, nterms=len(trows),
+        nb=max(len(a_) for _, a_ in batches) if batches else 1,
+        scratch=max((pairs[pi]["abs_off"] - wfsize + 4 * pairs[pi]["nv"] for b_ in batches for pi in b_[0]), default=0))
 
 
 def _emit_colour_groups(ir, ncg, nj, nh):
@@ -672,10 +713,6 @@ def emit_process_source(ir, block=None, minblocks=None):
 
     hp_tables, hp_jamp, hp_colour, hp_unrolled, hp = emit_hp(ir)
     hp_unroll = 'true' if hp['unroll'] else 'false'
-    # only emitted when chains are on, so that the default sources stay as they were measured
-    hp_chain_members = ("\n  // chains of tiles accumulate in the tensor-core accumulators (hp_mma_chains); the warps take units = chains\n"
-                        "  static constexpr bool HP_CHAIN = true;\n"
-                        "  MF_DEV static uint2 unit(int i) { return MF_TAB(units)[i]; }") if hp['chain'] else ""
     hp_scratch_n = 0 if hp['unroll'] else hp['scratch']
     hp_nb = 0 if hp['unroll'] else hp['nb']
     hp_ncg = hp['ncg']
@@ -741,7 +778,7 @@ struct Proc {{
   static constexpr int HP_THREADS = HP_E * HP_NHP * HP_NCG;                // threads per block
   // tile descriptors per warp and trip (x HP_E tiles in flight): 2 tiles in flight measured best -- more only adds
   // padded tiles at the end of a batch (g g > t t~ g g: 17.7e6 events/s with 2, 16.5e6 with 4, 14.5e6 with 8)
-  static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 2)) // hp_e)};{hp_chain_members}
+  static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 2)) // hp_e)};
   // colour contraction: 0 in-thread, 1 generated code over colour groups, 2 tensor cores, 3 CUDA-core loop
   // (2 and 3 read the block-symmetrised matrix d_cfsym and JAMP planes of HP_PLANE doubles per colour)
   static constexpr int HP_COLOUR = {hp['cmode']}, HP_NCP = {hp['ncp']}, HP_PLANE = HP_NHP + 4;
@@ -756,12 +793,11 @@ struct Proc {{
   MF_DEV static const double* cfsym() {{ return MF_TAB(cfsym); }}
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
-  MF_DEV static mf::HpItem item(int i) {{ return mf::hp_fetch32(&MF_TAB(items)[i]); }}
+  MF_DEV static mf::HpTerm term(int i) {{ return mf::hp_fetch32(&MF_TAB(terms)[i]); }}
+  MF_DEV static mf::HpWorkItem work_item(int i) {{ return MF_TAB(work_items)[i]; }}  // one 8-byte load
+  MF_DEV static unsigned unit(int i) {{ return MF_TAB(units)[i]; }}
   MF_DEV static int level_begin(int L) {{ return MF_TAB(level_begin)[L]; }}
   MF_DEV static const mf::HpTile* tile(int i) {{ return &MF_TAB(tiles)[i]; }}
-  MF_DEV static mf::HpPair pair(int i) {{ return mf::hp_fetch32(&MF_TAB(pairs)[i]); }}
-  MF_DEV static mf::HpPairItem pair_item(int i) {{ return MF_TAB(pair_items)[i]; }}  // one 8-byte load
-  MF_DEV static mf::HpPairItem cur_item(int i) {{ return MF_TAB(cur_items)[i]; }}
   MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
   // JAMP updates of batch `b` for colour group `cg` (warp-uniform switches): ab = the event's amplitude
   // buffer at this thread's helicity combination, row r at ab[r * HP_NHP]; JAMP registers addressed statically

@@ -57,69 +57,59 @@ struct HpExt {
   unsigned short out;
 };
 
-// Amplitude phase.  Every amplitude is written as  amp = sum_k x[2+k] * Q[k]  where x is its input
-// with the most legs and Q ("pair object") is the rest of the vertex contracted once per helicity
-// variant of ITS legs, with -i*COUP and the metric signs folded in:
-//   FFV1_0(I,O,G):  x=I: Q = Obar Gslash (row)   x=O: Q = Gslash I (column)   x=G: Q = current(I,O)
-//   VVV1_0(1,2,3):  Q = three-gluon vertex contracted with the two other legs (cyclic order)
-//   VVVVk_0:        Q = contact term contracted with the three other legs
+// Vertices.  Every vertex is evaluated as a NUMERATOR in dual form: with one of its lines left open,
+//   Q[k] = -i COUP (vertex contracted with its other lines)_k,   metric signs folded in,
+// so that closing the open line with a wavefunction x gives the amplitude  amp = sum_k x[2+k] Q[k]  and a current is
+// the same numerator times its propagator (hp_unit below):
+//   ROW  (O, G):    Obar Gslash            FFV1_1(O, G)   | FFV1_0 closed with x = I
+//   COL  (I, G):    Gslash I               FFV1_2(I, G)   | FFV1_0 closed with x = O
+//   CUR  (I, O):    Obar gamma^mu I        FFV1P0_3(I, O) | FFV1_0 closed with x = G
+//   VVV  (V2, V3):  three-gluon vertex     VVV1P0_1       | VVV1_0, the other two lines in cyclic order
+//   VVVV (3 lines): contact term           VVVVkP0_1      | VVVVk_0
 // The reference evaluates the whole vertex for each of the 2^n helicity combinations
-// (matrix_method_python.inc:99-102); here the vertex costs 2^|legs(Q)| evaluations and each of the
-// 2^n combinations only a 4-term complex dot product.
-enum HpPairType : unsigned char { HP_Q_ROW = 0, HP_Q_COL = 1, HP_Q_CUR = 2, HP_Q_VVV = 3, HP_Q_VVVV = 4 };
+// (matrix_method_python.inc:99-102); here a numerator costs 2^|its legs| evaluations and each of the 2^n
+// combinations of an amplitude only a 4-term complex dot product (the tensor-core tiles below).
+enum HpVertex : unsigned char { HP_Q_ROW = 0, HP_Q_COL = 1, HP_Q_CUR = 2, HP_Q_VVV = 3, HP_Q_VVVV = 4 };
+enum HpFinish : unsigned char { HP_F_NONE = 0, HP_F_G = 1, HP_F_O = 2, HP_F_I = 3 };
 
-// (32 bytes, fetched with two 16-byte loads: hp_fetch32)
-struct alignas(16) HpPair {
-  unsigned char type, nin, coup, coup_neg;
-  unsigned char term[2];       // HP_Q_VVVV: sign<<6 | vector<<4 | dotA<<2 | dotB  (indices into the inputs)
-  unsigned short nv;           // helicity variants of the object
-  unsigned short off;          // offset in the event's scratch area (cxd)
-  unsigned short in_off[3];    // inputs: offset of the wavefunction block in the event's area
-  unsigned short in_nv[3];
-  unsigned char vmask[3];      // bits of the object's variant index that form the input's variant index
-  unsigned char pad[7];
+// One term of an object (current or pair object = vertex numerator).  An object is the sum of its terms,
+//   sum_t phase_t * numerator_t,   phase in {1, -1, i, -i}
+// -- sub-diagrams over the same legs with linearly dependent colour factors (madflow_b200/recursion.py), all sharing
+// one propagator -- and is stored once per helicity variant of its legs.  (32 bytes, fetched with two 16-byte loads.)
+struct alignas(16) HpTerm {
+  unsigned char type, nin, coup, phase;   // phase code 0..3 = 1, -1, i, -i (the sign of the coupling folded in)
+  unsigned char term[2];                  // HP_Q_VVVV: sign<<6 | vector<<4 | dotA<<2 | dotB  (indices into the inputs)
+  unsigned short out_nv, out_off;         // the object: helicity variants, offset in the event area (cxd)
+  unsigned short in_off[3], in_nv[3];     // inputs: offset of the wavefunction block in the event area, variants
+  unsigned char vmask[3];                 // bits of the object's variant index that form the input's variant index
+  unsigned char finish;                   // HpFinish: none (numerator), or the propagator of a g / o / i current
+  signed char mass_idx, width_idx;        // < 0: ZERO
+  unsigned char pad[4];
 };
-static_assert(sizeof(HpPair) == 32, "HpPair is fetched as two 16-byte words");
+static_assert(sizeof(HpTerm) == 32, "HpTerm is fetched as two 16-byte words");
 
-struct alignas(8) HpPairItem {  // work item of a pair phase: (object, helicity variant) and, precomputed, the
-  unsigned short pair;          // variants of the object's inputs that belong to it
-  unsigned char v, iv[3];
+struct alignas(8) HpWorkItem {  // (term, helicity variant of the object) and, precomputed, the variants of the term's
+  unsigned short term;          // inputs that belong to it.  A UNIT = the work items of one (object, variant), stored
+  unsigned char v, iv[3];       // consecutively; unit descriptor = first item | number of items << 24.
   unsigned short pad;
 };
-static_assert(sizeof(HpPairItem) == 8, "HpPairItem is fetched with one 8-byte load");
+static_assert(sizeof(HpWorkItem) == 8, "HpWorkItem is fetched with one 8-byte load");
 
 // One tensor-core work item of the amplitude phase: rows = 8 helicity variants of the pair object Q
 // (from variant q0), columns = 8 variants of the wavefunction x (from x0); element (r, c) is the
 // amplitude of helicity combination rowh[r] | colh[c] and goes to row `slot` of the amplitude buffer.
 struct alignas(16) HpTile {
-  unsigned short q, x;          // component 0 of Q in the event's scratch area / of x in its wavefunction area (cxd)
+  unsigned short q, x;          // component 0 of Q and of x in the event area (cxd)
   unsigned short qnv, xnv;      // component strides = helicity variants of the objects
   unsigned char q0, x0;         // first variant of the tile
   unsigned char qvalid, xvalid; // rows / columns in use (the rest is padding)
-  unsigned short slot, flags;   // flags (chains of tiles, codegen.hp_chain): 1 = adds to the tile before it, 2 = the next
-  unsigned char rowh[8], colh[8];   // tile adds to it, bits 2-3 = phase of this member (1, -1, i, -i); 0 = a tile on its own
+  unsigned short slot, flags;   // row of the amplitude buffer; flags unused
+  unsigned char rowh[8], colh[8];
 };
 
-// does the process use chains of tiles (Proc::HP_CHAIN is only emitted when it does)
-template <class P, class = void>
-struct hp_has_chain : std::false_type {};
-template <class P>
-struct hp_has_chain<P, std::void_t<decltype(P::HP_CHAIN)>> : std::true_type {};
-
-struct HpBatch {   // one (helicity pass, batch): its pair-object work items and its tiles
-  int item_begin, item_end, tile_begin, tile_end;
+struct HpBatch {   // one (helicity pass, batch): the units of its pair objects and its tiles
+  int unit_begin, unit_end, tile_begin, tile_end;
 };
-
-struct alignas(16) HpItem {
-  unsigned char type, nin;
-  signed char mass_idx, width_idx;   // < 0: ZERO
-  unsigned char coup, coup_neg;
-  unsigned short out_off, out_nv;    // output wavefunction block (offset in the event's area, variants)
-  unsigned short in_off[3], in_nv[3];
-  unsigned char vmask[3];            // bits of the output's variant index that form the input's variant index
-  unsigned char pad[7];
-};
-static_assert(sizeof(HpItem) == 32, "HpItem is fetched as two 16-byte words");
 
 // a 32-byte table row with two 16-byte loads instead of one load per field
 template <class T>
@@ -172,56 +162,6 @@ MF_DEV void hp_load(const cxd* blk, int nv, int v, cxd out[6]) {
   hp_load_comp(blk, nv, v, out);
 }
 
-// phase 2: work item (current, output variant, variants of its inputs) of the event whose area is wf_e
-template <class P>
-MF_DEV void hp_current(const HpPairItem w, const double* par, const cxd* coup_e, cxd* wf_e) {
-  const HpItem it = P::item(w.pair);
-  const int v = w.v;
-  cxd a[6], b[6], c[6], r[6];
-  hp_load(wf_e + it.in_off[0], it.in_nv[0], w.iv[0], a);
-  hp_load(wf_e + it.in_off[1], it.in_nv[1], w.iv[1], b);
-  if (it.nin > 2) hp_load(wf_e + it.in_off[2], it.in_nv[2], w.iv[2], c);
-  cxd cp = coup_e[it.coup];
-  if (it.coup_neg) cp = -cp;
-  const double M = it.mass_idx < 0 ? 0.0 : par[it.mass_idx];
-  const double W = it.width_idx < 0 ? 0.0 : par[it.width_idx];
-  switch (it.type) {
-    case HP_FFV1_1: FFV1_1(a, b, cp, M, W, r); break;
-    case HP_FFV1_2: FFV1_2(a, b, cp, M, W, r); break;
-    case HP_FFV1P0_3: FFV1P0_3(a, b, cp, M, W, r); break;
-    case HP_VVV1P0_1: VVV1P0_1(a, b, cp, M, W, r); break;
-    case HP_VVVV1P0_1: VVVVP0_1<1>(a, b, c, cp, M, W, r); break;
-    case HP_VVVV3P0_1: VVVVP0_1<3>(a, b, c, cp, M, W, r); break;
-    default: VVVVP0_1<4>(a, b, c, cp, M, W, r); break;
-  }
-  cxd* o = wf_e + it.out_off;
-  const int nv = it.out_nv;
-  if (v == 0) o[0] = r[0], o[1] = r[1];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) o[2 + hp_slot(k, nv, v)] = r[2 + k];
-}
-
-// vtab[mask * NCOMB + h]: the helicity variant, of an object over the leg set `mask`, that belongs to
-// helicity combination h (= the bits of h at the positions in mask, packed).  Filled once per block.
-template <class P>
-MF_DEV void hp_fill_vtab(int idx, unsigned char* vtab) {
-  const int mask = idx / P::NCOMB, h = idx - mask * P::NCOMB;
-  int out = 0, pos = 0;
-  for (int b = 0; b < P::NEXT; ++b)
-    if (mask & (1 << b)) {
-      out |= ((h >> b) & 1) << pos;
-      ++pos;
-    }
-  vtab[idx] = (unsigned char)out;
-}
-
-// wavefunction w as helicity combination h sees it (used by the straight-line flavour)
-template <class P>
-MF_DEV void hp_load_amp(const cxd* wf_e, const unsigned char* vtab, int h, int w, cxd out[6]) {
-  const HpWf d = P::wf(w);
-  hp_load(wf_e + d.off, d.nv, vtab[d.legs * P::NCOMB + h], out);
-}
-
 // K += sign * in[vi] * (in[da] . in[db]) for one term of a four-gluon structure (all indices warp-uniform)
 MF_DEV void hp_quartic_term(unsigned char d, const cxd a[6], const cxd b[6], const cxd c[6], cxd d01, cxd d02, cxd d12,
                             cxd K[4]) {
@@ -244,67 +184,139 @@ MF_DEV void hp_quartic_term(unsigned char d, const cxd a[6], const cxd b[6], con
   }
 }
 
-// pair phase: work item (object, variant, variants of its inputs) of one event -> Q[4] into the scratch area
+// One unit of the current / pair-object phases: (object, helicity variant) of the event whose area is ev_e.  The
+// terms of the object are evaluated in turn and added up; the last one applies the propagator (currents) and stores.
 template <class P>
-MF_DEV void hp_pair(const HpPairItem item, const cxd* coup_e, const cxd* wf_e, cxd* scratch_e) {
-  const HpPair pr = P::pair(item.pair);
-  const int v = item.v;
-  cxd a[6], b[6], c[6];
-  hp_load_comp(wf_e + pr.in_off[0], pr.in_nv[0], item.iv[0], a);
-  hp_load_comp(wf_e + pr.in_off[1], pr.in_nv[1], item.iv[1], b);
-  cxd cp = coup_e[pr.coup];
-  if (pr.coup_neg) cp = -cp;
-  const cxd f = mul_mi(cp);  // -i * COUP
-  cxd Q[4];
-  switch (pr.type) {
-    case HP_Q_ROW: {  // a = O (F2), b = G
-      cxd X[4];
-      slash_row(a, b, X);
+MF_DEV void hp_unit(const unsigned unit, const double* par, const cxd* coup_e, cxd* ev_e) {
+  const int begin = (int)(unit & 0xffffffu), count = (int)(unit >> 24);
+  cxd Q[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
+  HpTerm t;
+  HpWorkItem it;
+#pragma unroll 1
+  for (int j = 0; j < count; ++j) {
+    it = P::work_item(begin + j);
+    t = P::term(it.term);
+    const cxd* ab = ev_e + t.in_off[0];
+    const cxd* bb = ev_e + t.in_off[1];
+    cxd a[6], b[6];
+    hp_load_comp(ab, t.in_nv[0], it.iv[0], a);
+    hp_load_comp(bb, t.in_nv[1], it.iv[1], b);
+    cxd f = mul_mi(coup_e[t.coup]);  // -i * COUP * phase
+    if (t.phase & 2) f = mul_i(f);
+    if (t.phase & 1) f = -f;
+    switch (t.type) {
+      case HP_Q_ROW: {  // a = O (F2), b = G
+        cxd X[4];
+        slash_row(a, b, X);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) Q[k] = f * X[k];
-    } break;
-    case HP_Q_COL: {  // a = I (F1), b = G
-      cxd Y[4];
-      slash_col(a, b, Y);
+        for (int k = 0; k < 4; ++k) Q[k] = fma_c(f, X[k], Q[k]);
+      } break;
+      case HP_Q_COL: {  // a = I (F1), b = G
+        cxd Y[4];
+        slash_col(a, b, Y);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) Q[k] = f * Y[k];
-    } break;
-    case HP_Q_CUR: {  // a = I (F1), b = O (F2): J^mu with FFV1_0 = -i COUP (J.V)
-      const cxd t0 = a[2] * b[4], t1 = a[3] * b[5], t2 = a[4] * b[2], t3 = a[5] * b[3];
-      const cxd u0 = a[2] * b[5], u1 = a[3] * b[4], u2 = a[4] * b[3], u3 = a[5] * b[2];
-      Q[0] = f * (t0 + t1 + t2 + t3);
-      Q[1] = f * (u0 + u1 - u2 - u3);            // -J1
-      Q[2] = f * mul_i(u0 - u1 - u2 + u3);       // -J2
-      Q[3] = f * (t0 - t1 - t2 + t3);            // -J3
-    } break;
-    case HP_Q_VVV: {  // a = V2, b = V3 of VVV1_0(V1,V2,V3); P1 = -(P2+P3); the only kind that needs the momenta
-      a[0] = wf_e[pr.in_off[0]], a[1] = wf_e[pr.in_off[0] + 1];
-      b[0] = wf_e[pr.in_off[1]], b[1] = wf_e[pr.in_off[1] + 1];
-      const Mom P2 = mom_of(a, 1.0), P3 = mom_of(b, 1.0);
-      const Mom d12 = Mom{-2.0 * P2.e - P3.e, -2.0 * P2.x - P3.x, -2.0 * P2.y - P3.y, -2.0 * P2.z - P3.z};  // P1-P2
-      const Mom d31 = Mom{2.0 * P3.e + P2.e, 2.0 * P3.x + P2.x, 2.0 * P3.y + P2.y, 2.0 * P3.z + P2.z};      // P3-P1
-      const cxd s3 = pdot(d12, b), s2 = pdot(d31, a), s23 = vdot(a, b);
-      const double q[4] = {P2.e - P3.e, P2.x - P3.x, P2.y - P3.y, P2.z - P3.z};
-      const cxd K0 = a[2] * s3 + b[2] * s2 + q[0] * s23;
-      const cxd K1 = a[3] * s3 + b[3] * s2 + q[1] * s23;
-      const cxd K2 = a[4] * s3 + b[4] * s2 + q[2] * s23;
-      const cxd K3 = a[5] * s3 + b[5] * s2 + q[3] * s23;
-      Q[0] = f * K0, Q[1] = -(f * K1), Q[2] = -(f * K2), Q[3] = -(f * K3);
-    } break;
-    default: {  // HP_Q_VVVV: K = sum_t sign_t * in[vec_t] * (in[dotA_t] . in[dotB_t])
-      hp_load_comp(wf_e + pr.in_off[2], pr.in_nv[2], item.iv[2], c);
-      // the three Minkowski products once; each term picks one of them and one vector (warp-uniform)
-      const cxd d01 = vdot(a, b), d02 = vdot(a, c), d12 = vdot(b, c);
-      cxd K[4] = {mk(0, 0), mk(0, 0), mk(0, 0), mk(0, 0)};
-      hp_quartic_term(pr.term[0], a, b, c, d01, d02, d12, K);
-      hp_quartic_term(pr.term[1], a, b, c, d01, d02, d12, K);
-      Q[0] = f * K[0], Q[1] = -(f * K[1]), Q[2] = -(f * K[2]), Q[3] = -(f * K[3]);
-    } break;
+        for (int k = 0; k < 4; ++k) Q[k] = fma_c(f, Y[k], Q[k]);
+      } break;
+      case HP_Q_CUR: {  // a = I (F1), b = O (F2): J^mu with FFV1_0 = -i COUP (J.V)
+        const cxd tp = fma_c(a[5], b[3], a[2] * b[4]), tm = fma_c(a[4], b[2], a[3] * b[5]);  // t0 + t3, t1 + t2
+        const cxd u0 = a[2] * b[5], u1 = a[3] * b[4], u2 = a[4] * b[3], u3 = a[5] * b[2];
+        Q[0] = fma_c(f, tp + tm, Q[0]);
+        Q[1] = fma_c(f, (u0 - u3) + (u1 - u2), Q[1]);          // -J1
+        Q[2] = fma_c(f, mul_i((u0 + u3) - (u1 + u2)), Q[2]);   // -J2
+        Q[3] = fma_c(f, tp - tm, Q[3]);                        // -J3
+      } break;
+      case HP_Q_VVV: {  // a = V2, b = V3 of VVV1_0(V1,V2,V3); P1 = -(P2+P3); the only kind that needs the momenta
+        a[0] = ab[0], a[1] = ab[1], b[0] = bb[0], b[1] = bb[1];
+        const Mom P2 = mom_of(a, 1.0), P3 = mom_of(b, 1.0);
+        const Mom d12 = Mom{-2.0 * P2.e - P3.e, -2.0 * P2.x - P3.x, -2.0 * P2.y - P3.y, -2.0 * P2.z - P3.z};  // P1-P2
+        const Mom d31 = Mom{2.0 * P3.e + P2.e, 2.0 * P3.x + P2.x, 2.0 * P3.y + P2.y, 2.0 * P3.z + P2.z};      // P3-P1
+        const cxd s3 = pdot(d12, b), s2 = pdot(d31, a), s23 = vdot(a, b);
+        const double q[4] = {P2.e - P3.e, P2.x - P3.x, P2.y - P3.y, P2.z - P3.z};
+        const cxd fm = -f;
+        Q[0] = fma_c(f, fma_c(a[2], s3, fma_c(b[2], s2, q[0] * s23)), Q[0]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) Q[k] = fma_c(fm, fma_c(a[2 + k], s3, fma_c(b[2 + k], s2, q[k] * s23)), Q[k]);
+      } break;
+      default: {  // HP_Q_VVVV: K = sum_t sign_t * in[vec_t] * (in[dotA_t] . in[dotB_t])
+        cxd c[6];
+        hp_load_comp(ev_e + t.in_off[2], t.in_nv[2], it.iv[2], c);
+        // the three Minkowski products once; each term picks one of them and one vector (warp-uniform)
+        const cxd d01 = vdot(a, b), d02 = vdot(a, c), d12 = vdot(b, c);
+        cxd K[4] = {mk(0, 0), mk(0, 0), mk(0, 0), mk(0, 0)};
+        hp_quartic_term(t.term[0], a, b, c, d01, d02, d12, K);
+        hp_quartic_term(t.term[1], a, b, c, d01, d02, d12, K);
+        const cxd fm = -f;
+        Q[0] = fma_c(f, K[0], Q[0]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) Q[k] = fma_c(fm, K[k], Q[k]);
+      } break;
+    }
   }
-  cxd* o = scratch_e + pr.off;
-  const int nv = pr.nv;
+  cxd* o = ev_e + t.out_off;
+  const int nv = t.out_nv, v = it.v;
+  if (t.finish == HP_F_NONE) {  // a vertex numerator (pair object): components only
 #pragma unroll
-  for (int k = 0; k < 4; ++k) o[hp_slot(k, nv, v)] = Q[k];
+    for (int k = 0; k < 4; ++k) o[hp_slot(k, nv, v)] = Q[k];
+    return;
+  }
+  // a current: momentum slots = the sum of its inputs', propagator 1 / (P^2 - M(M - iW)) with P = -(sum)
+  cxd w[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    w[k] = ev_e[t.in_off[0] + k] + ev_e[t.in_off[1] + k];
+    if (t.nin > 2) w[k] += ev_e[t.in_off[2] + k];
+  }
+  const Mom Pm = Mom{-w[0].re, -w[1].re, -w[1].im, -w[0].im};
+  const double M = t.mass_idx < 0 ? 0.0 : par[t.mass_idx];
+  const double W = t.width_idx < 0 ? 0.0 : par[t.width_idx];
+  const cxd inv = propagator(mk(1.0, 0.0), Pm, M, W);
+  cxd r[4];
+  if (t.finish == HP_F_G) {  // V^mu = numerator^mu / (P^2 - ..): undo the metric signs of the dual form
+    r[0] = inv * Q[0];
+    const cxd ninv = -inv;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) r[k] = ninv * Q[k];
+  } else {
+    // fermion propagators (FFV1_1 / FFV1_2 of aloha_sm.cuh with i COUP X / den = -Q / den)
+    const cxd ninv = -inv;
+    const double Pp = Pm.e + Pm.z, Pn = Pm.e - Pm.z;
+    const cxd Pa = mk(Pm.x, Pm.y), Pb = mk(Pm.x, -Pm.y);
+    if (t.finish == HP_F_O) {
+      r[0] = ninv * (M * Q[0] - Pp * Q[2] - Pa * Q[3]);
+      r[1] = ninv * (M * Q[1] - Pb * Q[2] - Pn * Q[3]);
+      r[2] = ninv * (M * Q[2] - Pn * Q[0] + Pa * Q[1]);
+      r[3] = ninv * (M * Q[3] + Pb * Q[0] - Pp * Q[1]);
+    } else {
+      r[0] = ninv * (M * Q[0] + Pn * Q[2] - Pb * Q[3]);
+      r[1] = ninv * (M * Q[1] + Pp * Q[3] - Pa * Q[2]);
+      r[2] = ninv * (M * Q[2] + Pp * Q[0] + Pb * Q[1]);
+      r[3] = ninv * (M * Q[3] + Pa * Q[0] + Pn * Q[1]);
+    }
+  }
+  if (v == 0) o[0] = w[0], o[1] = w[1];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[2 + hp_slot(k, nv, v)] = r[k];
+}
+
+// vtab[mask * NCOMB + h]: the helicity variant, of an object over the leg set `mask`, that belongs to
+// helicity combination h (= the bits of h at the positions in mask, packed).  Filled once per block.
+template <class P>
+MF_DEV void hp_fill_vtab(int idx, unsigned char* vtab) {
+  const int mask = idx / P::NCOMB, h = idx - mask * P::NCOMB;
+  int out = 0, pos = 0;
+  for (int b = 0; b < P::NEXT; ++b)
+    if (mask & (1 << b)) {
+      out |= ((h >> b) & 1) << pos;
+      ++pos;
+    }
+  vtab[idx] = (unsigned char)out;
+}
+
+// wavefunction w as helicity combination h sees it (used by the straight-line flavour)
+template <class P>
+MF_DEV void hp_load_amp(const cxd* wf_e, const unsigned char* vtab, int h, int w, cxd out[6]) {
+  const HpWf d = P::wf(w);
+  hp_load(wf_e + d.off, d.nv, vtab[d.legs * P::NCOMB + h], out);
 }
 
 // D += A(8x4) B(4x8) on the FP64 tensor cores.  Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
@@ -357,7 +369,7 @@ __device__ __forceinline__ void hp_mma_tiles(const HpTileWords (&tile)[NT], int 
     const int q = w0.x & 0xffff, x = w0.x >> 16, qnv = w0.y & 0xffff, xnv = w0.y >> 16;
     const int q0 = w0.z & 0xff, x0 = (w0.z >> 8) & 0xff, qvalid = (w0.z >> 16) & 0xff, xvalid = w0.z >> 24;
     const int slot = w0.w & 0xffff;
-    qi[t] = evs + 16u * (P::HP_WFSIZE + q + hp_slot(k, qnv, (q0 + r) & (qnv - 1)));
+    qi[t] = evs + 16u * (q + hp_slot(k, qnv, (q0 + r) & (qnv - 1)));
     xi[t] = evs + 16u * (x + hp_slot(k, xnv, (x0 + r) & (xnv - 1)));
     const int hq = (((r & 4) ? w1.y : w1.x) >> (8 * (r & 3))) & 0xff;
     const unsigned hc = (((k & 2) ? w1.w : w1.z) >> (16 * (k & 1))) & 0xffff;
@@ -395,79 +407,15 @@ __device__ __forceinline__ void hp_mma_tiles(const HpTileWords (&tile)[NT], int 
     }
 }
 
-// Chains of tiles (codegen.hp_chain): a unit = `n` consecutive tile descriptors with the same geometry and destination
-// whose products  phase_m * Q_m . x_m  are added up in the tensor-core accumulators and stored once -- amplitudes of one
-// colour signature and one split of the legs reach the JAMP sums only through their sum.  NT units x E events in flight
-// per warp; `unit[t]` = (first tile, number of tiles), warp-uniform.
-template <class P, int NT>
-__device__ __forceinline__ void hp_mma_chains(const uint2 (&unit)[NT], int lane, unsigned evs) {
-  constexpr int E = P::HP_E;
-  constexpr unsigned EVB = P::HP_EVSTRIDE * 16u;
-  const int r = lane >> 2, k = lane & 3;
-  double cr0[NT][E], cr1[NT][E], ci0[NT][E], ci1[NT][E];
-  unsigned d0[NT], d1[NT];
-  bool s0[NT], s1[NT];
-  unsigned maxlen = 0;
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    maxlen = unit[t].y > maxlen ? unit[t].y : maxlen;
-#pragma unroll
-    for (int e = 0; e < E; ++e) cr0[t][e] = cr1[t][e] = ci0[t][e] = ci1[t][e] = 0.0;
-  }
-#pragma unroll 1
-  for (unsigned m = 0; m < maxlen; ++m) {
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      if (m >= unit[t].y) continue;  // warp-uniform
-      const HpTileWords tw = hp_tile_words(P::tile(unit[t].x + m));
-      const uint4 w0 = tw.w0, w1 = tw.w1;
-      const int q = w0.x & 0xffff, x = w0.x >> 16, qnv = w0.y & 0xffff, xnv = w0.y >> 16;
-      const int q0 = w0.z & 0xff, x0 = (w0.z >> 8) & 0xff, qvalid = (w0.z >> 16) & 0xff, xvalid = w0.z >> 24;
-      const int slot = w0.w & 0xffff, ph = (w0.w >> 18) & 3;
-      const unsigned qi = evs + 16u * (P::HP_WFSIZE + q + hp_slot(k, qnv, (q0 + r) & (qnv - 1)));
-      const unsigned xi = evs + 16u * (x + hp_slot(k, xnv, (x0 + r) & (xnv - 1)));
-      if (m == 0) {  // destination and validity are the same for all members
-        const int hq = (((r & 4) ? w1.y : w1.x) >> (8 * (r & 3))) & 0xff;
-        const unsigned hc = (((k & 2) ? w1.w : w1.z) >> (16 * (k & 1))) & 0xffff;
-        d0[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::HP_NHP + hp_abuf_pos(hq | (hc & 0xff)));
-        d1[t] = evs + 16u * (P::HP_WFSIZE + P::HP_SCRATCH + slot * P::HP_NHP + hp_abuf_pos(hq | (hc >> 8)));
-        s0[t] = r < qvalid && 2 * k < xvalid, s1[t] = r < qvalid && 2 * k + 1 < xvalid;
-      }
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const cxd qa = lds_cxd(qi + e * EVB), xb = lds_cxd(xi + e * EVB);
-        // phase * Q: 1 -> (re, im), -1 -> (-re, -im), i -> (-im, re), -i -> (im, -re)   (warp-uniform)
-        const double pre = (ph & 2) ? ((ph & 1) ? qa.im : -qa.im) : ((ph & 1) ? -qa.re : qa.re);
-        const double pim = (ph & 2) ? ((ph & 1) ? -qa.re : qa.re) : ((ph & 1) ? -qa.im : qa.im);
-        dmma_m8n8k4(cr0[t][e], cr1[t][e], pre, xb.re);
-        dmma_m8n8k4(ci0[t][e], ci1[t][e], pre, xb.im);
-        dmma_m8n8k4(cr0[t][e], cr1[t][e], -pim, xb.im);
-        dmma_m8n8k4(ci0[t][e], ci1[t][e], pim, xb.re);
-      }
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < NT; ++t)
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      if (s0[t]) sts_cxd(d0[t] + e * EVB, cr0[t][e], ci0[t][e]);
-      if (s1[t]) sts_cxd(d1[t] + e * EVB, cr1[t][e], ci1[t][e]);
-    }
-}
-
 // the same tile on the CPU (tests/hostcheck): plain loops over its rows and columns
 template <class P>
-inline void hp_mma_tile_host(const HpTile* tp, const cxd* wf_e, const cxd* scratch_e, cxd* abuf_e) {
+inline void hp_mma_tile_host(const HpTile* tp, const cxd* ev_e, cxd* abuf_e) {
   for (int r = 0; r < tp->qvalid; ++r)
     for (int c = 0; c < tp->xvalid; ++c) {
       cxd amp = mk(0.0, 0.0);
       for (int k = 0; k < 4; ++k)
-        amp = fma_c(scratch_e[tp->q + hp_slot(k, tp->qnv, tp->q0 + r)], wf_e[tp->x + hp_slot(k, tp->xnv, tp->x0 + c)], amp);
-      const int ph = (tp->flags >> 2) & 3;  // member of a chain: phase * amplitude, added to the members before it
-      if (ph & 2) amp = mul_i(amp);
-      if (ph & 1) amp = -amp;
-      cxd& dst = abuf_e[tp->slot * P::HP_NHP + hp_abuf_pos(tp->rowh[r] | tp->colh[c])];
-      dst = (tp->flags & 1) ? dst + amp : amp;
+        amp = fma_c(ev_e[tp->q + hp_slot(k, tp->qnv, tp->q0 + r)], ev_e[tp->x + hp_slot(k, tp->xnv, tp->x0 + c)], amp);
+      abuf_e[tp->slot * P::HP_NHP + hp_abuf_pos(tp->rowh[r] | tp->colh[c])] = amp;
     }
 }
 
@@ -578,12 +526,12 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
   MF_PROF(0);
 #pragma unroll 1
   for (int L = 2; L <= P::HP_MAXLEVEL; ++L) {
-    // work items (current, variant) of this level, from a table that also holds the variants of the inputs
+    // units (object, variant) of this level: the currents and the pair objects that stay in shared memory
     const int begin = P::level_begin(L), total = (P::level_begin(L + 1) - begin) * E;
 #pragma unroll 1
     for (int w = tid; w < total; w += T) {
       const int ii = w / E, e = w - ii * E;
-      hp_current<P>(P::cur_item(begin + ii), par, coup + e * P::NCOUP, ev + e * EVS);
+      hp_unit<P>(P::unit(begin + ii), par, coup + e * P::NCOUP, ev + e * EVS);
     }
     __syncthreads();
   }
@@ -606,27 +554,15 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
 #pragma unroll 1
       for (int bi = 0; bi < P::HP_NBATCH; ++bi) {
         const HpBatch bt = P::batch(pass * P::HP_NBATCH + bi);
-        const int total = (bt.item_end - bt.item_begin) * E;
+        const int total = (bt.unit_end - bt.unit_begin) * E;
 #pragma unroll 1
         for (int w = tid; w < total; w += T) {
           const int ii = w / E, ee = w - ii * E;
-          hp_pair<P>(P::pair_item(bt.item_begin + ii), coup + ee * P::NCOUP, ev + ee * EVS, ev + ee * EVS + P::HP_WFSIZE);
+          hp_unit<P>(P::unit(bt.unit_begin + ii), par, coup + ee * P::NCOUP, ev + ee * EVS);
         }
-        __syncthreads();
+        __syncthreads();   // pair objects complete; the JAMP reads of the batch before are done (amplitude buffer reused)
         MF_PROF(2);
-        if constexpr (hp_has_chain<P>::value) {
-          // every warp takes MT units (chains of tiles) per trip; an index past the end repeats the batch's last unit
-          constexpr int NW = T / 32, MT = P::HP_TILES_IN_FLIGHT;
-          const unsigned evs = (unsigned)__cvta_generic_to_shared(ev);
-          const int last = bt.tile_end - 1;  // with chains the batch's tile range is its range of units
-#pragma unroll 1
-          for (int w = bt.tile_begin + warp; w < bt.tile_end; w += MT * NW) {
-            uint2 un[MT];
-#pragma unroll
-            for (int t = 0; t < MT; ++t) un[t] = P::unit(w + t * NW < last ? w + t * NW : last);
-            hp_mma_chains<P, MT>(un, lane, evs);
-          }
-        } else {
+        {
           // every warp takes MT tiles per trip; an index past the end repeats the batch's last tile
           // (same values stored twice) so that the trips stay straight-line
           constexpr int NW = T / 32, MT = P::HP_TILES_IN_FLIGHT;

@@ -413,7 +413,9 @@ def _coef(c):
 
 
 def generate_ir(n_final_gluons, name=None, root="centroid"):
-    """IR of  g g > t t~ + n_final_gluons g."""
+    """IR of  g g > t t~ + n_final_gluons g.  From two final-state gluons on the IR also carries ir["plan"]: the
+    colour-reduced evaluation plan of the same sum of diagrams (madflow_b200/recursion.py), which the helicity-parallel
+    kernels evaluate instead of the diagram list; the oracle and the reference-style call list do not know it."""
     k = n_final_gluons
     gen = Generator(k)
     n = gen.n
@@ -514,6 +516,10 @@ def generate_ir(n_final_gluons, name=None, root="centroid"):
         "calls": calls, "jamp": jamp, "color_num": nums, "color_denom": dens,
         "color_basis": [list(w) for w in basis],
     }
+    if k >= 2 and root == "centroid":
+        from . import recursion
+
+        ir["plan"] = recursion.build_plan(k, {c["leg"]: c for c in calls if "leg" in c})
     return ir
 
 

@@ -5,19 +5,6 @@
 
 #include MF_PROC_SOURCE
 
-// range of tile descriptors of a batch (with chains of tiles the batch holds a range of units = runs of tiles);
-// templates so that Proc::unit is only named for processes that have it
-template <class P>
-static int hc_tile_begin(const mf::HpBatch& bt) {
-  if constexpr (mf::hp_has_chain<P>::value) return (int)P::unit(bt.tile_begin).x;
-  else return bt.tile_begin;
-}
-template <class P>
-static int hc_tile_end(const mf::HpBatch& bt) {
-  if constexpr (mf::hp_has_chain<P>::value) return (int)(P::unit(bt.tile_end - 1).x + P::unit(bt.tile_end - 1).y);
-  else return bt.tile_end;
-}
-
 extern "C" int hostcheck_smatrix(const double* p, long long nevt, const double* par, const double* coup,
                                  long long coup_stride, double sqh, int only_comb, double* out) {
   for (long long ev = 0; ev < nevt; ++ev) {
@@ -67,7 +54,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
       const int begin = Proc::level_begin(L), total = (Proc::level_begin(L + 1) - begin) * E;
       for (int w = 0; w < total; ++w) {
         const int ii = w / E, e = w - ii * E;
-        mf::hp_current<Proc>(Proc::cur_item(begin + ii), par, cp.data() + e * Proc::NCOUP, evarea.data() + e * EVS);
+        mf::hp_unit<Proc>(Proc::unit(begin + ii), par, cp.data() + e * Proc::NCOUP, evarea.data() + e * EVS);
       }
     }
     std::vector<double> me_h((size_t)E * NH, 0.0);
@@ -82,17 +69,15 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
         std::vector<cxd> J((size_t)T * NJ, mk(0.0, 0.0));
         for (int bi = 0; bi < Proc::HP_NBATCH; ++bi) {
           const mf::HpBatch bt = Proc::batch(pass * Proc::HP_NBATCH + bi);
-          for (int w = 0; w < (bt.item_end - bt.item_begin) * E; ++w) {
+          for (int w = 0; w < (bt.unit_end - bt.unit_begin) * E; ++w) {
             const int ii = w / E, ee = w - ii * E;
-            mf::hp_pair<Proc>(Proc::pair_item(bt.item_begin + ii), cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS,
-                              evarea.data() + ee * EVS + Proc::HP_WFSIZE);
+            mf::hp_unit<Proc>(Proc::unit(bt.unit_begin + ii), par, cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS);
           }
-          // the tiles of the batch in table order (with chains the batch holds a range of units = runs of tiles)
-          const int tile_begin = hc_tile_begin<Proc>(bt), tile_end = hc_tile_end<Proc>(bt);
+          // the tiles of the batch in table order
           for (int ee = 0; ee < E; ++ee)
-            for (int ti = tile_begin; ti < tile_end; ++ti) {
+            for (int ti = bt.tile_begin; ti < bt.tile_end; ++ti) {
               cxd* a_e = evarea.data() + ee * EVS;
-              mf::hp_mma_tile_host<Proc>(Proc::tile(ti), a_e, a_e + Proc::HP_WFSIZE, a_e + Proc::HP_WFSIZE + Proc::HP_SCRATCH);
+              mf::hp_mma_tile_host<Proc>(Proc::tile(ti), a_e, a_e + Proc::HP_WFSIZE + Proc::HP_SCRATCH);
             }
           for (int t = 0; t < T; ++t) {
             const int e = t / (NCG * NHP), cg = (t / NHP) % NCG, h = t % NHP;

@@ -359,27 +359,51 @@ def test_builtin_processes_against_the_independent_generator(irs, k):
     np.testing.assert_allclose(omatrix.smatrix(a, p, sm_params(), EXACT), omatrix.smatrix(b, p, sm_params(), EXACT), rtol=1e-12)
 
 
-@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
 @pytest.mark.parametrize("k", [2, 3])
-def test_tile_chains_on_host(irs, k, monkeypatch):
-    """MADFLOW_B200_HP_CHAIN=1 (default off until measured on the GPU): amplitudes of one colour signature and one
-    split of the legs are added up in the tile phase and stored once.  Tables, unit ranges, phases and the JAMP code
-    of that flavour executed on the CPU against the oracle; fewer rows of the amplitude buffer than amplitudes."""
+def test_colour_reduced_plan_equals_the_diagram_list(irs, k):
+    """madflow_b200/recursion.py: the plan the helicity-parallel kernels evaluate (basis currents = sums of sub-trees
+    with linearly dependent colour, rows = current x basis vertex numerator) against the diagram-by-diagram oracle,
+    through a numpy interpreter of the plan that uses the oracle's HELAS / ALOHA routines -- no CUDA code involved."""
+    import plan_eval
+    from madflow_b200 import recursion
+
+    ir = irs[k]
+    stats = recursion.plan_stats(ir["plan"])
+    namps = len({c["amp"] for c in ir["calls"] if "amp" in c})
+    raw_terms = sum(len(t) for t in ir["jamp"])
+    assert stats["rows"] < 0.45 * namps and stats["jamp_terms"] < 0.35 * raw_terms
+    assert (stats["rows"], stats["jamp_terms"]) == {2: (64, 208), 3: (388, 1768)}[k]
+    # every coefficient of the plan is a unit: the kernels fold it into the coupling (+-1, +-i)
+    coefs = {tuple(t["coef"]) for o in ir["plan"]["objects"] + ir["plan"]["pairs"] for t in o["terms"]}
+    assert coefs <= {(1.0, 0.0), (-1.0, 0.0), (0.0, 1.0), (0.0, -1.0)}
+    npts = 2 if k == 3 else 40
+    p = _points(k, n=npts, seed=21)
+    params = sm_params(alpha_s=0.09 + 0.05 * np.random.default_rng(5).random(npts))
+    np.testing.assert_allclose(plan_eval.smatrix(ir, p, params), omatrix.smatrix(ir, p, params), rtol=1e-13)
+    row = 9
+    one = plan_eval.matrix(ir, p, ir["helicities"][row], params)
+    ref = omatrix.matrix(ir, p, ir["helicities"][row], params)
+    assert np.max(np.abs(one - ref) / np.maximum(np.abs(ref), 1e-6 * np.max(np.abs(ref)))) < 1e-9
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+def test_diagram_list_flavour_on_host(irs, monkeypatch):
+    """MADFLOW_B200_HP_REDUCE=0: the kernels evaluate the IR's diagram list (single-term objects, one row per
+    amplitude) -- the A/B partner of the colour-reduced plan and the path of every IR that carries no plan."""
     import hostcheck as hc
 
-    monkeypatch.setenv("MADFLOW_B200_HP_CHAIN", "1")
-    ir = process_ir.clone(irs[k])
-    ir["name"] += "_chain"
+    monkeypatch.setenv("MADFLOW_B200_HP_REDUCE", "0")
+    ir = process_ir.clone(irs[2])
+    ir["name"] += "_diagrams"
     info = codegen.emit_hp(ir)[4]
-    assert info["chain"] == 1
-    monkeypatch.delenv("MADFLOW_B200_HP_CHAIN")
-    plain = codegen.emit_hp(irs[k])[4]
-    assert plain["chain"] == 0 and info["ntiles"] == plain["ntiles"] and info["jamp_terms"] < plain["jamp_terms"]
-    monkeypatch.setenv("MADFLOW_B200_HP_CHAIN", "1")
+    monkeypatch.delenv("MADFLOW_B200_HP_REDUCE")
+    red = codegen.emit_hp(irs[2])[4]
+    assert not info["reduced"] and red["reduced"] and info["namps"] == 159 and red["namps"] == 64
+    assert red["ntiles"] < 0.5 * info["ntiles"] and red["jamp_terms"] < 0.5 * info["jamp_terms"]
+    monkeypatch.setenv("MADFLOW_B200_HP_REDUCE", "0")
     lib = hc.process(ir)
-    npts = 2 if k == 3 else 5
-    p = _points(k, n=npts, seed=13)
-    a_s = 0.09 + 0.05 * np.random.default_rng(4).random(npts)
+    p = _points(2, n=5, seed=13)
+    a_s = 0.09 + 0.05 * np.random.default_rng(4).random(5)
     params = sm_params(alpha_s=a_s)
     coup = np.stack([params[c] for c in ir["couplings"]])
     ref = omatrix.smatrix(ir, p, params)
