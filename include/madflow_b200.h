@@ -79,7 +79,7 @@ int mf_vegas_blocks(void);
 /* accumulate: t = xjac*f; partial (nblocks, 4+ndim*50): header (see MF_VEGAS_HEADER), histogram of t^2 */
 int mf_vegas_accumulate(const double* d_f, const double* d_xjac, const uint8_t* d_bins, int64_t nevt, int ndim,
                         int with_hist, double* d_partial, int nblocks, void* stream);
-/* the same with t = sum_i d_f[i][e] * d_w[i][e] over nterms <= 8 subprocesses evaluated on the same events
+/* the same with t = sum_i d_f[i][e] * d_w[i][e] over nterms <= 16 subprocesses evaluated on the same events
  * (scripts/madflow_exec.py:444-455); d_f / d_w: host arrays of device pointers                    */
 int mf_vegas_accumulate_sum(int nterms, const double* const* d_f, const double* const* d_w, const uint8_t* d_bins,
                             int64_t nevt, int ndim, int with_hist, double* d_partial, int nblocks, void* stream);

@@ -418,7 +418,8 @@ int mf_vegas_accumulate(const double* d_f, const double* d_xjac, const uint8_t* 
                         int with_hist, double* d_partial, int nblocks, void* stream) {
   if (ndim < 1 || ndim > MF_MAX_DIM) return fail_msg("mf_vegas_accumulate: 1 <= ndim <= 32");
   if (nblocks < 1) return fail_msg("mf_vegas_accumulate: nblocks < 1");
-  const size_t smem = (ndim * VEGAS_BINS + 24) * sizeof(double);
+  const size_t smem = accumulate_smem(ndim);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   accumulate_kernel<<<nblocks, ACC_BLOCK, smem, (cudaStream_t)stream>>>(d_f, d_xjac, d_bins, nevt, ndim, with_hist,
                                                                         d_partial);
   return check_launch("accumulate_kernel");
@@ -427,12 +428,13 @@ int mf_vegas_accumulate(const double* d_f, const double* d_xjac, const uint8_t* 
 int mf_vegas_accumulate_sum(int nterms, const double* const* d_f, const double* const* d_w, const uint8_t* d_bins,
                             int64_t nevt, int ndim, int with_hist, double* d_partial, int nblocks, void* stream) {
   if (ndim < 1 || ndim > MF_MAX_DIM) return fail_msg("mf_vegas_accumulate_sum: 1 <= ndim <= 32");
-  if (nterms < 1 || nterms > ACC_MAX_TERMS) return fail_msg("mf_vegas_accumulate_sum: 1 <= nterms <= 8");
+  if (nterms < 1 || nterms > ACC_MAX_TERMS) return fail_msg("mf_vegas_accumulate_sum: 1 <= nterms <= 16");
   if (nblocks < 1) return fail_msg("mf_vegas_accumulate_sum: nblocks < 1");
   AccTerms t;
   t.n = nterms;
   for (int i = 0; i < ACC_MAX_TERMS; ++i) t.f[i] = i < nterms ? d_f[i] : nullptr, t.w[i] = i < nterms ? d_w[i] : nullptr;
-  const size_t smem = (ndim * VEGAS_BINS + 24) * sizeof(double);
+  const size_t smem = accumulate_smem(ndim);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(accumulate_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   accumulate_sum_kernel<<<nblocks, ACC_BLOCK, smem, (cudaStream_t)stream>>>(t, d_bins, nevt, ndim, with_hist, d_partial);
   return check_launch("accumulate_sum_kernel");
 }
@@ -455,8 +457,16 @@ int mf_event_histogram(const double* d_mom, const double* d_w1, const double* d_
   if (particle < 0 || particle >= nexternal) return fail_msg("mf_event_histogram: particle index out of range");
   if (observable < 0 || observable > OBS_MASS) return fail_msg("mf_event_histogram: unknown observable");
   if (nbins < 1 || nbins > EVH_MAX_BINS || !(hi > lo)) return fail_msg("mf_event_histogram: need 1 <= nbins <= 1022 and lo < hi");
-  event_histogram_kernel<<<grid_for(nevt, EVH_BLOCK, 8), EVH_BLOCK, (nbins + 2) * sizeof(double), (cudaStream_t)stream>>>(
-      d_mom, d_w1, d_w2, nevt, nexternal, particle, observable, lo, nbins / (hi - lo), nbins, d_hist);
+  // per-block partial histograms in a stream-ordered scratch buffer, then a fixed-order sum over the blocks
+  const int nb = nbins + 2;
+  const int blocks = grid_for(nevt, EVH_HIST_BLOCK, 4);
+  double* partial = nullptr;
+  cudaError_t err = cudaMallocAsync(&partial, (size_t)blocks * nb * sizeof(double), (cudaStream_t)stream);
+  if (err != cudaSuccess) return fail("mf_event_histogram scratch", err);
+  event_histogram_kernel<<<blocks, EVH_HIST_BLOCK, (size_t)(EVH_HIST_BLOCK / 32) * nb * sizeof(double), (cudaStream_t)stream>>>(
+      d_mom, d_w1, d_w2, nevt, nexternal, particle, observable, lo, nbins / (hi - lo), nbins, partial);
+  event_histogram_reduce_kernel<<<(nb + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, blocks, nb, d_hist);
+  cudaFreeAsync(partial, (cudaStream_t)stream);
   return check_launch("event_histogram_kernel");
 }
 

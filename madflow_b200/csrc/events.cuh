@@ -39,26 +39,50 @@ MF_DEV int histogram_bin(double v, double lo, double inv_width, int nbins) {
 }
 
 constexpr int EVH_BLOCK = 256;
+constexpr int EVH_HIST_BLOCK = 128;
 constexpr int EVH_MAX_BINS = 1022;
 
-// hist[nbins + 2] += weights; weight of slot i = w1[i] * (w2 ? w2[i] : 1); slots with weight 0 are skipped
-__global__ void __launch_bounds__(EVH_BLOCK) event_histogram_kernel(const double* mom, const double* w1, const double* w2,
-                                                                   long long nevt, int next, int particle, int obs,
-                                                                   double lo, double inv_width, int nbins, double* hist) {
-  extern __shared__ double sh[];
-  for (int i = threadIdx.x; i < nbins + 2; i += blockDim.x) sh[i] = 0.0;
+// partial[block][nbins + 2] = weights of the block's slots per bin; weight of slot i = w1[i] * (w2 ? w2[i] : 1); slots with
+// weight 0 are skipped.  One histogram per warp in shared memory, filled in a fixed order (vegas.cuh::warp_hist_add)
+// and merged in warp order; event_histogram_reduce_kernel then adds the blocks in block order: the result does not
+// depend on scheduling (floating-point atomics did).
+__global__ void __launch_bounds__(EVH_HIST_BLOCK) event_histogram_kernel(const double* mom, const double* w1, const double* w2,
+                                                                        long long nevt, int next, int particle, int obs,
+                                                                        double lo, double inv_width, int nbins, double* partial) {
+  extern __shared__ double sh[];   // [warp][nbins + 2]
+  constexpr int NW = EVH_HIST_BLOCK / 32;
+  const int nb = nbins + 2;
+  for (int i = threadIdx.x; i < NW * nb; i += blockDim.x) sh[i] = 0.0;
   __syncthreads();
+  double* whist = sh + (threadIdx.x >> 5) * nb;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
-    const double w = w2 ? w1[e] * w2[e] : w1[e];
-    if (w == 0.0) continue;
-    const double4 v = reinterpret_cast<const double4*>(mom)[e * next + particle];
-    const double p[4] = {v.x, v.y, v.z, v.w};
-    atomicAdd(&sh[histogram_bin(observable_value(obs, p), lo, inv_width, nbins)], w);
+  const long long rounds = (nevt + stride - 1) / stride;
+  for (long long r = 0; r < rounds; ++r) {
+    const long long e = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double w = 0.0;
+    int bin = 0;
+    if (e < nevt) w = w2 ? w1[e] * w2[e] : w1[e];
+    if (w != 0.0) {
+      const double4 v = reinterpret_cast<const double4*>(mom)[e * next + particle];
+      const double p[4] = {v.x, v.y, v.z, v.w};
+      bin = histogram_bin(observable_value(obs, p), lo, inv_width, nbins);
+    }
+    if (__any_sync(0xffffffffu, w != 0.0)) warp_hist_add(whist, bin, w, w != 0.0);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nbins + 2; i += blockDim.x)
-    if (sh[i] != 0.0) atomicAdd(&hist[i], sh[i]);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    double h = 0.0;
+    for (int wv = 0; wv < NW; ++wv) h += sh[wv * nb + i];
+    partial[(long long)blockIdx.x * nb + i] = h;
+  }
+}
+
+__global__ void event_histogram_reduce_kernel(const double* partial, int nblocks, int nb, double* hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  double h = 0.0;
+  for (int b = 0; b < nblocks; ++b) h += partial[(long long)b * nb + i];
+  hist[i] += h;
 }
 
 // per block: partial[block] = {max |w|, sum |w|, sum w^2} over its slots (the caller reduces the blocks in a fixed

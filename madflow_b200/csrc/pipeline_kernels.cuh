@@ -128,41 +128,54 @@ __global__ void __launch_bounds__(GEN_BLOCK) ps_generate_kernel(const GenArgs a)
   }
 }
 
-constexpr int ACC_BLOCK = 256;
-// t = value(e) = f * xjac; per block: [sum t, sum t^2, #(t != 0), 0] + histogram of t^2 over (dimension, bin)
+constexpr int ACC_BLOCK = 128;
+// shared memory of the accumulation kernels: one histogram per warp + the reduction scratch
+inline size_t accumulate_smem(int ndim) { return ((size_t)(ACC_BLOCK / 32) * ndim * VEGAS_BINS + 24) * sizeof(double); }
+// t = value(e) = f * xjac; per block: [sum t, sum t^2, #(t != 0), 0] + histogram of t^2 over (dimension, bin).
+// Every sum is formed in an order that depends on the launch shape only (warp_hist_add), not on scheduling.
 template <class Value>
 __device__ __forceinline__ void accumulate_block(Value value, const unsigned char* bins, long long nevt, int ndim,
                                                  int with_hist, double* partial) {
-  extern __shared__ double shist[];  // ndim*50, then 3*8 for the reduction
-  double* red = shist + ndim * VEGAS_BINS;
-  for (int i = threadIdx.x; i < ndim * VEGAS_BINS; i += blockDim.x) shist[i] = 0.0;
+  extern __shared__ double shist[];  // [warp][ndim*50], then 3*8 for the reduction
+  constexpr int NW = ACC_BLOCK / 32;
+  const int nh = ndim * VEGAS_BINS;
+  double* red = shist + NW * nh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* whist = shist + warp * nh;
+  for (int i = threadIdx.x; i < NW * nh; i += blockDim.x) shist[i] = 0.0;
   __syncthreads();
   double s1 = 0.0, s2 = 0.0, cnt = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nevt; e += stride) {
-    const double t = value(e);
+  const long long rounds = (nevt + stride - 1) / stride;   // the same trip count for every lane of the warp
+  for (long long r = 0; r < rounds; ++r) {
+    const long long e = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const double t = e < nevt ? value(e) : 0.0;
     const double t2 = t * t;
     s1 += t;
     s2 += t2;
     cnt += (t != 0.0) ? 1.0 : 0.0;
-    if (with_hist && t2 != 0.0)
-      for (int d = 0; d < ndim; ++d) atomicAdd(&shist[d * VEGAS_BINS + bins[(long long)d * nevt + e]], t2);
+    if (with_hist && __any_sync(0xffffffffu, t2 != 0.0))
+      for (int d = 0; d < ndim; ++d)
+        warp_hist_add(whist + d * VEGAS_BINS, t2 != 0.0 ? bins[(long long)d * nevt + e] : 0, t2, t2 != 0.0);
   }
   for (int o = 16; o > 0; o >>= 1) {
     s1 += __shfl_down_sync(0xffffffffu, s1, o);
     s2 += __shfl_down_sync(0xffffffffu, s2, o);
     cnt += __shfl_down_sync(0xffffffffu, cnt, o);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) red[warp] = s1, red[8 + warp] = s2, red[16 + warp] = cnt;
   __syncthreads();
   double* out = partial + (long long)blockIdx.x * (VEGAS_HEADER + ndim * VEGAS_BINS);
   if (threadIdx.x == 0) {
     double a = 0.0, b = 0.0, c = 0.0;
-    for (int w = 0; w < ACC_BLOCK / 32; ++w) a += red[w], b += red[8 + w], c += red[16 + w];
+    for (int w = 0; w < NW; ++w) a += red[w], b += red[8 + w], c += red[16 + w];
     out[0] = a, out[1] = b, out[2] = c, out[3] = 0.0;
   }
-  for (int i = threadIdx.x; i < ndim * VEGAS_BINS; i += blockDim.x) out[VEGAS_HEADER + i] = shist[i];
+  for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+    double h = 0.0;
+    for (int w = 0; w < NW; ++w) h += shist[w * nh + i];   // warp order
+    out[VEGAS_HEADER + i] = h;
+  }
 }
 
 __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const double* f, const double* xjac,
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const double* f, 
 
 // several subprocesses on the same events (madflow_exec.py:444-455: ret += luminosity_i * smatrix_i):
 // t = sum_i f_i * w_i with w_i = xjac * phase-space weight * luminosity_i
-constexpr int ACC_MAX_TERMS = 8;
+constexpr int ACC_MAX_TERMS = 16;   // p p > t t~ j j has 12 subprocesses
 struct AccTerms {
   int n;
   const double* f[ACC_MAX_TERMS];

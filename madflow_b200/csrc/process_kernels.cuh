@@ -117,7 +117,7 @@ struct IntegrandSmem {
   static constexpr int NDIM = 4 * (P::NEXT - 2) + 2;
   static constexpr int QCAP = 2 * P::BLOCK;
   double grid[NDIM * VEGAS_EDGES];
-  double hist[NDIM * VEGAS_BINS];
+  double hist[P::BLOCK / 32][NDIM * VEGAS_BINS];   // one per warp: deterministic accumulation (vegas.cuh::warp_hist_add)
   double qmom[P::NEXT * 4][QCAP];
   double qw[QCAP];      // xjac * phase-space weight
   double qas[QCAP];     // alpha_s
@@ -126,10 +126,13 @@ struct IntegrandSmem {
   double red[3][32];
 };
 
+// `valid`: this thread has an event in `slot` (all threads of a warp must call: the histogram update is a warp
+// collective with a fixed summation order)
 template <class P>
-__device__ __forceinline__ void integrand_process_entry(const IntegrandArgs& a, IntegrandSmem<P>& s, int slot,
+__device__ __forceinline__ void integrand_process_entry(const IntegrandArgs& a, IntegrandSmem<P>& s, int slot, bool valid,
                                                         double& s1, double& s2, double& cnt) {
   constexpr int NDIM = IntegrandSmem<P>::NDIM;
+  if (!valid) slot = 0;
   double m[P::NEXT][4];
 #pragma unroll
   for (int i = 0; i < P::NEXT; ++i)
@@ -144,15 +147,16 @@ __device__ __forceinline__ void integrand_process_entry(const IntegrandArgs& a, 
     for (int k = 0; k < P::coup_power(c); ++k) g *= G;
     coup[c] = mk(P::coup_re(c) * g, P::coup_im(c) * g);
   }
-  const double me = smatrix_event<P>(m, a.u.par, coup, a.u.sqh);
-  const double t = me * s.qw[slot];
+  const double me = valid ? smatrix_event<P>(m, a.u.par, coup, a.u.sqh) : 0.0;
+  const double t = valid ? me * s.qw[slot] : 0.0;
   const double t2 = t * t;
   s1 += t;
   s2 += t2;
-  cnt += 1.0;
+  cnt += valid ? 1.0 : 0.0;
   if (a.u.accumulate_hist) {
+    double* whist = s.hist[threadIdx.x >> 5];
 #pragma unroll 1
-    for (int d = 0; d < NDIM; ++d) atomicAdd(&s.hist[d * VEGAS_BINS + s.qbin[d][slot]], t2);
+    for (int d = 0; d < NDIM; ++d) warp_hist_add(whist + d * VEGAS_BINS, s.qbin[d][slot], t2, valid);
   }
 }
 
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(P::BLOCK, P::MINBLOCKS) integrand_kernel(const
   constexpr int NWARP = B / 32;
 
   for (int i = tid; i < NDIM * VEGAS_EDGES; i += B) s.grid[i] = a.u.d_grid[i];
-  for (int i = tid; i < NDIM * VEGAS_BINS; i += B) s.hist[i] = 0.0;
+  for (int i = tid; i < NWARP * NDIM * VEGAS_BINS; i += B) (&s.hist[0][0])[i] = 0.0;
   __syncthreads();
 
   double s1 = 0.0, s2 = 0.0, cnt = 0.0;
@@ -232,12 +236,12 @@ __global__ void __launch_bounds__(P::BLOCK, P::MINBLOCKS) integrand_kernel(const
     qcount += total;
     __syncthreads();
     if (qcount >= B) {  // at most once per tile: qcount < 2B always
-      integrand_process_entry<P>(a, s, qcount - B + tid, s1, s2, cnt);
+      integrand_process_entry<P>(a, s, qcount - B + tid, true, s1, s2, cnt);
       qcount -= B;
       __syncthreads();
     }
   }
-  if (tid < qcount) integrand_process_entry<P>(a, s, tid, s1, s2, cnt);
+  if (__any_sync(0xffffffffu, tid < qcount)) integrand_process_entry<P>(a, s, tid, tid < qcount, s1, s2, cnt);
 
   // deterministic block reduction of the two sums
 #pragma unroll
@@ -254,7 +258,12 @@ __global__ void __launch_bounds__(P::BLOCK, P::MINBLOCKS) integrand_kernel(const
     for (int wv = 0; wv < NWARP; ++wv) t1 += s.red[0][wv], t2 += s.red[1][wv], t3 += s.red[2][wv];
     out[0] = t1, out[1] = t2, out[2] = t3, out[3] = 0.0;
   }
-  for (int i = tid; i < NDIM * VEGAS_BINS; i += B) out[VEGAS_HEADER + i] = s.hist[i];
+  for (int i = tid; i < NDIM * VEGAS_BINS; i += B) {
+    double h = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < NWARP; ++wv) h += s.hist[wv][i];   // warp order
+    out[VEGAS_HEADER + i] = h;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

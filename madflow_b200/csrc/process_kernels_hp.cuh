@@ -818,7 +818,7 @@ int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
   if (e != cudaSuccess) return fail("smatrix_kernel_hp launch", e);
 
   if (u->skip_accumulate) return 0;  // the caller sums several subprocesses (mf_vegas_accumulate_sum)
-  accumulate_kernel<<<u->nblocks, ACC_BLOCK, (NDIM * VEGAS_BINS + 24) * sizeof(double), st>>>(
+  accumulate_kernel<<<u->nblocks, ACC_BLOCK, accumulate_smem(NDIM), st>>>(
       g.buf.me, g.buf.w, g.buf.bins, g.buf.cap, NDIM, u->accumulate_hist, u->d_partial);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("accumulate_kernel launch", e);

@@ -27,4 +27,30 @@ MF_DEV double vegas_map(const double* edges, double r, int& bin, double& w) {
   return lo + delta * (xn - k);
 }
 
+// Deterministic histogram accumulation.  hist[bin] += v for the lanes of one warp, in a FIXED order: the lanes that
+// hit the same bin are summed by the lowest of them in ascending lane order and the sum is added with a plain store
+// to a histogram that only THIS WARP writes (no floating-point atomics: their order -- and with it the last bits of
+// the VEGAS grid, which the refinement amplifies on a spiky integrand -- changed from run to run).  The warp-private
+// histograms of a block are merged in warp order, the blocks in block order (vegas_reduce_kernel).
+// All 32 lanes must call; `active` = this lane has something to add.
+#ifdef __CUDACC__
+__device__ __forceinline__ void warp_hist_add(double* whist, int bin, double v, bool active) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(full, active ? bin : -1);
+  const int n = __popc(peers);
+  const int nmax = __reduce_max_sync(full, active ? n : 0);
+  double sum = 0.0;
+  unsigned rem = peers;
+  for (int k = 0; k < nmax; ++k) {
+    const int src = rem ? __ffs(rem) - 1 : lane;  // the k-th lane of my group
+    rem &= rem - 1;
+    const double x = __shfl_sync(full, v, src);
+    if (k < n) sum += x;
+  }
+  if (active && lane == __ffs(peers) - 1) whist[bin] += sum;
+  __syncwarp();
+}
+#endif
+
 }  // namespace mf

@@ -1,4 +1,6 @@
-"""The cross-section integrand of scripts/madflow_exec.py:422-470 as ONE fused kernel.
+"""The cross-section integrand of scripts/madflow_exec.py:422-470 evaluated entirely on the device: ONE fused kernel
+in the one-event-per-thread flavour (g g > t t~, .. g), a three-kernel pipeline (generate -> matrix element ->
+accumulate over an event buffer in HBM, csrc/pipeline_kernels.cuh) in the helicity-parallel flavour.
 
     sigma-integrand(xrand) = luminosity(x1, x2, q2) * smatrix(ps(xrand); couplings(alpha_s(q2))) * ps_weight
 
@@ -224,9 +226,9 @@ class MultiProcessIntegrand:
                 raise ValueError("the subprocesses must share the phase space (particles, masses, cuts, frame)")
             if fi.matrix.variant != "hp":
                 fi.matrix.set_variant("hp")   # the kernel pipeline that keeps the events in device memory
-        if len(self.parts) > 8:
+        if len(self.parts) > 16:
             raise ValueError(f"{len(self.parts)} subprocesses: mf_vegas_accumulate_sum takes at most 8 terms per event "
-                             "(ACC_MAX_TERMS in csrc/pipeline_kernels.cuh; p p > t t~ j j needs 12)")
+                             "(ACC_MAX_TERMS in csrc/pipeline_kernels.cuh)")
         self.n_dim, self.nexternal = first.n_dim, first.nexternal
         self.max_events_per_launch = min(fi.max_events_per_launch for fi in self.parts)
         self._common_blocks = None

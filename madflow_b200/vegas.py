@@ -14,7 +14,12 @@ DESIGN.md "VEGAS") on a Philox4x32-10 counter stream (csrc/philox.cuh).
 Two kinds of integrand:
   * any Python callable on torch CUDA tensors: sample kernel -> callable -> accumulate kernel;
   * a `FusedIntegrand` (madflow_b200.integrand): the whole event pipeline including the matrix
-    element runs in one persistent kernel and only the per-block sums come back.
+    element runs on the device (one persistent kernel for the one-event-per-thread flavour, the three-kernel
+    pipeline generate -> matrix element -> accumulate over an event buffer in HBM for the helicity-parallel
+    flavour) and only the per-block sums come back.
+
+Every sum of an iteration is formed in an order that depends on the launch shape only (csrc/vegas.cuh::warp_hist_add,
+fixed-order block reduction): two runs with the same seed give bit-identical grids.
 
 Multi-GPU (one process per GPU, torch.distributed): each rank takes a contiguous slice of the
 iteration's global event range -- the Philox counter is the global event index, so the sample set
@@ -114,13 +119,37 @@ class VegasFlow:
     def compile(self, integrand, compilable=True):
         self.integrand = integrand
 
-    def save_grid(self):
-        return {"divisions": self.divisions.cpu().clone(), "iteration": self.iteration, "seed": self.seed,
-                "history": list(self.history)}
+    def save_grid(self, path=None):
+        """Checkpoint: the grid, the Philox position (seed, iteration) and the iteration history.  With `path` the
+        state is also written as an .npz file; `load_grid(path)` in a later process resumes the very same sequence of
+        samples (the random numbers are counters: key = seed, counter = (event, iteration, dimension))."""
+        state = {"divisions": self.divisions.cpu().clone(), "iteration": self.iteration, "seed": self.seed,
+                 "history": list(self.history), "train": self.train, "n_events": self.n_events}
+        if path is not None:
+            import numpy as np
+
+            np.savez(path, divisions=state["divisions"].numpy(), iteration=self.iteration, seed=self.seed,
+                     history=np.asarray(self.history, dtype=np.float64).reshape(-1, 2), train=self.train,
+                     n_events=self.n_events)
+        return state
 
     def load_grid(self, state):
+        """Restore a checkpoint: a dict from save_grid() or the path of its .npz file."""
+        if isinstance(state, (str, bytes)) or hasattr(state, "__fspath__"):
+            import numpy as np
+
+            with np.load(state) as z:
+                state = {"divisions": torch.from_numpy(z["divisions"].copy()), "iteration": int(z["iteration"]),
+                         "seed": int(z["seed"]), "history": [tuple(map(float, r)) for r in z["history"]],
+                         "train": bool(z["train"]), "n_events": int(z["n_events"])}
+        if tuple(state["divisions"].shape) != tuple(self.divisions.shape):
+            raise ValueError(f"checkpoint grid has shape {tuple(state['divisions'].shape)}, this integrator {tuple(self.divisions.shape)}")
         self.divisions.copy_(state["divisions"].to(self.divisions.device))
-        self.iteration, self.seed, self.history = state["iteration"], state["seed"], list(state["history"])
+        self.iteration, self.seed, self.history = int(state["iteration"]), int(state["seed"]), list(state["history"])
+        if "train" in state:
+            self.train = bool(state["train"])
+        if "n_events" in state:
+            self.n_events = int(state["n_events"])
 
     # -- one iteration
     def _partial_buf(self, nblocks):

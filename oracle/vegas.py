@@ -141,7 +141,7 @@ class Vegas:
 
 
 def make_cross_section(ir, params_fn, sqrts, masses, pt_cut=None, const=None, lab_frame=True,
-                       alpha_s_fn=None, cuts=(), pdf=None, fixed_q2=None):
+                       alpha_s_fn=None, cuts=(), pdf=None, fixed_q2=None, smatrix_fn=None):
     """The integrand of scripts/madflow_exec.py:422-470: ramboflow -> cuts on COM momenta -> boost ->
     alpha_s(q2=(sum mT/2)^2) or frozen -> luminosity * smatrix * wts, zeros at cut events.
     pdf (oracle.pdf.GridPDF): luminosity = sum over the initial states (+ mirrored) of
@@ -169,7 +169,7 @@ def make_cross_section(ir, params_fn, sqrts, masses, pt_cut=None, const=None, la
             full_mt = np.sum(ps.mt(all_ps[:, 2:n, :]), axis=-1)
             q2 = (full_mt / 2.0) ** 2
         params = params_fn(alpha_s_fn(q2)) if alpha_s_fn is not None else params_fn(None)
-        val = om.smatrix(ir, all_ps, params, const)
+        val = (smatrix_fn or om.smatrix)(ir, all_ps, params, const)   # smatrix_fn: om.smatrix_recycled for long lists
         if pdf is not None:
             ini = [tuple(pr) for pr in ir["initial_states"]]
             if ir.get("mirror_initial_states"):

@@ -287,3 +287,22 @@ def test_pdf_interpolation_properties(tmp_path):
     assert np.all(np.diff(aa) < 0)
     assert g.alphasQ2([1e9])[0] == g.as_vals[-1] and g.alphasQ2([1.0])[0] > g.as_vals[0]
     assert abs(g.alphasQ2([91.1876**2])[0] - 0.118) < 1e-12
+
+
+def test_recycled_helicity_sum_equals_the_plain_one():
+    """oracle.matrix.smatrix_recycled (wavefunctions memoised per helicity of their own legs, JAMPs as one matrix
+    product) is the same sum as smatrix: every value comes from the same routine with the same inputs."""
+    from conftest import sm_params
+    from madflow_b200 import procgen
+    from oracle import matrix as om
+    from oracle import phasespace as ops
+
+    for k, npts in ((1, 60), (2, 12)):
+        ir = procgen.generate_ir(k)
+        n = 4 + k
+        x = np.random.default_rng(40 + k).random((npts, 4 * (n - 2) + 2))
+        p, _, x1, x2 = ops.ramboflow(x, n, 13e3, [173.0, 173.0] + [0.0] * k, xfactor="converged")
+        p = ops.boost_to_lab(p, x1, x2)
+        params = sm_params(alpha_s=0.09 + 0.05 * np.random.default_rng(1).random(npts))
+        a, b = om.smatrix(ir, p, params), om.smatrix_recycled(ir, p, params, chunk=7)
+        np.testing.assert_allclose(b, a, rtol=1e-14)
