@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--process NAME] [--impl ours|reference]
 
-One "step" = one VEGAS iteration of the fused integrand kernel over `--events` generated events
-per GPU (Philox -> VEGAS map -> RAMBO -> cuts -> boost -> alpha_s -> smatrix -> accumulate), then
-the deterministic reduction, the single all-reduce (N > 1) and the grid refinement.  Prints ONE
-JSON line (rank 0); see DESIGN.md "Measurement" for every field.
+One "step" = one VEGAS iteration of the device-resident integrand over `--events` generated events IN TOTAL
+(Philox -> VEGAS map -> RAMBO -> cuts -> boost -> alpha_s -> smatrix -> accumulate), sharded over the N GPUs
+(strong scaling: BASELINE config 3 is "1e8 events/iteration at 1/2/4/8 B200") and launched in chunks of at most
+`max_events_per_launch` events, then the deterministic reduction, the single all-reduce (N > 1) and the grid
+refinement.  Prints ONE JSON line (rank 0); see DESIGN.md "Measurement" for every field.  The line of the default
+process also carries `other_configs`: BASELINE configs 1, 2 and 4 measured the same way in the same run.
 """
 import argparse
 import json
@@ -25,15 +27,17 @@ METRIC = "fp64_matrix_element_events_per_sec"
 UNIT = "events/s"
 
 # per-process workload: BASELINE.json configs (sqrts 13 TeV, m_t 173, pt > 30 GeV on every outgoing leg)
+# `events` = generated events per iteration IN TOTAL (all GPUs together)
 WORKLOADS = {
     "1_gg_ttx": dict(label="g g > t t~ LO, --no_pdf, RAMBO + VEGAS, pt>30, alpha_s frozen 0.118", masses=[MT, MT],
-                     pt_cut=30.0, running=False, events=1 << 26, e2e_events=1 << 22),
+                     pt_cut=30.0, running=False, events=1 << 27, e2e_events=1 << 22, config=1),
     "1_gg_ttxg": dict(label="g g > t t~ g LO, --no_pdf, pt>30 cuts, alpha_s frozen", masses=[MT, MT, 0.0],
-                      pt_cut=30.0, running=False, events=1 << 24, e2e_events=1 << 21),
-    "1_gg_ttxgg": dict(label="g g > t t~ g g LO, --no_pdf, pt>30 cuts, running g_s (one-loop alpha_s at (sum mT/2)^2)",
-                       masses=[MT, MT, 0.0, 0.0], pt_cut=30.0, running=True, events=1 << 22, e2e_events=1 << 20),
+                      pt_cut=30.0, running=False, events=1 << 25, e2e_events=1 << 21, config=2),
+    "1_gg_ttxgg": dict(label="g g > t t~ g g LO, --no_pdf, pt>30 cuts, running g_s (one-loop alpha_s at (sum mT/2)^2), "
+                             "1e8 events/iteration", masses=[MT, MT, 0.0, 0.0], pt_cut=30.0, running=True,
+                       events=100_000_000, e2e_events=1 << 20, config=3),
     "1_gg_ttxggg": dict(label="g g > t t~ g g g LO, --no_pdf, pt>30 cuts, running g_s", masses=[MT, MT, 0.0, 0.0, 0.0],
-                        pt_cut=30.0, running=True, events=1 << 18, e2e_events=1 << 16),
+                        pt_cut=30.0, running=True, events=1 << 21, e2e_events=1 << 16, config=4),
 }
 # the light-quark subprocesses of p p > t t~ (j): same phase space and cuts as their gluon-fusion counterparts
 WORKLOADS["1_uux_ttx"] = dict(WORKLOADS["1_gg_ttx"], label="u u~ > t t~ LO, --no_pdf, RAMBO + VEGAS, pt>30, alpha_s frozen 0.118")
@@ -136,7 +140,7 @@ def run_reference(args, wl, proc):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "process": proc,
                    "note": "oracle/ numpy restatement of the reference's TF graph (TensorFlow/vegasflow/pdfflow not "
                            "installable offline), op-by-op vectorised over events, one process per host core"},
@@ -146,6 +150,56 @@ def run_reference(args, wl, proc):
     print(json.dumps(line), flush=True)
 
 
+def measure_iterations(vegas, steps, warmup, barrier, dist, torch, sampler=None):
+    """W untimed + K timed VEGAS iterations: (ME events, ms = max over ranks, clocks)."""
+    for _ in range(warmup):
+        vegas.run_iteration()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    n_me = 0
+    for _ in range(steps):
+        vegas.run_iteration()
+        n_me += vegas.last_me_events
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler is not None else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return n_me, float(t.item()), clocks
+
+
+def time_kernel_alone(fi, vegas, n_total, rank, world, reps, torch):
+    """The integrand kernels of ONE launch chunk, alone on the launching stream: (ms per launch, events of the chunk)."""
+    from madflow_b200 import vegas as mfv
+
+    nblocks = fi.nblocks()
+    partial = vegas._partial_buf(nblocks)
+    first, count = mfv.shard_events(n_total, rank, world)
+    count = min(count, fi.max_events_per_launch)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fi.launch(vegas.divisions, 4, 9999, first, count, 1.0 / n_total, partial, nblocks, True)
+    torch.cuda.synchronize()
+    k0.record()
+    for i in range(reps):
+        fi.launch(vegas.divisions, 4, 10000 + i, first, count, 1.0 / n_total, partial, nblocks, True)
+    k1.record()
+    torch.cuda.synchronize()
+    return k0.elapsed_time(k1) / reps, count
+
+
+def load_executed(proc):
+    try:  # executed FP64 instruction counts of the dominant kernel, from the committed ncu captures
+        return json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json"))).get(proc, {})
+    except OSError:
+        return {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,8 +207,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--process", default=None)
-    ap.add_argument("--events", type=int, default=None, help="generated events per GPU per step")
+    ap.add_argument("--events", type=int, default=None, help="generated events per step in total (all GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs 1, 2, 4 in the default run")
     ap.add_argument("--variant", default="default", choices=["default", "thread", "hp"])
     ap.add_argument("--pdf", default=None, help="LHAPDF set (member 0) for the parton luminosity and alpha_s, as madflow "
                     "without --no_pdf; needs the set on disk (--pdf_dir / LHAPDF_DATA_PATH).  Default: --no_pdf")
@@ -197,74 +252,51 @@ def main():
     from madflow_b200 import phasespace as mfps
     from madflow_b200 import vegas as mfv
 
-    m, model = mfm.get_process(proc)
-    m.set_variant(args.variant)
-    pdf = None
-    if wl.get("pdf"):
-        from madflow_b200.pdf import mkPDF
+    def build(proc_, wl_):
+        m_, model_ = mfm.get_process(proc_)
+        m_.set_variant(args.variant)
+        pdf = None
+        if wl_.get("pdf"):
+            from madflow_b200.pdf import mkPDF
 
-        pdf = mkPDF(wl["pdf"], dirname=wl["pdf_dir"])
-    fi = mfi.FusedIntegrand(m, model, sqrts=13e3, masses=wl["masses"], pt_cut=wl["pt_cut"], lab_frame=True,
-                            running=wl["running"], pdf=pdf)
-    n_per_gpu = wl["events"]
-    vegas = mfv.VegasFlow(fi.n_dim, n_per_gpu * world, seed=4)
-    vegas.compile(fi)
+            pdf = mkPDF(wl_["pdf"], dirname=wl_["pdf_dir"])
+        fi_ = mfi.FusedIntegrand(m_, model_, sqrts=13e3, masses=wl_["masses"], pt_cut=wl_["pt_cut"], lab_frame=True,
+                                 running=wl_["running"], pdf=pdf)
+        v_ = mfv.VegasFlow(fi_.n_dim, wl_["events"], seed=4)
+        v_.compile(fi_)
+        return m_, model_, fi_, v_
+
+    m, model, fi, vegas = build(proc, wl)
+    n_total = wl["events"]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # FP64 FMA peak of this device, measured in this run (MEASURED_PEAKS.json has no FP64 entry)
+    # FP64 peak of this device, measured in this run (MEASURED_PEAKS.json has no FP64 entry): the DFMA rate and the rate
+    # of the FP64 tensor instruction (they share one pipe); the roofline denominator is the larger of the two
     lib = rt.core()
     tf_, ms_ = ctypes.c_double(), ctypes.c_double()
     rt.check(lib, lib.mf_fp64_peak(20000, ctypes.byref(tf_), ctypes.byref(ms_)))
     fp64_burst = tf_.value
 
-    for _ in range(args.warmup):
-        vegas.run_iteration()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    n_me = 0
-    results = []
-    for _ in range(args.steps):
-        results.append(vegas.run_iteration())
-        n_me += vegas.last_me_events
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    n_me, ms, clocks = measure_iterations(vegas, args.steps, args.warmup, barrier, dist, torch,
+                                          ClockSampler(local) if rank == 0 else None)
     value = n_me / (ms * 1e-3)
-    generated = n_per_gpu * world * args.steps
+    generated = n_total * args.steps
 
-    # dominant kernel alone: K launches of the fused integrand kernel on the launching stream
-    nblocks = fi.nblocks()
-    partial = vegas._partial_buf(nblocks)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    first, count = mfv.shard_events(n_per_gpu * world, rank, world)
-    fi.launch(vegas.divisions, 4, 9999, first, count, 1.0 / (n_per_gpu * world), partial, nblocks, True)
-    torch.cuda.synchronize()
-    k0.record()
-    for i in range(args.steps):
-        fi.launch(vegas.divisions, 4, 10000 + i, first, count, 1.0 / (n_per_gpu * world), partial, nblocks, True)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / args.steps
-    me_per_launch = n_me / args.steps / world
+    # dominant kernel alone: launches of the integrand kernels over one launch chunk on the launching stream
+    kernel_ms, chunk_events = time_kernel_alone(fi, vegas, n_total, rank, world, min(args.steps, 3), torch)
+    me_per_launch = chunk_events * (n_me / generated)
     flops = m.flops_per_event
     achieved = flops * me_per_launch / (kernel_ms * 1e-3) / 1e12
-    # sustained FP64 probe right after the long kernels (clocks settle under load)
+    # sustained FP64 probes right after the long kernels (clocks settle under load)
     rt.check(lib, lib.mf_fp64_peak(200000, ctypes.byref(tf_), ctypes.byref(ms_)))
-    fp64_sustained = tf_.value
+    dfma_sustained = tf_.value
+    rt.check(lib, lib.mf_dmma_peak(100000, ctypes.byref(tf_), ctypes.byref(ms_)))
+    dmma_sustained = tf_.value
+    fp64_peak = max(dfma_sustained, dmma_sustained)
 
     # end to end through the public API with HOST buffers: pinned momenta -> H2D -> smatrix -> D2H
     n_e2e = wl["e2e_events"]
@@ -311,6 +343,29 @@ def main():
     e2e_value = n_e2e * world * args.steps / float(t.item())
     h2d = h_ps.numel() * 8 + sum(c.numel() * 16 for c in h_coup if c.numel() > 1)
     d2h = n_e2e * 8
+    del h_ps, h_out
+
+    # BASELINE configs 1, 2 and 4 the same way (all ranks take part: the iterations all-reduce)
+    others = []
+    if args.process is None and not args.no_other_configs:
+        for oproc in ("1_gg_ttx", "1_gg_ttxg", "1_gg_ttxggg"):
+            if not os.path.exists(os.path.join(ROOT, "madflow_b200", "lib", f"libmfp_{oproc}.so")):
+                continue
+            owl = dict(WORKLOADS[oproc])
+            om_, _, ofi, ov = build(oproc, owl)
+            o_me, o_ms, _ = measure_iterations(ov, 3, 2, barrier, dist, torch)
+            o_kms, o_chunk = time_kernel_alone(ofi, ov, owl["events"], rank, world, 2, torch)
+            o_exec = load_executed(oproc)
+            o_mel = o_chunk * (o_me / (3.0 * owl["events"]))
+            o_tf = o_exec.get("flops_per_me_event", 0.0) * o_mel / (o_kms * 1e-3) / 1e12
+            others.append({
+                "baseline_config": owl["config"], "process": oproc, "workload": owl["label"], "value": o_me / (o_ms * 1e-3),
+                "unit": UNIT, "steps": 3, "warmup": 2, "ms_per_step": o_ms / 3, "events_generated_per_step": owl["events"],
+                "kernel_variant": om_.variant, "kernel_ms": o_kms,
+                "algorithmic_frac": om_.flops_per_event * o_mel / (o_kms * 1e-3) / 1e12 / fp64_peak,
+                "executed_flops_per_event": o_exec.get("flops_per_me_event"),
+                "executed_frac": o_tf / fp64_peak if o_exec.get("flops_per_me_event") else None})
+            del ofi, ov
 
     if rank != 0:
         if dist is not None:
@@ -326,52 +381,55 @@ def main():
                         "sample": f"{n} generated events of the same workload ({nme} reach the matrix element), "
                                   f"{dt:.1f} s wall; oracle/ numpy restatement, one process per core"}
 
-    peaks, executed = {}, {}
+    peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    try:  # executed FP64 instruction counts of the dominant kernel, from the committed ncu captures
-        executed = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json"))).get(proc, {})
-    except OSError:
-        pass
+    executed = load_executed(proc)
     exec_flops = executed.get("flops_per_me_event")
     exec_tflops = exec_flops * me_per_launch / (kernel_ms * 1e-3) / 1e12 if exec_flops else None
-    final, err, chi2 = mfv.combine_iterations(results)
     # kernels of this package inside the timed region, per step: the integrand (1 fused kernel, or generate +
     # matrix element + accumulate for the helicity-parallel pipeline) and the block-partial reduction per launch
     # chunk, plus the grid refinement
-    chunks = -(-n_per_gpu // min(n_per_gpu, fi.max_events_per_launch))
+    per_rank = mfv.shard_events(n_total, 0, world)[1]
+    chunks = -(-per_rank // min(per_rank, fi.max_events_per_launch))
     gpu_launches = args.steps * (chunks * ((3 if m.variant == "hp" else 1) + 1) + 1)
     bytes_per_event = 0.0  # the fused kernel reads no per-event input from HBM
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": wl["label"], "process": proc, "events_generated_per_gpu_per_step": n_per_gpu,
+            "workload": wl["label"], "process": proc, "events_generated_per_step": n_total,
+            "events_generated_per_gpu_per_step": per_rank, "launch_chunks_per_gpu_per_step": chunks,
             "events_reaching_matrix_element_per_step": n_me // args.steps,
             "generated_events_per_sec": generated / (ms * 1e-3),
             "l2": "inputs are generated in-kernel from Philox counters (no per-event HBM input); e2e inputs "
                   f"{h2d / 2**20:.0f} MiB per step exceed the 126 MB L2",
-            "sigma_pb": final, "sigma_err_pb": err, "constants": "reference", "kernel_variant": m.variant,
+            "constants": "reference", "kernel_variant": m.variant,
+            "note": "no cross section is quoted on this line: with the reference's cuts (pt only) the g || g collinear "
+                    "region of this process is not regulated and single iterations fluctuate by tens of percent "
+                    "(DESIGN.md section 8); integrated-sigma checks against the oracle live in tests/ and in "
+                    "profiles/ (Delta R regulated)",
         },
         "roofline": {
-            "bound": "fp64", "achieved": achieved, "peak": fp64_sustained, "unit": "TFLOP/s",
-            "frac": achieved / fp64_sustained, "traffic": executed.get("dram_bytes_per_launch"),
+            "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp64_peak, "traffic": executed.get("dram_bytes_per_launch"),
             "traffic_source": executed.get("dram_source"),
-            "kernel": "integrand_kernel_hp<Proc>" if m.variant == "hp" else "integrand_kernel<Proc>", "kernel_ms": kernel_ms,
-            "flops_per_event_algorithmic": flops,
-            "peak_source": "mf_fp64_peak DFMA probe in this run (sustained, after the timed kernels); burst "
-                           f"{fp64_burst:.1f} TFLOP/s; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2; "
-                           "MEASURED_PEAKS.json has no FP64 entry",
+            "kernel": "smatrix_kernel_hp<Proc> (+ ps_generate_kernel, accumulate_kernel)" if m.variant == "hp" else "integrand_kernel<Proc>",
+            "kernel_ms": kernel_ms, "events_per_launch": chunk_events, "flops_per_event_algorithmic": flops,
+            "peak_source": f"max of the in-run probes after the timed kernels: DFMA {dfma_sustained:.1f}, FP64 tensor "
+                           f"instruction (mma.sync.m8n8k4, same pipe) {dmma_sustained:.1f} TFLOP/s; DFMA burst before: "
+                           f"{fp64_burst:.1f}; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2; MEASURED_PEAKS.json has "
+                           "no FP64 entry",
             "hbm_gbs_measured": peaks.get("hbm_gbs"), "hbm_bytes_per_event": bytes_per_event,
-            "note": "achieved = F_alg (the reference's operation count over all helicities, SURVEY 8d) x events / time; "
-                    "the kernel executes fewer operations (wavefunctions and vertices are evaluated once per helicity "
-                    "variant of their own legs), so this fraction can exceed 1; the executed figures below are the "
+            "note": "achieved = F_alg (the reference's operation count over all helicities and diagrams, SURVEY 8d) x "
+                    "events / time; the kernel executes far fewer operations (colour-reduced recursion, every object once "
+                    "per helicity variant of its own legs), so this fraction exceeds 1; the executed figures are the "
                     "hardware-side view",
             "executed_flops_per_event": exec_flops, "executed_tflops": exec_tflops,
-            "executed_frac": exec_tflops / fp64_sustained if exec_tflops else None,
+            "executed_frac": exec_tflops / fp64_peak if exec_tflops else None,
             "executed_source": executed.get("source"),
         },
         "cpu_baseline": cpu_baseline,
@@ -380,6 +438,7 @@ def main():
                 "events_per_step": n_e2e},
         "gpu_launches": gpu_launches,
         "clocks": clocks,
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -123,6 +123,9 @@ int mf_pdf_alphasq2(const double* d_table, const double* d_q2, int64_t nevt, dou
  * FP64 FMA throughput of the current device, measured: `iters` dependent DFMA per chain, 8 chains
  * per thread, full grid.  Synchronous.  Returns TFLOP/s in *tflops (2 flop per DFMA).            */
 int mf_fp64_peak(int iters, double* tflops, double* ms);
+/* the same for the FP64 tensor instruction (mma.sync.m8n8k4.f64): `iters` x 4 independent accumulators per warp,
+ * 4 warps per block, 4 blocks per SM; 512 flop per instruction.  DFMA and DMMA share one pipe on sm_100a.          */
+int mf_dmma_peak(int iters, double* tflops, double* ms);
 
 #ifdef __cplusplus
 }

@@ -282,6 +282,22 @@ __global__ void __launch_bounds__(256) dfma_kernel(int iters, double seed, doubl
   if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
 }
 
+// the FP64 tensor instruction of sm_100a (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): 4 independent accumulator pairs per warp
+__global__ void __launch_bounds__(128) dmma_kernel(int iters, double seed, double* out) {
+  double c0[4], c1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c0[i] = seed + threadIdx.x + i, c1[i] = c0[i] + 0.5;
+  const double a = 1.0000001, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i])
+                   : "d"(a), "d"(b));
+  }
+  const double s = ((c0[0] + c0[1]) + (c0[2] + c0[3])) + ((c1[0] + c1[1]) + (c1[2] + c1[3]));
+  if (s == 12345.678) out[0] = s;
+}
 
 // ------------------------------------------------------------------------------ PDFs (csrc/pdf.cuh)
 struct PdfFlavours { int n; int col[MF_PDF_MAX_FLAVOURS]; };
@@ -525,6 +541,28 @@ int mf_fp64_peak(int iters, double* tflops, double* ms) {
   cudaEventDestroy(a), cudaEventDestroy(b), cudaFree(d);
   if (e != cudaSuccess) return fail("dfma_kernel", e);
   const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+  *tflops = fl / (t * 1e-3) / 1e12;
+  *ms = t;
+  return 0;
+}
+
+int mf_dmma_peak(int iters, double* tflops, double* ms) {
+  double* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(double));
+  if (e != cudaSuccess) return fail("cudaMalloc", e);
+  const int blocks = sm_count() * 4, threads = 128;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a), cudaEventCreate(&b);
+  dmma_kernel<<<blocks, threads>>>(iters / 10 + 1, 1.0, d);  // warm-up
+  cudaEventRecord(a);
+  dmma_kernel<<<blocks, threads>>>(iters, 1.0, d);
+  cudaEventRecord(b);
+  e = cudaEventSynchronize(b);
+  float t = 0.f;
+  cudaEventElapsedTime(&t, a, b);
+  cudaEventDestroy(a), cudaEventDestroy(b), cudaFree(d);
+  if (e != cudaSuccess) return fail("dmma_kernel", e);
+  const double fl = 512.0 * 4.0 * (double)iters * blocks * (threads / 32);   // 2 * 8 * 8 * 4 flop per instruction
   *tflops = fl / (t * 1e-3) / 1e12;
   *ms = t;
   return 0;
