@@ -9,11 +9,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def builtin_irs():
+    """Every process compiled into the package: the pinned g g > t t~, g g > t t~ + 1..3 g, q q~ > t t~, the
+    light-line five-point processes (`p p > t t~ j`) and the six-point subprocesses of `p p > t t~ j j` (light-line
+    and four-quark, from procgen_lines)."""
     irs = [process_ir.gg_ttx_pinned()]
     try:
-        from . import procgen
+        from . import procgen, procgen_lines
 
         irs += procgen.builtin_irs()
+        have = {ir["name"] for ir in irs}
+        irs += [procgen_lines.process_ir(n) for n in procgen.MULTI_PROCESSES["p p > t t~ j j"] if n not in have]
     except ImportError:
         pass
     return irs
@@ -40,11 +45,16 @@ def build_named(name, verbose=False):
     return codegen.build_process(procgen_lines.process_ir(name), verbose=verbose)
 
 
-def build_all(verbose=False):
-    libs = [build_core(verbose)]
-    for ir in builtin_irs():
-        libs.append(codegen.build_process(ir, verbose=verbose))
-    return libs
+def build_all(verbose=False, jobs=None):
+    """Compile the core library and every built-in process, `jobs` nvcc processes at a time."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    jobs = jobs or max(1, min(8, os.cpu_count() or 1))
+    irs = builtin_irs()
+    with ThreadPoolExecutor(max_workers=jobs) as pool:
+        core = pool.submit(build_core, verbose)
+        procs = [pool.submit(codegen.build_process, ir, None, verbose) for ir in irs]
+        return [core.result()] + [f.result() for f in procs]
 
 
 if __name__ == "__main__":

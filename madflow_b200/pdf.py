@@ -165,6 +165,8 @@ class PDF:
         """x f(x, Q2) for the flavours `pid` (PDG ids): (nevt, len(pid)) float64 on the GPU, squeezed like
         pdfflow's result (the reference reshapes it to (-1, nflavours) anyway, madflow_exec.py:415-416)."""
         pids = [int(p) for p in (pid.tolist() if hasattr(pid, "tolist") else pid)] if not isinstance(pid, int) else [pid]
+        asked = pids
+        pids = sorted(set(pids))     # every flavour once (a `p p > ..` luminosity list repeats them), gathered below
         cols = (ctypes.c_int32 * len(pids))(*[self.column(p) for p in pids])
         x, q2 = rt.to_device(x).reshape(-1), rt.to_device(q2).reshape(-1)
         if q2.numel() == 1 and x.numel() > 1:
@@ -176,6 +178,8 @@ class PDF:
         lib = rt.core()
         rt.check(lib, lib.mf_pdf_xfxq2(rt.ptr(self.table), cols, len(pids), rt.ptr(x), rt.ptr(q2), ctypes.c_int64(n),
                                        rt.ptr(out), rt.stream_ptr()))
+        if asked != pids:
+            out = out[:, [pids.index(p) for p in asked]]
         return out.squeeze()
 
     def xfxQ2_allpid(self, x, q2):

@@ -968,3 +968,64 @@ def test_vegas_checkpoint_resume(mf, tmp_path):
     rb = [vb.run_iteration() for _ in range(2)]
     assert ra == rb
     np.testing.assert_array_equal(cpu(va.divisions), cpu(vb.divisions))
+
+
+# ------------------------------------------------------------------------------ p p > t t~ j j
+PPJJ_SIX_POINT = ["1_gg_ttxuux", "1_gu_ttxug", "1_gux_ttxuxg", "1_uux_ttxgg", "1_uu_ttxuu", "1_ud_ttxud", "1_uxux_ttxuxux",
+                  "1_uxdx_ttxuxdx", "1_uux_ttxuux", "1_uux_ttxddx", "1_udx_ttxudx"]
+
+
+@pytest.mark.parametrize("name", PPJJ_SIX_POINT)
+def test_six_point_light_quark_processes_vs_oracle(mf, name):
+    """The light-line (q q~ > t t~ g g and crossings, g g > t t~ q q~) and four-quark subprocesses of p p > t t~ j j
+    (madflow_b200/procgen_lines.py) on the GPU: per-event |M|^2 against the oracle interpreting the same IR (parity
+    unpinned with respect to MG5, like every generated process), running couplings, lab-frame RAMBO points."""
+    from madflow_b200 import procgen_lines
+
+    ir = procgen_lines.process_ir(name)
+    m, model = mf.matrix.get_process(name)
+    assert m.nexternal == 6 and m.ncomb == 64
+    npts = 1500
+    x = np.random.default_rng(31).random((npts, 18))
+    p, w, x1, x2 = ops.ramboflow(x, 6, 13e3, [MT, MT, 0.0, 0.0], xfactor="converged")
+    lab = ops.boost_to_lab(p, x1, x2)
+    a_s = 0.09 + 0.05 * np.random.default_rng(32).random(npts)
+    ref = omatrix.smatrix(ir, lab, sm_params(alpha_s=a_s))
+    out = cpu(m.smatrix(lab, *model.evaluate(a_s)))
+    np.testing.assert_allclose(out, ref, rtol=REL_ME)
+
+
+def test_pp_ttxjj_sums_twelve_subprocesses(mf, toy_pdf):
+    """`p p > t t~ j j`: the twelve subprocess libraries on the same events with their luminosities (the loop of
+    madflow_exec.py:141-155, 444-455) == the separate C-ABI calls == the oracle, on identical Philox points."""
+    from madflow_b200 import procgen, procgen_lines
+
+    pd, og = toy_pdf
+    names = procgen.MULTI_PROCESSES["p p > t t~ j j"]
+    assert len(names) == 12
+    irs = {nm: (procgen.generate_ir(2) if nm == "1_gg_ttxgg" else procgen_lines.process_ir(nm)) for nm in names}
+    masses = [MT, MT, 0.0, 0.0]
+    nev = 3000
+    parts = []
+    for nm in names:
+        m, model = mf.matrix.get_process(nm)
+        parts.append(mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=masses, pt_cut=30.0, lab_frame=True,
+                                                 running=True, pdf=pd))
+    multi = mf.integrand.MultiProcessIntegrand(parts)
+    try:
+        v1 = mf.vegas.VegasFlow(18, nev, seed=4)
+        v1.compile(multi)
+        r1 = v1.run_iteration()
+        v2 = mf.vegas.VegasFlow(18, nev, seed=4)
+        v2.compile(multi.python_integrand())
+        r2 = v2.run_iteration()
+        assert abs(r1[0] / r2[0] - 1) < 1e-10 and abs(r1[1] / r2[1] - 1) < 1e-8
+        xss = [ovegas.make_cross_section(irs[nm], lambda a: sm_params(alpha_s=a), 13e3, masses, pt_cut=30.0, lab_frame=True,
+                                         alpha_s_fn=og.alphasQ2, pdf=og) for nm in names]
+        ov = ovegas.Vegas(18, nev, seed=4)
+        ov.compile(lambda xr, **kw: sum(xs(xr) for xs in xss))
+        r0 = ov.run_iteration()
+        assert abs(r1[0] / r0[0] - 1) < 1e-10 and abs(r1[1] / r0[1] - 1) < 1e-8
+        np.testing.assert_allclose(cpu(v1.divisions), ov.grid, rtol=1e-6, atol=1e-11)
+    finally:
+        multi.release()
