@@ -45,9 +45,59 @@ FLOPS = {
 COUPLING_DEFS = {"GC_10": (-1.0, 0.0, 1), "GC_11": (0.0, 1.0, 1), "GC_12": (0.0, 1.0, 2)}
 
 
+# hand-written device routines (csrc/helas.cuh, csrc/aloha_sm.cuh); every other vertex of a call list must come with its
+# ALOHA routine, written by the pyout plugin's CUDA ALOHA writer (madgraph_plugin/PyOut_create_aloha.py), in
+# ir["aloha_routines"] = {routine name: device source text}
+BUILTIN_OPS = set(FLOPS)
+PLUGIN_ROUTINE_FLOPS = 300   # nominal operation count of a plugin-written routine (F_alg bookkeeping only)
+
+
+def plugin_ops(ir):
+    """Vertex routines of the call list that are not hand-written: they are taken from ir["aloha_routines"]."""
+    ops = sorted({c["op"] for c in ir["calls"]} - BUILTIN_OPS)
+    missing = [op for op in ops if op not in ir.get("aloha_routines", {})]
+    if missing:
+        raise ValueError(f"vertex routines {missing} are neither built in nor supplied in ir['aloha_routines'] "
+                         "(the pyout plugin's ALOHA writer produces them from the UFO model)")
+    return ops
+
+
+def hp_available(ir):
+    """The helicity-parallel kernels evaluate the vertices of the QCD sector through table-driven numerators
+    (HP_TYPES); call lists with other Lorentz structures run in the one-event-per-thread flavour."""
+    return not plugin_ops(ir)
+
+
+def _emit_plugin_routines(ir):
+    """The ALOHA routines supplied with the IR + adapters to the complex type of the kernels (cxd)."""
+    ops = plugin_ops(ir)
+    if not ops:
+        return ""
+    L = ["namespace plg {", "typedef cuda::std::complex<double> cxtype;"]
+    for op in ops:
+        L.append(ir["aloha_routines"][op].strip())
+    L.append("}  // namespace plg")
+    for op in ops:
+        call = next(c for c in ir["calls"] if c["op"] == op)
+        nin = len(call["in"])
+        names = [f"W{q}" for q in range(nin)]
+        conv = " ".join(f"plg::cxtype x{q}[6]; for (int k = 0; k < 6; ++k) x{q}[k] = plg::cxtype({n}[k].re, {n}[k].im);"
+                        for q, n in enumerate(names))
+        xs = ", ".join(f"x{q}" for q in range(nin))
+        sig = ", ".join(f"const cxd* {n}" for n in names)
+        if "amp" in call:
+            L.append(f"MF_DEV cxd plg_{op}({sig}, cxd COUP) {{ {conv} plg::cxtype v(0., 0.); "
+                     f"plg::{op}({xs}, plg::cxtype(COUP.re, COUP.im), v); return mk(v.real(), v.imag()); }}")
+        else:
+            L.append(f"MF_DEV void plg_{op}({sig}, cxd COUP, double M, double W, cxd* OUT) {{ {conv} plg::cxtype o[6]; "
+                     f"plg::{op}({xs}, plg::cxtype(COUP.re, COUP.im), M, W, o); "
+                     "for (int k = 0; k < 6; ++k) OUT[k] = mk(o[k].real(), o[k].imag()); }")
+    return "\n".join(L)
+
+
 def flops_per_event(ir):
     """F_alg of SURVEY.md section 8(d): ncomb*(sum calls + F_jamp + F_colour) + ncomb + 1."""
-    per_hel = sum(FLOPS[c["op"]] for c in ir["calls"])
+    per_hel = sum(FLOPS.get(c["op"], PLUGIN_ROUTINE_FLOPS) for c in ir["calls"])
     fj = 0
     for terms in ir["jamp"]:
         fj += 2 * (len(terms) - 1)
@@ -83,13 +133,15 @@ def _emit_call(ir, c):
     if op == "sxxxxx":
         return f"mf::sxxxxx(p[{c['leg']}], {c['nsf']}, w{c['out']});"
     ins = ", ".join(f"w{i}" for i in c["in"])
-    fn = op
-    if op.startswith("VVVV"):
+    fn = "mf::" + op
+    if op not in BUILTIN_OPS:
+        fn = "plg_" + op       # written by the plugin's ALOHA writer (_emit_plugin_routines)
+    elif op.startswith("VVVV"):
         kind = op[4]
-        fn = f"VVVV_0<{kind}>" if op.endswith("_0") else f"VVVVP0_1<{kind}>"
+        fn = f"mf::VVVV_0<{kind}>" if op.endswith("_0") else f"mf::VVVVP0_1<{kind}>"
     if "amp" in c:
-        return f"mf::{fn}({ins}, {_coup_expr(ir, c)})"
-    return (f"mf::{fn}({ins}, {_coup_expr(ir, c)}, {_par_expr(ir, c['mass'])}, {_par_expr(ir, c['width'])}, "
+        return f"{fn}({ins}, {_coup_expr(ir, c)})"
+    return (f"{fn}({ins}, {_coup_expr(ir, c)}, {_par_expr(ir, c['mass'])}, {_par_expr(ir, c['width'])}, "
             f"w{c['out']});")
 
 
@@ -329,7 +381,12 @@ def hp_plan_from_ir(ir):
 def emit_hp(ir):
     """Tables + the generated amplitude/JAMP/colour code of the helicity-parallel kernels."""
     reduced = hp_use_plan(ir)
-    plan = ir["plan"] if reduced else hp_plan_from_ir(ir)
+    if not hp_available(ir):
+        # vertices outside the table-driven set: only the externals are described, the flavour is switched off (HP_AVAILABLE)
+        plan = {"objects": [{"legs": [c["leg"]], "ext": c, "terms": []} for c in ir["calls"] if "leg" in c], "pairs": [], "rows": []}
+        reduced = False
+    else:
+        plan = ir["plan"] if reduced else hp_plan_from_ir(ir)
     n = ir["nexternal"]
     assert ir["ncomb"] == 2**n, "the hp kernels need the full 2^n helicity table"
     NH = ir["ncomb"]
@@ -580,6 +637,8 @@ def emit_hp(ir):
     A.append("    default: break;")
     A.append("    }")
     unroll = len(plan["rows"]) <= HP_UNROLL_MAX_AMPS and not reduced
+    if not hp_available(ir):
+        unroll = False
     cmode = "thread" if unroll else hp_colour_mode(ir, NCG)
     ncp = -(-ncolor // 8) * 8
     if cmode == "thread":
@@ -718,15 +777,19 @@ def emit_process_source(ir, block=None, minblocks=None):
     hp_ncg = hp['ncg']
     hp_nj = -(-ncolor // hp_ncg)
     hp_e = hp_config(ir, "E")
-    use_hp = "true" if use_hp_default(ir) else "false"
-    has_thread = "true" if (len(ir["calls"]) <= THREAD_MAX_CALLS or os.environ.get("MADFLOW_B200_BUILD_THREAD") == "1") else "false"
+    hp_ok = hp_available(ir)
+    use_hp = "true" if (use_hp_default(ir) and hp_ok) else "false"
+    has_thread = "true" if (len(ir["calls"]) <= THREAD_MAX_CALLS or not hp_ok or os.environ.get("MADFLOW_B200_BUILD_THREAD") == "1") else "false"
+    if not hp_ok and len(ir["calls"]) > STRAIGHT_LINE_MAX_CALLS:
+        raise ValueError("call lists with plugin-written vertex routines are limited to the one-event-per-thread flavour "
+                         f"({STRAIGHT_LINE_MAX_CALLS} calls)")
     hp_minblocks, hp_wfsize, hp_maxlevel, hp_nwf, hp_nitems = hp_config(ir, "MINBLOCKS"), hp["wfsize"], hp["maxlevel"], hp["nwf"], hp["nitems"]
     pnames = ", ".join(f'"{p}"' for p in ir["params"]) or '""'
     cnames = ", ".join(f'"{c}"' for c in ir["couplings"]) or '""'
     src = f"""// GENERATED by madflow_b200.codegen -- do not edit.  Process: {ir.get('process', ir['name'])}
 // One fused FP64 kernel per process: HELAS wavefunctions -> ALOHA vertices -> JAMP -> colour matrix.
 #include "process_kernels_hp.cuh"
-
+{'#include <cuda/std/complex>' if plugin_ops(ir) else ''}
 namespace {{
 __device__ __constant__ signed char d_hel[{ir['ncomb'] * n}] = {{{hel_flat}}};
 static const signed char h_hel[{ir['ncomb'] * n}] = {{{hel_flat}}};
@@ -747,6 +810,8 @@ MF_DEV int P_hel(int icomb, int leg) {{
 #endif
 }}
 
+{_emit_plugin_routines(ir)}
+
 struct Proc {{
   static constexpr int NEXT = {n}, NINIT = {ir['ninitial']}, NCOMB = {ir['ncomb']}, NCOLOR = {ncolor};
   static constexpr int NDIAGS = {ir['ndiags']}, NAMPS = {namps}, NWF = {ir['nwavefuncs']};
@@ -764,6 +829,8 @@ struct Proc {{
 
   // helicity-parallel variant (process_kernels_hp.cuh)
   static constexpr bool USE_HP = {use_hp};
+  // false: the call list uses vertex routines outside the table-driven set (written by the plugin's ALOHA writer)
+  static constexpr bool HP_AVAILABLE = {'true' if hp_ok else 'false'};
   // the one-event-per-thread kernels are only compiled while a helicity's wavefunctions can stay in
   // registers; beyond that they spill to DRAM (profiles/r01_ttxgg_thread_per_event.summary.txt)
   static constexpr bool HAS_THREAD = {has_thread};

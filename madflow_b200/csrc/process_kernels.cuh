@@ -15,6 +15,8 @@
 //                           queued in shared memory and the matrix element always runs on full
 //                           blocks (the reference compacts with tf.boolean_mask, phasespace.py:506-515).
 #pragma once
+#include <cstring>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 
@@ -351,26 +353,86 @@ int launch_integrand(const mfp_integrand_args* u, cudaStream_t st) {
   return 0;
 }
 
+// Host-buffer entry point (mfp_smatrix_host): pageable host arrays in, pageable host array out.  The events go
+// through the device in chunks over two streams with PINNED staging buffers that the library keeps between calls
+// (no cudaMalloc / cudaFree and no pageable cudaMemcpy per call): while chunk i computes, chunk i+1 is staged and
+// copied.  One pipeline per process library, calls are serialised.
+struct HostPipe {
+  static constexpr long long CHUNK = 1 << 17;
+  double *d_p[2] = {nullptr, nullptr}, *d_c[2] = {nullptr, nullptr}, *d_o[2] = {nullptr, nullptr};
+  double *h_p[2] = {nullptr, nullptr}, *h_c[2] = {nullptr, nullptr}, *h_o[2] = {nullptr, nullptr};
+  cudaStream_t st[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  bool ready = false;
+  int init(size_t pb, size_t cb) {
+    if (ready) return 0;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      if (e == cudaSuccess) e = cudaMalloc(&d_p[i], pb);
+      if (e == cudaSuccess) e = cudaMalloc(&d_o[i], CHUNK * sizeof(double));
+      if (e == cudaSuccess && cb) e = cudaMalloc(&d_c[i], cb);
+      if (e == cudaSuccess) e = cudaMallocHost(&h_p[i], pb);
+      if (e == cudaSuccess) e = cudaMallocHost(&h_o[i], CHUNK * sizeof(double));
+      if (e == cudaSuccess && cb) e = cudaMallocHost(&h_c[i], cb);
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return fail("mfp_smatrix_host: staging buffers", e);
+    ready = true;
+    return 0;
+  }
+};
+
 template <class P, class Launch>
 int smatrix_host(Launch launch, const double* h_p, int layout, long long nevt, const double* par,
                  const double* h_coup, long long coup_stride, double sqh, double* h_out) {
   if (nevt <= 0) return 0;
-  double *d_p = nullptr, *d_c = nullptr, *d_o = nullptr;
-  const size_t pb = (size_t)nevt * P::NEXT * 4 * sizeof(double);
-  const size_t cb = (size_t)(coup_stride ? nevt : 1) * P::NCOUP * 2 * sizeof(double);
+  if (layout != MFP_LAYOUT_AOS && layout != MFP_LAYOUT_SOA) return fail_msg("mfp_smatrix_host: unknown layout");
+  static HostPipe pipe;
+  static std::mutex lock;
+  std::lock_guard<std::mutex> guard(lock);
+  constexpr long long CH = HostPipe::CHUNK;
+  constexpr int ROWS = P::NEXT * 4;
+  const size_t pb = (size_t)CH * ROWS * sizeof(double);
+  const size_t cb = (size_t)CH * P::NCOUP * 2 * sizeof(double);   // per-event couplings; frozen ones use the first slot
+  if (int rc = pipe.init(pb, cb)) return rc;
   cudaError_t e;
-  if ((e = cudaMalloc(&d_p, pb)) != cudaSuccess) return fail("cudaMalloc momenta", e);
-  if ((e = cudaMalloc(&d_o, nevt * sizeof(double))) != cudaSuccess) { cudaFree(d_p); return fail("cudaMalloc out", e); }
-  if (cb && (e = cudaMalloc(&d_c, cb)) != cudaSuccess) { cudaFree(d_p); cudaFree(d_o); return fail("cudaMalloc coup", e); }
-  int rc = 0;
-  if ((e = cudaMemcpy(d_p, h_p, pb, cudaMemcpyHostToDevice)) != cudaSuccess) rc = fail("H2D momenta", e);
-  if (!rc && cb && (e = cudaMemcpy(d_c, h_coup, cb, cudaMemcpyHostToDevice)) != cudaSuccess) rc = fail("H2D coup", e);
-  if (!rc) rc = launch(d_p, layout, nevt, par, d_c, coup_stride, sqh, d_o, -1, (cudaStream_t)0);
-  if (!rc && (e = cudaMemcpy(h_out, d_o, nevt * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
-    rc = fail("D2H result", e);
-  cudaFree(d_p), cudaFree(d_o);
-  if (d_c) cudaFree(d_c);
-  return rc;
+  const long long nchunks = (nevt + CH - 1) / CH;
+  auto drain = [&](long long c) -> int {   // results of chunk c: wait, then pinned -> caller's array
+    const int s = (int)(c & 1);
+    if ((e = cudaEventSynchronize(pipe.done[s])) != cudaSuccess) return fail("mfp_smatrix_host: chunk", e);
+    const long long off = c * CH, n = (nevt - off) < CH ? (nevt - off) : CH;
+    memcpy(h_out + off, pipe.h_o[s], (size_t)n * sizeof(double));
+    return 0;
+  };
+  for (long long c = 0; c < nchunks; ++c) {
+    const int s = (int)(c & 1);
+    if (c >= 2)
+      if (int rc = drain(c - 2)) return rc;   // frees staging set s
+    const long long off = c * CH, n = (nevt - off) < CH ? (nevt - off) : CH;
+    if (layout == MFP_LAYOUT_AOS) {
+      memcpy(pipe.h_p[s], h_p + off * ROWS, (size_t)n * ROWS * sizeof(double));
+    } else {
+      for (int r = 0; r < ROWS; ++r) memcpy(pipe.h_p[s] + (long long)r * n, h_p + (long long)r * nevt + off, (size_t)n * sizeof(double));
+    }
+    cudaMemcpyAsync(pipe.d_p[s], pipe.h_p[s], (size_t)n * ROWS * sizeof(double), cudaMemcpyHostToDevice, pipe.st[s]);
+    if (P::NCOUP > 0) {
+      if (coup_stride) {
+        for (int k = 0; k < P::NCOUP; ++k)
+          memcpy(pipe.h_c[s] + 2 * (long long)k * n, h_coup + 2 * ((long long)k * nevt + off), (size_t)n * 2 * sizeof(double));
+        cudaMemcpyAsync(pipe.d_c[s], pipe.h_c[s], (size_t)n * P::NCOUP * 2 * sizeof(double), cudaMemcpyHostToDevice, pipe.st[s]);
+      } else {
+        memcpy(pipe.h_c[s], h_coup, (size_t)P::NCOUP * 2 * sizeof(double));
+        cudaMemcpyAsync(pipe.d_c[s], pipe.h_c[s], (size_t)P::NCOUP * 2 * sizeof(double), cudaMemcpyHostToDevice, pipe.st[s]);
+      }
+    }
+    if (int rc = launch(pipe.d_p[s], layout, n, par, pipe.d_c[s], coup_stride, sqh, pipe.d_o[s], -1, pipe.st[s])) return rc;
+    cudaMemcpyAsync(pipe.h_o[s], pipe.d_o[s], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, pipe.st[s]);
+    if ((e = cudaEventRecord(pipe.done[s], pipe.st[s])) != cudaSuccess) return fail("mfp_smatrix_host: record", e);
+  }
+  for (long long c = nchunks >= 2 ? nchunks - 2 : 0; c < nchunks; ++c)
+    if (int rc = drain(c)) return rc;
+  return 0;
 }
 
 }  // namespace mf

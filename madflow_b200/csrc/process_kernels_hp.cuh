@@ -828,7 +828,7 @@ int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
 // kernel flavour: 0 = the process's default (P::USE_HP), 1 = one event per thread, 2 = helicity-parallel
 static int g_variant = 0;
 template <class P>
-bool use_hp() { return !P::HAS_THREAD || (g_variant == 0 ? P::USE_HP : g_variant == 2); }
+bool use_hp() { return P::HP_AVAILABLE && (!P::HAS_THREAD || (g_variant == 0 ? P::USE_HP : g_variant == 2)); }
 
 template <class P>
 int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double* par, const double* d_coup,
@@ -881,6 +881,8 @@ int dispatch_smatrix(const double* d_p, int layout, long long nevt, const double
   }                                                                                                            \
   int mfp_set_variant(int v) {                                                                                 \
     if (v < 0 || v > 2) return mf::fail_msg("mfp_set_variant: 0 default, 1 thread-per-event, 2 helicity-parallel"); \
+    if (v == 2 && !P::HP_AVAILABLE)                                                                            \
+      return mf::fail_msg("mfp_set_variant: the helicity-parallel flavour does not know this process's vertices"); \
     if (v == 1 && !P::HAS_THREAD)                                                                              \
       return mf::fail_msg("mfp_set_variant: the one-event-per-thread flavour is not compiled for this process"); \
     mf::g_variant = v;                                                                                         \

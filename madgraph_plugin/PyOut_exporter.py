@@ -107,6 +107,24 @@ def coupling_power_law(expr, namespace=None):
     return None
 
 
+def attach_aloha_routines(ir, routines):
+    """ir["aloha_routines"] = the device source of every vertex routine of the call list that the CUDA backend does not
+    have hand-written (madflow_b200.codegen.BUILTIN_OPS).  `routines`: {name: text} or a callable producing it (the
+    ALOHA computation is only started when something is missing)."""
+    from madflow_b200 import codegen
+
+    missing = sorted({c["op"] for c in ir["calls"]} - codegen.BUILTIN_OPS)
+    if not missing:
+        return ir
+    if callable(routines):
+        routines = routines()
+    absent = [op for op in missing if op not in routines]
+    if absent:
+        raise PyOutExporterError("ALOHA did not produce the routines %s" % absent)
+    ir["aloha_routines"] = {op: routines[op] for op in missing}
+    return ir
+
+
 MATRIX_TEMPLATE = open(pjoin(plugin_path, "template_files", "matrix_method_cuda.inc")).read()
 
 
@@ -196,6 +214,29 @@ class PyOutExporter(export_python.ProcessExporterPython):
                     defs[c.name] = law
         return defs
 
+    def write_alohas(self, matrix_element):
+        """The ALOHA routines of the matrix elements as CUDA device source, by routine name (reference:
+        PyOut_exporter.py:507-540 writes aloha_<proc>.py with TensorFlow code).  Only the routines that are not
+        hand-written in csrc/aloha_sm.cuh end up in the process's translation unit (attach_aloha_routines)."""
+        from . import PyOut_create_aloha as pyout_create_aloha
+        from ._mg5 import aloha_writers, create_aloha
+
+        aloha_model = create_aloha.AbstractALOHAModel(os.path.basename(self.model.get('modelpath')))
+        aloha_model.add_Lorentz_object(self.model.get('lorentz'))
+        wanted_lorentz = set(sum([me.get_used_lorentz() for me in self.matrix_elements], []))
+        if wanted_lorentz:
+            aloha_model.compute_subset(list(wanted_lorentz))
+        else:
+            aloha_model.compute_all(save=False)
+        routines = {}
+        for k, v in aloha_model.items():
+            routine = pyout_create_aloha.PyOutAbstractRoutine(v)
+            routines[aloha_writers.get_routine_name(abstract=routine)] = routine.write(output_dir='')
+        proc = matrix_element.get('processes')[0].shell_string()
+        with open(pjoin(self.dir_path, 'aloha_%s.cuh' % proc), 'w') as fout:
+            fout.write(pyout_create_aloha.CUDA_PROLOGUE + "\n".join(routines.values()))
+        return routines
+
     def generate_subprocess_directory(self, subproc_group, fortran_model, me=None):
         self.helas_writer = pyout_helas_call_writer.PyOutUFOHelasCallWriter(self.model)
         super(PyOutExporter, self).__init__(subproc_group, self.helas_writer)
@@ -204,6 +245,7 @@ class PyOutExporter(export_python.ProcessExporterPython):
             calls = self.helas_call_writer.get_matrix_element_calls(matrix_element, False)
             ir = matrix_element_to_ir(matrix_element, calls)
             ir["coupling_defs"] = {k: list(v) for k, v in self.coupling_defs(ir).items()}
+            attach_aloha_routines(ir, lambda: self.write_alohas(matrix_element))
             write_process_files(ir, self.dir_path, self.get_model_parameter_lines(ir))
             proc = ir["name"]
             self.me_names.append('matrix_%s' % proc)

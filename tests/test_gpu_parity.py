@@ -137,6 +137,13 @@ def test_smatrix_gg_ttx_vs_reference_golden(mf, golden, variant):
     out = cpu(m.smatrix(g["13tev_lab_p"], g["params"][0], g["params"][1], -gs, 1j * gs))
     np.testing.assert_allclose(out, g["run_smatrix"], rtol=REL_ME)
     assert cpu(m.smatrix(np.zeros((0, 4, 4)), *params)).shape == (0,)
+    # the host-buffer entry point pipelines chunks of 2^17 events over two streams: several chunks, a ragged tail,
+    # per-event couplings
+    big = np.tile(g["13tev_lab_p"], (-(-300_001 // g["13tev_lab_p"].shape[0]), 1, 1))[:300_001]
+    gsb = np.resize(gs, 300_001)
+    ref_big = cpu(m.smatrix(big, g["params"][0], g["params"][1], -gsb, 1j * gsb))
+    np.testing.assert_array_equal(m.smatrix_host(big, g["params"][0], g["params"][1], -gsb, 1j * gsb), ref_big)
+    np.testing.assert_array_equal(m.smatrix_host(big, *params), cpu(m.smatrix(big, *params)))
     with pytest.raises(TypeError):
         m.smatrix(g["13tev_com_p"], 173.0)
     with pytest.raises(ValueError):
@@ -1029,3 +1036,72 @@ def test_pp_ttxjj_sums_twelve_subprocesses(mf, toy_pdf):
         np.testing.assert_allclose(cpu(v1.divisions), ov.grid, rtol=1e-6, atol=1e-11)
     finally:
         multi.release()
+
+
+def test_plugin_written_vertex_routine_on_the_gpu(mf, tmp_path, monkeypatch):
+    """The pyout plugin's ALOHA path on the device: a call list with an FFV2 vertex (text in MG5's C++ ALOHA format ->
+    cpp_to_cuda -> codegen -> nvcc) and a coupling outside GC_10/11/12, evaluated through the C ABI against numpy."""
+    import shutil
+
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    import test_plugin as tp
+    from madflow_b200 import codegen, process_ir
+    from madgraph_plugin.PyOut_create_aloha import cpp_to_cuda
+    from madgraph_plugin.PyOut_exporter import attach_aloha_routines
+
+    ir = process_ir.gg_ttx_pinned()
+    ir["name"] = "1_gg_ttx_ffv2"
+    for c in ir["calls"]:
+        if c["op"] == "FFV1_1":
+            c["op"], c["coup"] = "FFV2_1", "GC_100"
+        elif c.get("amp") == 1:
+            c["op"], c["coup"] = "FFV2_0", "GC_100"
+    ir["couplings"] = sorted({c["coup"] for c in ir["calls"] if "coup" in c})
+    ir["coupling_defs"] = {"GC_100": [0.0, 0.44, 2]}
+    attach_aloha_routines(ir, {"FFV2_0": cpp_to_cuda(tp.FFV2_0_CPP), "FFV2_1": cpp_to_cuda(tp.FFV2_1_CPP)})
+    src = str(tmp_path / "proc.cu")
+    open(src, "w").write(codegen.emit_process_source(ir))
+    so = codegen.compile_source(src, str(tmp_path / "libmfp_1_gg_ttx_ffv2.so"))
+    lib = mf.rt.ProcessLib(so)
+    assert lib.variant == "thread"
+    with pytest.raises(mf.rt.MadflowB200Error):
+        lib.set_variant("hp")
+    npts = 5000
+    x = np.random.default_rng(3).random((npts, 10))
+    p, w, x1, x2 = ops.ramboflow(x, 4, 13e3, [MT, MT], xfactor="converged")
+    lab = ops.boost_to_lab(p, x1, x2)
+    a_s = 0.09 + 0.05 * np.random.default_rng(4).random(npts)
+    params = sm_params(alpha_s=a_s)
+    params["GC_100"] = 0.44j * (2.0 * np.sqrt(np.pi * a_s)) ** 2
+    monkeypatch.setitem(aloha.ROUTINES, "FFV2_0", tp._np_ffv2_0)
+    monkeypatch.setitem(aloha.ROUTINES, "FFV2_1", tp._np_ffv2_1)
+    ref = omatrix.smatrix(ir, lab, params)
+    coup = torch.as_tensor(np.stack([params[c] for c in ir["couplings"]])).cuda().contiguous()
+    out = torch.empty(npts, dtype=torch.float64, device="cuda")
+    lib.smatrix(torch.as_tensor(lab).cuda().contiguous(), 0, npts, [MT, WT], coup, 1, SQH_REF, out)
+    np.testing.assert_allclose(cpu(out), ref, rtol=REL_ME)
+
+
+def test_one_matrix_integration_with_pdf(mf, toy_pdf):
+    """utilities.one_matrix_integration(pdf=, flavours=): the reference's regression harness (utilities.py:42-90,
+    tests/test_integration.py) -- luminosity of the given flavour at the fixed scale q, frozen couplings, COM momenta, no
+    cuts -- fused path == separate calls, and the first iteration == the oracle on the same Philox points.  The
+    reference's 103.4 pb needs the NNPDF31 grid, which is not available offline; this runs on the synthetic set."""
+    from madflow_b200 import process_ir
+    from madflow_b200.utilities import one_matrix_integration
+
+    pd, og = toy_pdf
+    m, model = mf.matrix.get_process("1_gg_ttx")
+    ra = one_matrix_integration(m, model, pdf=pd, flavours=(0,), out_masses=[MT, MT], n_events=40_000, n_iter=1, seed=4)
+    rb = one_matrix_integration(m, model, pdf=pd, flavours=(0,), out_masses=[MT, MT], n_events=40_000, n_iter=1, seed=4, fused=False)
+    assert abs(ra[0] / rb[0] - 1) < 1e-10
+    ir = process_ir.gg_ttx_pinned()
+    a32 = float(np.float32(0.118))
+    xs = ovegas.make_cross_section(ir, lambda a: sm_params(alpha_s=a32), 7e3, [MT, MT], lab_frame=False, pdf=og, fixed_q2=91.46**2)
+    ov = ovegas.Vegas(10, 40_000, seed=4)
+    ov.compile(xs)
+    r0 = ov.run_integration(1)
+    assert abs(ra[0] / r0[0] - 1) < 1e-10
+    with pytest.raises(ValueError):
+        one_matrix_integration(m, model, pdf=pd, out_masses=[MT, MT])

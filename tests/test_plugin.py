@@ -3,6 +3,7 @@
 import fractions
 import importlib
 import os
+import shutil
 import sys
 
 import numpy as np
@@ -182,7 +183,7 @@ def test_aloha_cpp_to_cuda_retargeting():
   V1[2] = COUP * TMP1 * cI;
 }"""
     cu = cpp_to_cuda(cpp)
-    assert cu.startswith("__device__ __forceinline__ void VVV1P0_1(const cxtype V2[], const cxtype V3[], cxtype COUP")
+    assert cu.startswith("__host__ __device__ __forceinline__ void VVV1P0_1(const cxtype V2[], const cxtype V3[], cxtype COUP")
     assert "cxtype V1[])" in cu and "const cxtype V1[]" not in cu
     assert "const cxtype cI(0., 1.);" in cu and "static" not in cu and "std::complex" not in cu
 
@@ -206,3 +207,104 @@ def test_leading_order_wrapper(tmp_path):
     assert '"1_gg_ttx": (Matrix_1_gg_ttx, model_1_gg_ttx)' in text
     assert '"1_gg_ttx": ["ZERO", "ZERO", "mdl_MT", "mdl_MT"]' in text
     assert "generate g g > t t~" in text and "FusedIntegrand(matrix, model, sqrts=SQRTS" in text
+
+
+# the text MG5's C++ ALOHA writer produces for two routines of the electroweak sector (UFO FFV2 = Gamma(3,2,-1) ProjM(-1,1))
+FFV2_0_CPP = """void FFV2_0(std::complex<double> F1[], std::complex<double> F2[], std::complex<double> V3[], std::complex<double> COUP, std::complex<double> & vertex)
+{
+  static std::complex<double> cI = std::complex<double> (0., 1.);
+  std::complex<double> TMP0;
+  TMP0 = (F1[2] * (F2[4] * (V3[2] + V3[5]) + F2[5] * (V3[3] + cI * (V3[4]))) + F1[3] * (F2[4] * (V3[3] - cI * (V3[4])) + F2[5] * (V3[2] - V3[5])));
+  vertex = COUP * - cI * TMP0;
+}"""
+FFV2_1_CPP = """void FFV2_1(std::complex<double> F2[], std::complex<double> V3[], std::complex<double> COUP, double M1, double W1, std::complex<double> F1[])
+{
+  static std::complex<double> cI = std::complex<double> (0., 1.);
+  double P1[4];
+  std::complex<double> denom;
+  F1[0] = +F2[0] + V3[0];
+  F1[1] = +F2[1] + V3[1];
+  P1[0] = -F1[0].real();
+  P1[1] = -F1[1].real();
+  P1[2] = -F1[1].imag();
+  P1[3] = -F1[0].imag();
+  denom = COUP/((P1[0] * P1[0]) - (P1[1] * P1[1]) - (P1[2] * P1[2]) - (P1[3] * P1[3]) - M1 * (M1 - cI * W1));
+  F1[2] = denom * cI * M1 * (F2[4] * (V3[2] + V3[5]) + F2[5] * (V3[3] + cI * (V3[4])));
+  F1[3] = denom * - cI * M1 * (F2[4] * (+cI * (V3[4]) - V3[3]) + F2[5] * (V3[5] - V3[2]));
+  F1[4] = denom * (-cI) * (F2[4] * (P1[0] * (V3[2] + V3[5]) + (P1[1] * (+cI * (V3[4]) - V3[3]) + (P1[2] * (-1.) * (V3[4] + cI * (V3[3])) - P1[3] * (V3[2] + V3[5])))) + F2[5] * (P1[0] * (V3[3] + cI * (V3[4])) + (P1[1] * (V3[5] - V3[2]) + (P1[2] * (-cI * (V3[2]) + cI * (V3[5])) - P1[3] * (V3[3] + cI * (V3[4]))))));
+  F1[5] = denom * cI * (F2[4] * (P1[0] * (+cI * (V3[4]) - V3[3]) + (P1[1] * (V3[2] + V3[5]) + (P1[2] * (-1.) * (+cI * (V3[2] + V3[5])) + P1[3] * (+cI * (V3[4]) - V3[3])))) + F2[5] * (P1[0] * (V3[5] - V3[2]) + (P1[1] * (V3[3] + cI * (V3[4])) + (P1[2] * (V3[4] - cI * (V3[3])) + P1[3] * (V3[5] - V3[2])))));
+}"""
+
+
+def _np_ffv2_0(F1, F2, V3, COUP):
+    TMP0 = (F1[2] * (F2[4] * (V3[2] + V3[5]) + F2[5] * (V3[3] + 1j * V3[4]))
+            + F1[3] * (F2[4] * (V3[3] - 1j * V3[4]) + F2[5] * (V3[2] - V3[5])))
+    return COUP * -1j * TMP0
+
+
+def _np_ffv2_1(F2, V3, COUP, M1, W1):
+    cI = 1j
+    F1 = [None] * 6
+    F1[0], F1[1] = F2[0] + V3[0], F2[1] + V3[1]
+    P1 = [-F1[0].real, -F1[1].real, -F1[1].imag, -F1[0].imag]
+    denom = COUP / (P1[0] ** 2 - P1[1] ** 2 - P1[2] ** 2 - P1[3] ** 2 - M1 * (M1 - cI * W1))
+    F1[2] = denom * cI * M1 * (F2[4] * (V3[2] + V3[5]) + F2[5] * (V3[3] + cI * V3[4]))
+    F1[3] = denom * -cI * M1 * (F2[4] * (cI * V3[4] - V3[3]) + F2[5] * (V3[5] - V3[2]))
+    F1[4] = denom * (-cI) * (F2[4] * (P1[0] * (V3[2] + V3[5]) + (P1[1] * (cI * V3[4] - V3[3]) + (P1[2] * (-1.) * (V3[4] + cI * V3[3]) - P1[3] * (V3[2] + V3[5]))))
+                             + F2[5] * (P1[0] * (V3[3] + cI * V3[4]) + (P1[1] * (V3[5] - V3[2]) + (P1[2] * (-cI * V3[2] + cI * V3[5]) - P1[3] * (V3[3] + cI * V3[4])))))
+    F1[5] = denom * cI * (F2[4] * (P1[0] * (cI * V3[4] - V3[3]) + (P1[1] * (V3[2] + V3[5]) + (P1[2] * (-1.) * (cI * (V3[2] + V3[5])) + P1[3] * (cI * V3[4] - V3[3]))))
+                          + F2[5] * (P1[0] * (V3[5] - V3[2]) + (P1[1] * (V3[3] + cI * V3[4]) + (P1[2] * (V3[4] - cI * V3[3]) + P1[3] * (V3[5] - V3[2])))))
+    return np.stack(np.broadcast_arrays(*F1))
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+def test_plugin_written_aloha_routines_reach_the_kernel(monkeypatch):
+    """A vertex outside the hand-written QCD set (FFV2, the left-handed current of the electroweak sector) and a coupling
+    outside GC_10/11/12: the routine text in MG5's C++ ALOHA format goes through cpp_to_cuda -> attach_aloha_routines ->
+    codegen (pasted into the translation unit, called from the generated matrix()) -> nvcc, and the generated code,
+    executed on the CPU, equals a numpy evaluation of the same call list (reference: PyOut_create_aloha.py:124-197,
+    PyOut_exporter.py:378-407, 507-540)."""
+    import hostcheck as hc
+    from madflow_b200 import codegen, process_ir
+    from madgraph_plugin.PyOut_create_aloha import cpp_to_cuda
+    from madgraph_plugin.PyOut_exporter import PyOutExporterError, attach_aloha_routines, coupling_power_law
+    from oracle import SQH_REF, aloha
+    from oracle import matrix as omatrix
+
+    ir = process_ir.gg_ttx_pinned()
+    ir["name"] = "1_gg_ttx_ffv2"
+    # the t-channel diagram with FFV2 vertices and their own coupling: a different (unphysical) process, the same plumbing
+    for c in ir["calls"]:
+        if c["op"] == "FFV1_1":
+            c["op"], c["coup"] = "FFV2_1", "GC_100"
+        elif c.get("amp") == 1:
+            c["op"], c["coup"] = "FFV2_0", "GC_100"
+    ir["couplings"] = sorted({c["coup"] for c in ir["calls"] if "coup" in c})
+    law = coupling_power_law("(ee*complex(0,1))/(sw*cmath.sqrt(2))*G**2", {"ee": 0.3, "sw": 0.48})
+    assert law is not None and law[2] == 2
+    ir["coupling_defs"] = {"GC_100": list(law)}
+    with pytest.raises(PyOutExporterError):
+        attach_aloha_routines(process_ir.clone(ir), {})
+    with pytest.raises(ValueError):
+        codegen.emit_process_source(ir)          # routines neither built in nor supplied
+    attach_aloha_routines(ir, {"FFV2_0": cpp_to_cuda(FFV2_0_CPP), "FFV2_1": cpp_to_cuda(FFV2_1_CPP), "FFV9_9": "unused"})
+    assert sorted(ir["aloha_routines"]) == ["FFV2_0", "FFV2_1"]
+    src = codegen.emit_process_source(ir)
+    assert "HP_AVAILABLE = false" in src and "plg_FFV2_1(" in src and "namespace plg" in src
+    process_ir.loads(process_ir.dumps(ir))
+    lib = hc.process(ir)
+    from test_procgen import _points
+    from conftest import MT, WT, sm_params
+
+    p = _points(0, n=50, seed=3)
+    a_s = 0.09 + 0.05 * np.random.default_rng(3).random(50)
+    params = sm_params(alpha_s=a_s)
+    G = 2.0 * np.sqrt(np.pi * a_s)
+    params["GC_100"] = complex(law[0], law[1]) * G ** law[2]
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    monkeypatch.setitem(aloha.ROUTINES, "FFV2_0", _np_ffv2_0)
+    monkeypatch.setitem(aloha.ROUTINES, "FFV2_1", _np_ffv2_1)
+    ref = omatrix.smatrix(ir, p, params)
+    out = hc.smatrix(lib, ir, p, [MT, WT], coup, SQH_REF)
+    np.testing.assert_allclose(out, ref, rtol=1e-12)
+    assert np.all(ref > 0)
