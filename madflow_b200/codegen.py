@@ -238,16 +238,28 @@ def hp_config(ir, key):
       MINBLOCKS  resident blocks per SM the register allocation aims at
       PERSIST    pair objects (vertex numerators) of up to this many helicity variants are evaluated once, together
                  with the currents of their level, and stay in shared memory; the others are evaluated batch by batch
+      PERSIST_FREE   with helicity passes: the pair objects that do not hold the pass leg are the same in every pass; up to
+                 this many complex numbers of them per event are evaluated once before the passes (a phase of its own
+                 after the last level of currents) and kept in shared memory
+      TSPLIT     objects with more terms than this are evaluated by 2, 4 or 8 neighbouring lanes (a few terms each, summed
+                 with warp shuffles in a fixed order); 0 = one thread per (object, variant) whatever its length.  With few
+                 units per phase and up to 12 terms per object (g g > t t~ g g g) the longest unit sets the phase's time
+      TMEMJ      1 = the JAMP accumulators live in Tensor Memory between the JAMP phases of the batches instead of in
+                 registers (frees NCOLOR/NCG complex registers for the current / pair / tile phases)
     Defaults from measurements on B200: up to 64 helicity combinations two events per
-    block and all JAMPs in one thread; beyond, one event per block (its wavefunctions fill a third of the
-    shared memory), 8 colour groups and batches of 64 amplitudes."""
+    block and all JAMPs in one thread (Tensor Memory off: with two blocks per SM it halves the rate, 2.4e7 -> 1.4e7
+    events/s for g g > t t~ g g, profiles/r02j_ttxgg_tmem.log); beyond, one event per block, 8 colour groups, batches
+    of 64 amplitudes, JAMPs in Tensor Memory."""
     env = os.environ.get("MADFLOW_B200_HP_" + key)
     if env:
         return int(env)
     if ir["ncomb"] > 64:
-        return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 4096, "MINBLOCKS": 1, "PERSIST": 0}[key]
+        # g g > t t~ g g g, measured (profiles/r02k_ttxggg_tmem_tuning.log): JAMPs parked in Tensor Memory 7.9e5 -> 9.4e5
+        # events/s (no more spills at 128 registers), + pass-independent pair objects kept 9.9e5; 4 colour groups 6.3e5
+        return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 2048 if hp_use_plan(ir) else 4096, "MINBLOCKS": 1, "PERSIST": 0,
+                "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 3, "TMEMJ": 1}[key]
     return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 21, "SCRATCH": 512, "MINBLOCKS": 2,
-            "PERSIST": 8 if hp_use_plan(ir) else 0}[key]
+            "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0}[key]
 
 
 def hp_use_plan(ir):
@@ -444,10 +456,18 @@ def emit_hp(ir):
         pr = {"legs": legs, "nv": 1 << len(legs), "terms": p["terms"], "finish": "none"}
         pr["ready"] = 1 + max(wfs[w]["level"] for t in p["terms"] for w in t["in"])
         pr["persist"] = pr["nv"] <= PERSIST and pr["ready"] <= maxlevel
+        pairs.append(pr)
+    # PERSIST_FREE = shared-memory budget (complex numbers per event) for pass-independent pair objects: those with the
+    # most terms first (the evaluations saved per complex number stored)
+    budget = hp_config(ir, "PERSIST_FREE") if LSTAR is not None else 0
+    for pr in sorted(pairs, key=lambda q: -len(q["terms"])):
+        if not pr["persist"] and LSTAR not in pr["legs"] and 4 * pr["nv"] <= budget:
+            pr["persist"] = True
+            budget -= 4 * pr["nv"]
+    for pr in pairs:
         if pr["persist"]:
             pr["abs_off"] = off
             off += 4 * pr["nv"]
-        pairs.append(pr)
     assert all(pr["nv"] <= 32 for pr in pairs), "pair objects hold up to 32 helicity variants"
     wfsize = off
 
@@ -525,25 +545,51 @@ def emit_hp(ir):
                 f"{{{', '.join(str(wfs[w]['off']) for w in ins3)}}}, {{{', '.join(str(wfs[w]['nv']) for w in ins3)}}}, "
                 f"{{{vm[0]}, {vm[1]}, {vm[2]}}}, {FINISH[obj['finish']]}, {pidx(obj.get('mass', 'ZERO'))}, {pidx(obj.get('width', 'ZERO'))}}}")
 
-    def add_units(obj, out_off, variants):
+    TSPLIT = hp_config(ir, "TSPLIT")
+
+    def add_units(obj, out_off, variants, phase_units):
+        """Append the units of `obj` for `variants` to phase_units as groups [(first item, count), ...]: a unit with more
+        than TSPLIT terms is split into 2^k parts that neighbouring lanes evaluate and add up with warp shuffles."""
         first = len(trows)
         masks = []
         for t in obj["terms"]:
             st, ins, q = lowered(t)
             masks.append([vmask(obj["legs"], wfs[w]["legs"]) for w in ins] + [0] * (3 - len(ins)))
             trows.append(term_row(obj, t, out_off))
+        nt = len(masks)
+        parts = 1
+        while TSPLIT and parts < 8 and -(-nt // parts) > TSPLIT:
+            parts *= 2
+        per = -(-nt // parts)
         for v in variants:
-            urow.append(f"{len(irow) | len(obj['terms']) << 24}u")
-            for ti, m in enumerate(masks):
-                irow.append(f"{{{first + ti}, {v}, {{{pext(v, m[0])}, {pext(v, m[1])}, {pext(v, m[2])}}}, 0}}")
+            group = []
+            for pi in range(parts):
+                mine = list(range(pi * per, min((pi + 1) * per, nt)))
+                group.append((len(irow), len(mine)))
+                for ti in mine:
+                    m = masks[ti]
+                    irow.append(f"{{{first + ti}, {v}, {{{pext(v, m[0])}, {pext(v, m[1])}, {pext(v, m[2])}}}, 0}}")
+            phase_units.append(group)
+
+    def flush_units(phase_units):
+        """Lay the groups of one phase out: largest groups first, so that every group of 2^k parts starts at a multiple of
+        2^k (its lanes sit in one warp, the phase starts at lane 0).  Unit = first item | items << 24 | log2(parts) << 28."""
+        for group in sorted(phase_units, key=lambda g: -len(g)):     # stable: keeps the type order within a size
+            glog = len(group).bit_length() - 1
+            for item0, cnt in group:
+                assert cnt < 16 and item0 < (1 << 24)
+                urow.append(f"{item0 | cnt << 24 | glog << 28}u")
 
     begins = []
+    maxlevel = max([maxlevel] + [pr["ready"] for pr in pairs if pr["persist"]])   # phases = levels of currents (+ one for pairs)
     for lev in range(0, maxlevel + 2):
         begins.append(len(urow))
         todo = [(w, w["off"]) for w in wfs if w["ext"] is None and w["level"] == lev]
         todo += [(pr, pr["abs_off"]) for pr in pairs if pr["persist"] and pr["ready"] == lev]
+        phase_units = []
         for obj, o_ in sorted(todo, key=lambda q: (len(q[0]["terms"]), type_key(q[0]), FINISH[q[0]["finish"]])):
-            add_units(obj, o_, range(obj["nv"]))
+            add_units(obj, o_, range(obj["nv"]), phase_units)
+        flush_units(phase_units)
 
     # ---- tensor-core tiles: amplitude(variant of Q, variant of x) = sum_k Q_k x_k is an (nvq x 4)(4 x nvx)
     # complex product; one work item = 8 variants of Q (rows) x 8 variants of x (columns)
@@ -553,9 +599,11 @@ def emit_hp(ir):
     for p in range(NPASS):
         for bi, (cur_pairs, cur_amps) in enumerate(batches):
             ub, tb = len(urow), len(tile_rows)
+            phase_units = []
             for pi in cur_pairs:
                 pr = pairs[pi]
-                add_units(pr, pr["abs_off"], vrange(pr["legs"], pr["nv"], p))
+                add_units(pr, pr["abs_off"], vrange(pr["legs"], pr["nv"], p), phase_units)
+            flush_units(phase_units)
             for slot, k in enumerate(cur_amps):
                 r = amp_rows[k]
                 xw, pr = wfs[r["x"]], pairs[r["pair"]]
@@ -618,7 +666,10 @@ def emit_hp(ir):
     L.append(both("mf::HpExt", "ext", n, ", ".join(
         f"{{{HP_TYPES[x['call']['op']]}, {x['call']['leg']}, {x['call']['nsf']}, {pidx(x['call']['mass'])}, {x['out']}}}"
         for x in ext_by_leg)))
-    L.append(both("mf::HpTerm", "terms", max(len(trows), 1), ",\n  ".join(trows) if trows else "{0}", const=not big))
+    # the term rows are the hottest table: constant memory (its cache is not squeezed by the shared-memory carve-out the
+    # way L1 is) while they fit next to the other constant tables
+    terms_const = len(trows) * 32 <= int(os.environ.get("MADFLOW_B200_HP_TERMS_CONST", 48 * 1024))
+    L.append(both("mf::HpTerm", "terms", max(len(trows), 1), ",\n  ".join(trows) if trows else "{0}", const=terms_const))
     L.append(both("mf::HpWorkItem", "work_items", max(len(irow), 1), ", ".join(irow) if irow else "{0, 0, {0, 0, 0}, 0}", const=False))
     L.append(both("unsigned", "units", max(len(urow), 1), ", ".join(urow) if urow else "0u", const=False))
     L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
@@ -843,6 +894,10 @@ struct Proc {{
   static constexpr int HP_NPASS = {hp['npass']}, HP_NHP = NCOMB / HP_NPASS;
   static constexpr int HP_NB = {hp_nb}, HP_NCG = {hp_ncg}, HP_NJ = {hp_nj}, HP_NTILES = {hp['ntiles']};
   static constexpr int HP_THREADS = HP_E * HP_NHP * HP_NCG;                // threads per block
+  // objects with many terms are split over neighbouring lanes (codegen.hp_config TSPLIT)
+  static constexpr bool HP_SPLIT = {'true' if hp_config(ir, "TSPLIT") else 'false'};
+  // the JAMP accumulators are parked in Tensor Memory between the JAMP phases of the batches (process_kernels_hp.cuh)
+  static constexpr bool HP_TMEM_J = {'true' if (hp_config(ir, "TMEMJ") and not hp['unroll']) else 'false'};
   // tile descriptors per warp and trip (x HP_E tiles in flight): 2 tiles in flight measured best -- more only adds
   // padded tiles at the end of a batch (g g > t t~ g g: 17.7e6 events/s with 2, 16.5e6 with 4, 14.5e6 with 8)
   static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 2)) // hp_e)};

@@ -136,7 +136,11 @@ MF_DEV void rambo(const double* xr, double sqrts, const double* masses, bool mas
   for (int i = 0; i < NOUT; ++i) msum += masses[i];
   const double r = msum / sqrts;
   double x = sqrt(1.0 - r * r);
-  // Newton on f(x) = sum_i sqrt(m_i^2 + x^2 e_i^2) - sqrts, per event (phasespace.py:76-90)
+  // Newton on f(x) = sum_i sqrt(m_i^2 + x^2 e_i^2) - sqrts, per event (phasespace.py:76-90).  The reference stops at
+  // f <= ACC = 1e-14 GeV (absolute), which the round-off of f at sqrt(s) ~ 1e2..1e4 GeV never lets it reach: it would
+  // always run all 10 steps.  Here the loop also stops once |f| is at the round-off level of sqrt(s); the steps that
+  // are skipped would move x by < 1e-15 relative.
+  const double f_noise = 8.0 * 2.220446049250313e-16 * sqrts;
   for (int it = 0; it < 10; ++it) {
     double f0 = -sqrts, g0 = 0.0;
 #pragma unroll
@@ -148,6 +152,7 @@ MF_DEV void rambo(const double* xr, double sqrts, const double* masses, bool mas
     }
     if (!(f0 > k.acc)) break;
     x = x - f0 / (x * g0);
+    if (fabs(f0) <= f_noise) break;   // this step was the last one that can change x
   }
   double wt2 = 1.0, wt3 = 0.0;
 #pragma unroll

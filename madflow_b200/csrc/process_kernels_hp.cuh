@@ -185,13 +185,12 @@ MF_DEV void hp_quartic_term(unsigned char d, const cxd a[6], const cxd b[6], con
 }
 
 // One unit of the current / pair-object phases: (object, helicity variant) of the event whose area is ev_e.  The
-// terms of the object are evaluated in turn and added up; the last one applies the propagator (currents) and stores.
+// terms of the object are evaluated in turn and added up (hp_unit_terms); the propagator is applied (currents) and the
+// result stored by hp_unit_finish.  An object with many terms is split over 2^k neighbouring lanes (k = bits 28-29 of
+// the unit descriptor), each evaluating a few terms; hp_units adds the partial sums with warp shuffles in a fixed order.
 template <class P>
-MF_DEV void hp_unit(const unsigned unit, const double* par, const cxd* coup_e, cxd* ev_e) {
-  const int begin = (int)(unit & 0xffffffu), count = (int)(unit >> 24);
-  cxd Q[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
-  HpTerm t;
-  HpWorkItem it;
+MF_DEV void hp_unit_terms(const unsigned unit, const cxd* coup_e, const cxd* ev_e, cxd Q[4], HpTerm& t, HpWorkItem& it) {
+  const int begin = (int)(unit & 0xffffffu), count = (int)((unit >> 24) & 0xfu);
 #pragma unroll 1
   for (int j = 0; j < count; ++j) {
     it = P::work_item(begin + j);
@@ -252,6 +251,10 @@ MF_DEV void hp_unit(const unsigned unit, const double* par, const cxd* coup_e, c
       } break;
     }
   }
+}
+
+template <class P>
+MF_DEV void hp_unit_finish(const HpTerm& t, const HpWorkItem& it, const cxd Q[4], const double* par, cxd* ev_e) {
   cxd* o = ev_e + t.out_off;
   const int nv = t.out_nv, v = it.v;
   if (t.finish == HP_F_NONE) {  // a vertex numerator (pair object): components only
@@ -296,6 +299,58 @@ MF_DEV void hp_unit(const unsigned unit, const double* par, const cxd* coup_e, c
   if (v == 0) o[0] = w[0], o[1] = w[1];
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[2 + hp_slot(k, nv, v)] = r[k];
+}
+
+// The units [begin, begin + n) of a phase for the E events of the block; thread w = tid, tid + nthreads, .. takes unit
+// w / E for event w % E.  SPLIT: the phase holds units split over neighbouring lanes (stride E); all lanes of a warp
+// then run the same number of trips and take part in the shuffles.  On the host the parts of a group are simply
+// evaluated one after the other.
+template <class P, bool SPLIT>
+MF_DEV void hp_units(int begin, int n, int tid, int nthreads, const double* par, const cxd* coup, cxd* ev) {
+  constexpr int E = P::HP_E, EVS = P::HP_EVSTRIDE;
+  const int total = n * E;
+#ifdef __CUDA_ARCH__
+  const int bound = SPLIT ? ((total + 31) & ~31) : total;
+#pragma unroll 1
+  for (int w = tid; w < bound; w += nthreads) {
+    const int ii = w / E, e = w - ii * E;
+    const unsigned unit = w < total ? P::unit(begin + ii) : 0u;
+    cxd Q[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
+    HpTerm t;
+    HpWorkItem it;
+    hp_unit_terms<P>(unit, coup + e * P::NCOUP, ev + e * EVS, Q, t, it);
+    if constexpr (SPLIT) {
+      // partial sums of a group of 2^glog lanes (stride E) -> its first lane, always in the order of a binary tree
+      const int glog = (int)((unit >> 28) & 3u), g = 1 << glog, part = ii & (g - 1);
+      const int gmax = __reduce_max_sync(0xffffffffu, glog);
+#pragma unroll 1
+      for (int r = 0; r < gmax; ++r) {
+        const int o = 1 << r;
+        const bool take = r < glog && (part & ((o << 1) - 1)) == 0;   // this lane adds the lane `o` parts further on
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double re = __shfl_down_sync(0xffffffffu, Q[k].re, o * E);
+          const double im = __shfl_down_sync(0xffffffffu, Q[k].im, o * E);
+          if (take) Q[k].re += re, Q[k].im += im;
+        }
+      }
+      if (part != 0) continue;
+    }
+    if ((unit >> 24) & 0xfu) hp_unit_finish<P>(t, it, Q, par, ev + e * EVS);
+  }
+#else
+  for (int w = tid; w < total; w += nthreads) {
+    const int ii = w / E, e = w - ii * E;
+    const unsigned unit = P::unit(begin + ii);
+    const int g = 1 << ((unit >> 28) & 3u);
+    if (ii & (g - 1)) continue;   // a part of a group: evaluated with its first unit
+    cxd Q[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
+    HpTerm t;
+    HpWorkItem it;
+    for (int pp = g - 1; pp >= 0; --pp) hp_unit_terms<P>(P::unit(begin + ii + pp), coup + e * P::NCOUP, ev + e * EVS, Q, t, it);
+    hp_unit_finish<P>(t, it, Q, par, ev + e * EVS);
+  }
+#endif
 }
 
 // vtab[mask * NCOMB + h]: the helicity variant, of an object over the leg set `mask`, that belongs to
@@ -419,6 +474,80 @@ inline void hp_mma_tile_host(const HpTile* tp, const cxd* ev_e, cxd* abuf_e) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// JAMP accumulators in Tensor Memory.  A thread's JAMPs (HP_NJ complex numbers) are live from the first batch of a
+// helicity pass to the colour contraction, but only touched in the short JAMP phase of every batch; kept in registers
+// they take 60-96 of a thread's registers away from the current / pair / tile phases (g g > t t~ g g g, 128 registers
+// per thread: 5 KB of spills per thread, all of them in the pair phase).  Blackwell's TMEM (256 KB per SM, 128 lanes x
+// 512 columns of 32 bits) is not used otherwise -- there is no FP64 tcgen05.mma -- so the accumulators are parked there
+// between JAMP phases: tcgen05.st after a batch, tcgen05.ld before the next.  Shape 32x32b: lane i of a warp owns TMEM
+// lane 32 * (warp % 4) + i, its words are consecutive columns; warps that share a lane quarter use different columns.
+template <int NWORDS>
+__device__ __forceinline__ void tmem_store_words(unsigned taddr, const unsigned (&r)[NWORDS]) {
+  static_assert(NWORDS % 16 == 0, "multiples of 16 words");
+#ifdef __CUDA_ARCH__
+#pragma unroll
+  for (int c = 0; c < NWORDS; c += 16)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr + c), "r"(r[c]), "r"(r[c + 1]), "r"(r[c + 2]), "r"(r[c + 3]), "r"(r[c + 4]), "r"(r[c + 5]),
+                 "r"(r[c + 6]), "r"(r[c + 7]), "r"(r[c + 8]), "r"(r[c + 9]), "r"(r[c + 10]), "r"(r[c + 11]), "r"(r[c + 12]),
+                 "r"(r[c + 13]), "r"(r[c + 14]), "r"(r[c + 15])
+                 : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+}
+template <int NWORDS>
+__device__ __forceinline__ void tmem_load_words(unsigned taddr, unsigned (&r)[NWORDS]) {
+  static_assert(NWORDS % 16 == 0, "multiples of 16 words");
+#ifdef __CUDA_ARCH__
+#pragma unroll
+  for (int c = 0; c < NWORDS; c += 16)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[c]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]),
+                   "=r"(r[c + 7]), "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]), "=r"(r[c + 12]),
+                   "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
+                 : "r"(taddr + c)
+                 : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
+}
+// words per thread (padded to a multiple of 16) and columns per block (a power of two >= 32) of the JAMP store
+template <class P>
+struct HpTmem {
+  static constexpr int NWORDS = ((4 * P::HP_NJ + 15) / 16) * 16;
+  static constexpr int WARPS_PER_QUARTER = (P::HP_THREADS / 32 + 3) / 4;
+  static constexpr int NEED = NWORDS * WARPS_PER_QUARTER;
+  static constexpr int NCOLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+  static_assert(NEED <= 512, "the JAMPs of a block do not fit in Tensor Memory");
+};
+template <class P>
+__device__ __forceinline__ void hp_jamp_park(unsigned tmem_base, const cxd (&J)[P::HP_NJ]) {
+#ifdef __CUDA_ARCH__
+  constexpr int NW = HpTmem<P>::NWORDS;
+  const int warp = threadIdx.x >> 5;
+  unsigned r[NW];
+#pragma unroll
+  for (int j = 0; j < NW / 4; ++j) {
+    const cxd v = j < P::HP_NJ ? J[j] : mk(0.0, 0.0);
+    r[4 * j] = (unsigned)__double2loint(v.re), r[4 * j + 1] = (unsigned)__double2hiint(v.re);
+    r[4 * j + 2] = (unsigned)__double2loint(v.im), r[4 * j + 3] = (unsigned)__double2hiint(v.im);
+  }
+  tmem_store_words<NW>(tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * NW), r);
+#endif
+}
+template <class P>
+__device__ __forceinline__ void hp_jamp_fetch(unsigned tmem_base, cxd (&J)[P::HP_NJ]) {
+#ifdef __CUDA_ARCH__
+  constexpr int NW = HpTmem<P>::NWORDS;
+  const int warp = threadIdx.x >> 5;
+  unsigned r[NW];
+  tmem_load_words<NW>(tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * NW), r);
+#pragma unroll
+  for (int j = 0; j < P::HP_NJ; ++j)
+    J[j] = mk(__hiloint2double((int)r[4 * j + 1], (int)r[4 * j]), __hiloint2double((int)r[4 * j + 3], (int)r[4 * j + 2]));
+#endif
+}
+
 // Optional phase timers (-DMF_HP_PROFILE, tools/profile_phases.py): SM cycles spent by each block in
 // externals / currents / pair objects / amplitudes / JAMP / colour+reduction, summed over blocks.
 #ifdef MF_HP_PROFILE
@@ -506,7 +635,8 @@ MF_DEV double hp_colour_loop(const double* planes, int hl, int cg, const double*
 template <class P>
 __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events */, const double* mom,
                                                    const cxd* coup, const double* par, double sqh, cxd* ev,
-                                                   const unsigned char* vtab, double* red /* [T/32] */, int only_h) {
+                                                   const unsigned char* vtab, double* red /* [T/32] */, int only_h,
+                                                   unsigned tmem_base = 0u) {
   constexpr int E = P::HP_E, NHP = P::HP_NHP, NCG = P::HP_NCG, TE = NHP * NCG, T = E * TE, EVS = P::HP_EVSTRIDE;
   const int tid = threadIdx.x;
   MF_PROF_DECL
@@ -527,12 +657,7 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
 #pragma unroll 1
   for (int L = 2; L <= P::HP_MAXLEVEL; ++L) {
     // units (object, variant) of this level: the currents and the pair objects that stay in shared memory
-    const int begin = P::level_begin(L), total = (P::level_begin(L + 1) - begin) * E;
-#pragma unroll 1
-    for (int w = tid; w < total; w += T) {
-      const int ii = w / E, e = w - ii * E;
-      hp_unit<P>(P::unit(begin + ii), par, coup + e * P::NCOUP, ev + e * EVS);
-    }
+    hp_units<P, P::HP_SPLIT>(P::level_begin(L), P::level_begin(L + 1) - P::level_begin(L), tid, T, par, coup, ev);
     __syncthreads();
   }
   MF_PROF(1);
@@ -554,12 +679,11 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
 #pragma unroll 1
       for (int bi = 0; bi < P::HP_NBATCH; ++bi) {
         const HpBatch bt = P::batch(pass * P::HP_NBATCH + bi);
-        const int total = (bt.unit_end - bt.unit_begin) * E;
-#pragma unroll 1
-        for (int w = tid; w < total; w += T) {
-          const int ii = w / E, ee = w - ii * E;
-          hp_unit<P>(P::unit(bt.unit_begin + ii), par, coup + ee * P::NCOUP, ev + ee * EVS);
-        }
+#ifdef MF_HP_EXPERIMENT_NOJ   // measurement only (wrong results): the JAMPs are not kept across the pair phase
+#pragma unroll
+        for (int j = 0; j < P::HP_NJ; ++j) J[j] = mk(0.0, 0.0);
+#endif
+        hp_units<P, P::HP_SPLIT>(bt.unit_begin, bt.unit_end - bt.unit_begin, tid, T, par, coup, ev);
         __syncthreads();   // pair objects complete; the JAMP reads of the batch before are done (amplitude buffer reused)
         MF_PROF(2);
         {
@@ -585,7 +709,22 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
         }
         __syncthreads();
         MF_PROF(3);
+#ifdef __CUDA_ARCH__
+        if constexpr (P::HP_TMEM_J) {   // the JAMPs were parked in Tensor Memory during the pair and tile phases
+          if (bi > 0) {
+            hp_jamp_fetch<P>(tmem_base, J);
+          } else {   // defined on every path: nothing of J is live before this point
+#pragma unroll
+            for (int j = 0; j < P::HP_NJ; ++j) J[j] = mk(0.0, 0.0);
+          }
+        }
+#endif
         P::jamp_batch(bi, cg, abuf_h, J);
+#ifdef __CUDA_ARCH__
+        if constexpr (P::HP_TMEM_J) {
+          if (bi + 1 < P::HP_NBATCH) hp_jamp_park<P>(tmem_base, J);
+        }
+#endif
         MF_PROF(4);
       }
       // the helicity combination of this thread within the whole table, and the row asked for (if any)
@@ -658,6 +797,7 @@ struct HpSmatrixSmem {
   double mom[E * P::NEXT * 4];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
   double red[T / 32 + 1];
+  unsigned tmem_addr;   // base of the block's Tensor Memory allocation (HP_TMEM_J)
   unsigned char vtab[P::HP_UNROLL ? (1 << P::NEXT) * P::NCOMB : 16];  // straight-line flavour only
   // followed by the event areas: cxd ev[E][HP_EVSTRIDE] = wavefunctions | pair objects | amplitude buffer
 };
@@ -671,6 +811,19 @@ __global__ void __launch_bounds__(P::HP_THREADS, P::HP_MINBLOCKS) smatrix_kernel
   const int tid = threadIdx.x;
   if constexpr (P::HP_UNROLL)
     for (int i = tid; i < (1 << P::NEXT) * P::NCOMB; i += T) hp_fill_vtab<P>(i, s.vtab);
+  unsigned tmem_base = 0u;
+  if constexpr (P::HP_TMEM_J) {   // Tensor Memory for the JAMP accumulators: warp 0 allocates, everybody reads the address
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s.tmem_addr)),
+                   "n"(HpTmem<P>::NCOLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_base = s.tmem_addr;
+  }
   int only_h = -1;
   if (a.only_comb >= 0) {
     only_h = 0;
@@ -706,11 +859,16 @@ __global__ void __launch_bounds__(P::HP_THREADS, P::HP_MINBLOCKS) smatrix_kernel
         }
       }
       __syncthreads();
-      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, evarea, s.vtab, s.red, only_h);
+      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, evarea, s.vtab, s.red, only_h, tmem_base);
       const int e = tid / TE;
       if (tid - e * TE == 0 && e < nev) a.out[ev0 + e] = me;
       __syncthreads();
     }
+  }
+  if constexpr (P::HP_TMEM_J) {
+    __syncthreads();
+    if (tid < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(HpTmem<P>::NCOLS) : "memory");
   }
 }
 
@@ -775,11 +933,18 @@ long long integrand_workspace_hp(long long nevents) {
   return (long long)event_buffer_layout(nevents, hp_segments<P>(integrand_blocks_hp<P>()), P::NEXT, NDIM, nullptr, nullptr);
 }
 
+// the segmentation the last launch cut this workspace into: the event view must be laid out the same way even if the
+// caller's grid size differed from integrand_blocks_hp() or the override changed in between
+static int g_last_nseg = 0;
+static long long g_last_nevents = -1;
+static const void* g_last_workspace = nullptr;
+
 template <class P>
 int integrand_events_hp(void* d_workspace, long long nevents, mfp_event_view* out) {
   constexpr int NDIM = 4 * (P::NEXT - 2) + 2;
   EventBuffer b;
-  event_buffer_layout(nevents, hp_segments<P>(integrand_blocks_hp<P>()), P::NEXT, NDIM, d_workspace, &b);
+  const bool same = g_last_nseg > 0 && g_last_nevents == nevents && g_last_workspace == d_workspace;
+  event_buffer_layout(nevents, same ? g_last_nseg : hp_segments<P>(integrand_blocks_hp<P>()), P::NEXT, NDIM, d_workspace, &b);
   out->d_mom = b.mom, out->d_weight = b.w, out->d_me = b.me, out->d_alpha_s = b.as, out->capacity = b.cap;
   out->d_bins = b.bins;
   return 0;
@@ -797,6 +962,7 @@ int launch_integrand_hp(const mfp_integrand_args* u, cudaStream_t st) {
   const size_t need = event_buffer_layout(u->nevents, nseg, P::NEXT, NDIM, u->d_workspace, &g.buf);
   if (!u->d_workspace || (size_t)u->workspace_bytes < need)
     return fail_msg("mfp_integrand: workspace missing or smaller than mfp_integrand_workspace(nevents)");
+  g_last_nseg = nseg, g_last_nevents = u->nevents, g_last_workspace = u->d_workspace;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

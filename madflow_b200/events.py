@@ -66,12 +66,17 @@ class Histogram:
 class EventSink:
     """Consumes the device event buffer after every launch of a FusedIntegrand."""
 
-    def __init__(self, integrand, histograms=(), unweight=False, capacity=1_000_000, seed=1234, wmax=None, wmax_scale=8.0):
+    def __init__(self, integrand, histograms=(), unweight=False, capacity=1_000_000, seed=1234, wmax=None, wmax_scale=8.0,
+                 collect_only=False):
         """unweight: keep slot i with probability min(1, |w_i| / wmax) and weight sign(w_i) max(|w_i|, wmax) -- an
-        unbiased sample in which all events but the few above wmax carry the same weight.  wmax: fixed threshold,
-        or None: min(largest weight seen, wmax_scale * sum w^2 / sum |w|) from the launches seen so far (the
-        first launch only feeds the statistics).  With the heavy-tailed weights of a flat phase space the largest
-        weight alone would make the efficiency collapse."""
+        unbiased sample in which all events but the few above wmax carry the same weight; the events above wmax keep
+        their own, larger weight (write_lhe scales it, it is never clipped).  wmax: ONE threshold for the whole
+        sample -- given, or frozen by freeze_threshold() from the weight statistics collected so far,
+        min(largest weight seen, wmax_scale * sum w^2 / sum |w|); with the heavy-tailed weights of a flat phase space
+        the largest weight alone would make the efficiency collapse.  collect_only: only gather the weight statistics
+        (no histograms, no selection) until freeze_threshold() -- what madflow_exec does during the last warm-up
+        iteration.  Without a frozen threshold the sink falls back to the running estimate, which changes from launch
+        to launch (a mixture of thresholds: still unbiased event by event through the weights, but not one sample)."""
         self.integrand = integrand
         self.histograms = list(histograms)
         self.unweight = bool(unweight)
@@ -80,6 +85,7 @@ class EventSink:
         self.wmax = float(wmax) if wmax else None
         self.wmax_scale = float(wmax_scale)
         self.enabled = True
+        self.collect_only = bool(collect_only)
         dev = config.device()
         n = integrand.nexternal
         self._nstat = int(rt.core().mf_weight_stats_blocks())
@@ -99,13 +105,14 @@ class EventSink:
             return
         lib = rt.core()
         nslots = int(mom.shape[0])
-        for h in self.histograms:
-            h.fill(mom, me, weight)
+        if not self.collect_only:
+            for h in self.histograms:
+                h.fill(mom, me, weight)
         if self.unweight:
             wmax = self.wmax
             if wmax is None and self.launches > 0:
                 wmax = self.threshold()
-            if wmax:
+            if wmax and not self.collect_only:
                 # global slot index: unique per (iteration, rank, launch) as long as capacities do not change
                 rt.check(lib, lib.mf_select_events(rt.ptr(mom), rt.ptr(me), rt.ptr(weight), ctypes.c_int64(nslots),
                                                    int(mom.shape[1]), ctypes.c_double(wmax), ctypes.c_uint64(self.seed),
@@ -129,6 +136,21 @@ class EventSink:
         mx, s1, s2 = self._stats.tolist()
         return min(mx, self.wmax_scale * s2 / s1) if s1 > 0.0 else 0.0
 
+    def freeze_threshold(self):
+        """Fix the unweighting threshold at its current estimate and start filling histograms / keeping events."""
+        if self.unweight:
+            self.wmax = self.threshold() or None
+        self.collect_only = False
+        return self.wmax
+
+    def overweight(self):
+        """(fraction of the kept events above the threshold, their share of the sample's total |weight|)."""
+        _, w = self.events()
+        if len(w) == 0 or not self.wmax:
+            return 0.0, 0.0
+        over = np.abs(w) > self.wmax * (1.0 + 1e-12)
+        return float(np.mean(over)), float(np.sum(np.abs(w[over])) / np.sum(np.abs(w)))
+
     def events(self):
         """(momenta (n, nexternal, 4), weights (n,)) of the kept events as numpy arrays, in global-index order."""
         if not self.unweight:
@@ -142,10 +164,12 @@ class EventSink:
         return self.unweight and int(self._count.item()) > self.capacity
 
     def write_lhe(self, writer, cross=None):
-        """Write the kept events through an LheWriter; every event gets weight `cross` (the integrated cross
-        section, as the reference does after unweighting, lhe_writer.py:339-341) or its own weight."""
+        """Write the kept events through an LheWriter.  cross: the integrated cross section -- an event at the threshold
+        gets weight +-cross (as the reference assigns after unweighting, lhe_writer.py:339-341), an event above it
+        +-cross * |w| / wmax: the excess weight of the tail is kept, so the sample stays unbiased.  None: own weights."""
         mom, w = self.events()
         if cross is not None:
-            w = np.sign(w) * float(cross)
+            scale = np.maximum(np.abs(w) / self.wmax, 1.0) if self.wmax else 1.0
+            w = np.sign(w) * float(cross) * scale
         writer.lhe_parser(mom, w)
         return len(w)

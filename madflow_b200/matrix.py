@@ -177,10 +177,35 @@ def load_ir(name):
     return None
 
 
-def get_process(name):
-    """(Matrix, Model) for one compiled process, e.g. "1_gg_ttx"."""
+# where the masses and widths of the built-in (SM) processes sit in an SLHA param_card
+PARAM_CARD_ENTRIES = {"mdl_MT": ("MASS", 6), "mdl_WT": ("DECAY", 6), "mdl_MB": ("MASS", 5), "mdl_MZ": ("MASS", 23),
+                      "mdl_WZ": ("DECAY", 23), "mdl_MW": ("MASS", 24), "mdl_WW": ("DECAY", 24), "mdl_MH": ("MASS", 25),
+                      "mdl_WH": ("DECAY", 25)}
+
+
+def param_values_from_card(path, names):
+    """Masses / widths `names` from an SLHA param_card (reference: get_model_param(model, param_card_path),
+    matrix_method_python.inc:36-41, madflow_exec.py:130-136); entries the card does not have keep their defaults."""
+    from .param_card import ParamCard
+
+    card = ParamCard(str(path))
+    out = {}
+    for n in names:
+        if n in PARAM_CARD_ENTRIES:
+            block, code = PARAM_CARD_ENTRIES[n]
+            entry = card.get(block, {}).get(code) if block in card else None
+            if entry is not None:
+                out[n] = float(entry.value)
+    return out
+
+
+def get_process(name, param_card=None, param_values=None):
+    """(Matrix, Model) for one compiled process, e.g. "1_gg_ttx".  param_card: path of an SLHA card whose masses and
+    widths replace the built-in SM values; param_values: {name: value} overrides on top."""
     m = Matrix(name, load_ir(name))
-    return m, get_model_param(m)
+    vals = param_values_from_card(param_card, m.param_names) if param_card is not None else {}
+    vals.update(param_values or {})
+    return m, get_model_param(m, vals)
 
 
 def get_processes(names=None):

@@ -74,6 +74,9 @@ def build_parser():
     arger.add_argument("--dr_cut", help="Extension: Delta R > value between every pair of outgoing massless particles (the "
                        "reference's pt cuts leave their collinear singularity open)", type=float, nargs="?", const=0.4)
     arger.add_argument("--seed", type=int, default=4)
+    arger.add_argument("--param_card", help="SLHA param_card with the masses and widths of the model (the reference reads "
+                       "Cards/param_card.dat of the MG5 output folder; default: that file under --output if it exists, else "
+                       "the SM values m_t = 173, Gamma_t = 1.4915)", type=Path, default=None)
     return arger
 
 
@@ -129,7 +132,12 @@ def madflow_main(args=None, quick_return=False):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
 
-    matrix, model = mfm.get_process(name)
+    card = args.param_card
+    if card is None and (output_path / "Cards" / "param_card.dat").exists():
+        card = output_path / "Cards" / "param_card.dat"   # madflow_exec.py:130-136
+    if card is not None:
+        logger.info("Model parameters from %s", card)
+    matrix, model = mfm.get_process(name, param_card=card)
     if args.histograms:
         matrix.set_variant("hp")   # the kernel pipeline that keeps the events in device memory
     nparticles = int(matrix.nexternal)
@@ -160,7 +168,7 @@ def madflow_main(args=None, quick_return=False):
 
     fi = integrand_of(matrix, model)
     if len(names) > 1:   # one event sample, the subprocesses summed per event
-        fi = mfi.MultiProcessIntegrand([fi] + [integrand_of(*mfm.get_process(nm)) for nm in names[1:]])
+        fi = mfi.MultiProcessIntegrand([fi] + [integrand_of(*mfm.get_process(nm, param_card=card)) for nm in names[1:]])
     if args.events_per_device:
         fi.max_events_per_launch = args.events_per_device
     if nparticles >= 5 and args.frozen_iter == 0:
@@ -174,17 +182,24 @@ def madflow_main(args=None, quick_return=False):
         warmup_iterations, final_iterations = max(args.iterations - args.frozen_iter, 2), args.frozen_iter
     t0 = time.time()
     logger.info("Running %d warm-up iterations of %d events each", warmup_iterations, args.events_per_iteration)
-    vegas.run_integration(warmup_iterations)
+    sink = None
+    if args.histograms:
+        # the unweighting threshold is fixed ONCE, from the weights of the last warm-up iteration (adapted grid), and
+        # holds for the whole final run: one sample, one threshold
+        vegas.run_integration(warmup_iterations - 1)
+        top = 2  # the first outgoing particle: the top quark in the built-in processes (compare_mg5_hists.py:31-32)
+        sink = mfe.EventSink(fi, histograms=[mfe.Histogram("pt", top, 0.0, 300.0, 50), mfe.Histogram("eta", top, -4.0, 4.0, 50)],
+                             unweight=True, capacity=args.unweighted_events, seed=args.seed, collect_only=True)
+        vegas.run_integration(1)
+        logger.info("Unweighting threshold frozen at %.6g (largest warm-up weight %.6g)", sink.freeze_threshold() or 0.0,
+                    sink.max_weight)
+    else:
+        vegas.run_integration(warmup_iterations)
     if args.frozen_iter > 0:
         vegas.freeze_grid()
     logger.info("Running %d iterations of %d events each%s", final_iterations, vegas.events_per_run,
                 " with the grid frozen" if args.frozen_iter > 0 else "")
 
-    sink = None
-    if args.histograms:
-        top = 2  # the first outgoing particle: the top quark in the built-in processes (compare_mg5_hists.py:31-32)
-        sink = mfe.EventSink(fi, histograms=[mfe.Histogram("pt", top, 0.0, 300.0, 50), mfe.Histogram("eta", top, -4.0, 4.0, 50)],
-                             unweight=True, capacity=args.unweighted_events, seed=args.seed)
     results = []
     n_final = 0
     for _ in range(final_iterations):
@@ -206,8 +221,17 @@ def madflow_main(args=None, quick_return=False):
         run = proc_name if world == 1 else f"{proc_name}_rank{rank}"
         for h in sink.histograms:
             h.allreduce()
-        with LheWriter(output_path, run, no_unweight=True, pdg=(matrix.ir or {}).get("pdg")) as lhe_writer:
+        pdg = list((matrix.ir or {}).get("pdg") or [])
+        if len(names) > 1 and pdg:
+            # several subprocesses were summed per event and no channel is recorded: the beams are labelled as protons
+            # (the reference writes the hadron-level process the same way), the final state as in the first subprocess
+            pdg[:2] = [2212, 2212]
+        with LheWriter(output_path, run, no_unweight=True, pdg=pdg or None) as lhe_writer:
             nkept = sink.write_lhe(lhe_writer, cross=res)
+            frac, share = sink.overweight()
+            if frac > 0.0:
+                logger.info("%.2f %% of the kept events lie above the unweighting threshold and carry %.1f %% of the total "
+                            "weight: they keep their own (larger) weight in the file", 100 * frac, 100 * share)
             lhe_writer.store_result((res, err))
             proc_folder = output_path / f"Events/{run}"
             lhe_writer.dump_result(proc_folder / "cross_err.txt")
@@ -221,6 +245,8 @@ def madflow_main(args=None, quick_return=False):
             (proc_folder / "histograms.json").write_text(json.dumps(hists, indent=1))
         logger.info("Written %d unweighted events%s, histograms and cross_err.txt to %s", nkept,
                     " (buffer full)" if sink.overflowed else "", proc_folder)
+    if hasattr(fi, "release"):
+        fi.release()   # the subprocess libraries share one grid size while summed: give it back
     if dist is not None:
         dist.destroy_process_group()
     return args, (res, err), proc_folder

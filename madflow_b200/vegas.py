@@ -66,6 +66,27 @@ def combine_iterations(results):
     return final, err, chi2
 
 
+class _Range:
+    """NVTX range around a phase of the iteration when MADFLOW_B200_NVTX=1 (shows up in Nsight Systems timelines)."""
+    enabled = None
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.enabled is None:
+            import os
+
+            _Range.enabled = os.environ.get("MADFLOW_B200_NVTX", "0") == "1" and torch.cuda.is_available()
+        if _Range.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Range.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -202,16 +223,19 @@ class VegasFlow:
         done = 0
         while done < count:
             n = min(limit, count - done)
-            if fused:
-                self._run_chunk_fused(first + done, n)
-            else:
-                self._run_chunk_generic(first + done, n)
+            with _Range(f"vegas chunk {first + done}+{n}"):
+                if fused:
+                    self._run_chunk_fused(first + done, n)
+                else:
+                    self._run_chunk_generic(first + done, n)
             done += n
-        allreduce_sums(self._sums)
+        with _Range("vegas all-reduce"):
+            allreduce_sums(self._sums)
         if self.train:
             lib = rt.core()
-            rt.check(lib, lib.mf_vegas_refine(rt.ptr(self.divisions), rt.ptr(self._sums), self.n_dim,
-                                              rt.stream_ptr()))
+            with _Range("vegas refine"):
+                rt.check(lib, lib.mf_vegas_refine(rt.ptr(self.divisions), rt.ptr(self._sums), self.n_dim,
+                                                  rt.stream_ptr()))
         res, res2, n_me, _ = self._sums[:HEADER].tolist()  # the only device->host read of the iteration
         self.last_me_events = int(n_me)
         self.iteration += 1

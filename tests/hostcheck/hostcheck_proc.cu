@@ -51,11 +51,8 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
     }
     for (int it = 0; it < Proc::NEXT * E * 2; ++it) mf::hp_externals<Proc>(it, E, mom.data(), par, sqh, evarea.data());
     for (int L = 2; L <= Proc::HP_MAXLEVEL; ++L) {
-      const int begin = Proc::level_begin(L), total = (Proc::level_begin(L + 1) - begin) * E;
-      for (int w = 0; w < total; ++w) {
-        const int ii = w / E, e = w - ii * E;
-        mf::hp_unit<Proc>(Proc::unit(begin + ii), par, cp.data() + e * Proc::NCOUP, evarea.data() + e * EVS);
-      }
+      mf::hp_units<Proc, Proc::HP_SPLIT>(Proc::level_begin(L), Proc::level_begin(L + 1) - Proc::level_begin(L), 0, 1, par, cp.data(),
+                                         evarea.data());
     }
     std::vector<double> me_h((size_t)E * NH, 0.0);
     if (Proc::HP_UNROLL) {
@@ -69,10 +66,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
         std::vector<cxd> J((size_t)T * NJ, mk(0.0, 0.0));
         for (int bi = 0; bi < Proc::HP_NBATCH; ++bi) {
           const mf::HpBatch bt = Proc::batch(pass * Proc::HP_NBATCH + bi);
-          for (int w = 0; w < (bt.unit_end - bt.unit_begin) * E; ++w) {
-            const int ii = w / E, ee = w - ii * E;
-            mf::hp_unit<Proc>(Proc::unit(bt.unit_begin + ii), par, cp.data() + ee * Proc::NCOUP, evarea.data() + ee * EVS);
-          }
+          mf::hp_units<Proc, Proc::HP_SPLIT>(bt.unit_begin, bt.unit_end - bt.unit_begin, 0, 1, par, cp.data(), evarea.data());
           // the tiles of the batch in table order
           for (int ee = 0; ee < E; ++ee)
             for (int ti = bt.tile_begin; ti < bt.tile_end; ++ti) {
