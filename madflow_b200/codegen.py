@@ -258,7 +258,8 @@ def hp_config(ir, key):
         # events/s (no more spills at 128 registers), + pass-independent pair objects kept 9.9e5; 4 colour groups 6.3e5
         return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 2048 if hp_use_plan(ir) else 4096, "MINBLOCKS": 1, "PERSIST": 0,
                 "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 3, "TMEMJ": 1}[key]
-    return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 21, "SCRATCH": 512, "MINBLOCKS": 2,
+    # NB: 22 rows let the 64 rows of the reduced g g > t t~ g g fit in 3 batches (with two blocks per SM still resident)
+    return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 22 if hp_use_plan(ir) else 21, "SCRATCH": 512, "MINBLOCKS": 2,
             "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0}[key]
 
 
@@ -435,11 +436,14 @@ def emit_hp(ir):
     # ---- wavefunctions (externals + currents) and their layout in the event area
     wfs, exts = [], []
     off = 0
-    for o in plan["objects"]:
+    # currents that no other object is built from (they only close amplitudes) need no momentum slots
+    feeds = {i for o in plan["objects"] for t in o["terms"] for i in t["in"]} | {i for p in plan["pairs"] for t in p["terms"] for i in t["in"]}
+    for oi, o in enumerate(plan["objects"]):
         legs = tuple(sorted(o["legs"]))
         w = {"legs": legs, "level": len(legs), "nv": 1 << len(legs), "off": off, "mask": sum(1 << l for l in legs),
              "ext": o["ext"], "terms": o["terms"], "mass": o.get("mass", "ZERO"), "width": o.get("width", "ZERO")}
-        off += 2 + 4 * w["nv"]
+        w["mom"] = 2 if (o["ext"] is not None or oi in feeds or not reduced) else 0
+        off += w["mom"] + 4 * w["nv"]
         if o["ext"] is not None:
             exts.append({"call": o["ext"], "out": len(wfs)})
             w["finish"] = "none"
@@ -541,9 +545,12 @@ def emit_hp(ir):
         ins3 = list(ins) + [0] * (3 - len(ins))
         vm = [vmask(obj["legs"], wfs[w]["legs"]) for w in ins] + [0] * (3 - len(ins))
         coup = ir["couplings"].index(t["coup"])
-        return (f"{{{PT[st]}, {len(ins)}, {coup}, {phase_of(t)}, {{{q[0]}, {q[1]}}}, {obj['nv']}, {out_off}, "
+        # finish + 4: a current without momentum slots (out_off then points two elements before its components)
+        fin = FINISH[obj["finish"]] + (4 if obj.get("mom", 2) == 0 and obj["finish"] != "none" else 0)
+        out = out_off - 2 if fin >= 4 else out_off
+        return (f"{{{PT[st]}, {len(ins)}, {coup}, {phase_of(t)}, {{{q[0]}, {q[1]}}}, {obj['nv']}, {out}, "
                 f"{{{', '.join(str(wfs[w]['off']) for w in ins3)}}}, {{{', '.join(str(wfs[w]['nv']) for w in ins3)}}}, "
-                f"{{{vm[0]}, {vm[1]}, {vm[2]}}}, {FINISH[obj['finish']]}, {pidx(obj.get('mass', 'ZERO'))}, {pidx(obj.get('width', 'ZERO'))}}}")
+                f"{{{vm[0]}, {vm[1]}, {vm[2]}}}, {fin}, {pidx(obj.get('mass', 'ZERO'))}, {pidx(obj.get('width', 'ZERO'))}}}")
 
     TSPLIT = hp_config(ir, "TSPLIT")
 
@@ -614,7 +621,7 @@ def emit_hp(ir):
                         qv, xv = min(8, qr.stop - q0), min(8, xr.stop - x0)
                         rowh = [spread(pr["legs"], q0 + i) if i < qv else 0 for i in range(8)]
                         colh = [spread(xw["legs"], x0 + i) if i < xv else 0 for i in range(8)]
-                        tile_rows.append(f"{{{pr['abs_off']}, {xw['off'] + 2}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
+                        tile_rows.append(f"{{{pr['abs_off']}, {xw['off'] + xw['mom']}, {pr['nv']}, {xw['nv']}, {q0}, {x0}, {qv}, {xv}, {slot}, 0, "
                                          f"{{{', '.join(map(str, rowh))}}}, {{{', '.join(map(str, colh))}}}}}")
             brow.append(f"{{{ub}, {len(urow)}, {tb}, {len(tile_rows)}}}")
 

@@ -70,7 +70,8 @@ struct HpExt {
 // (matrix_method_python.inc:99-102); here a numerator costs 2^|its legs| evaluations and each of the 2^n
 // combinations of an amplitude only a 4-term complex dot product (the tensor-core tiles below).
 enum HpVertex : unsigned char { HP_Q_ROW = 0, HP_Q_COL = 1, HP_Q_CUR = 2, HP_Q_VVV = 3, HP_Q_VVVV = 4 };
-enum HpFinish : unsigned char { HP_F_NONE = 0, HP_F_G = 1, HP_F_O = 2, HP_F_I = 3 };
+// + HP_F_NOMOM: a current that nothing else is built from stores no momentum slots
+enum HpFinish : unsigned char { HP_F_NONE = 0, HP_F_G = 1, HP_F_O = 2, HP_F_I = 3, HP_F_NOMOM = 4 };
 
 // One term of an object (current or pair object = vertex numerator).  An object is the sum of its terms,
 //   sum_t phase_t * numerator_t,   phase in {1, -1, i, -i}
@@ -273,8 +274,9 @@ MF_DEV void hp_unit_finish(const HpTerm& t, const HpWorkItem& it, const cxd Q[4]
   const double M = t.mass_idx < 0 ? 0.0 : par[t.mass_idx];
   const double W = t.width_idx < 0 ? 0.0 : par[t.width_idx];
   const cxd inv = propagator(mk(1.0, 0.0), Pm, M, W);
+  const int fin = t.finish & 3;
   cxd r[4];
-  if (t.finish == HP_F_G) {  // V^mu = numerator^mu / (P^2 - ..): undo the metric signs of the dual form
+  if (fin == HP_F_G) {  // V^mu = numerator^mu / (P^2 - ..): undo the metric signs of the dual form
     r[0] = inv * Q[0];
     const cxd ninv = -inv;
 #pragma unroll
@@ -284,7 +286,7 @@ MF_DEV void hp_unit_finish(const HpTerm& t, const HpWorkItem& it, const cxd Q[4]
     const cxd ninv = -inv;
     const double Pp = Pm.e + Pm.z, Pn = Pm.e - Pm.z;
     const cxd Pa = mk(Pm.x, Pm.y), Pb = mk(Pm.x, -Pm.y);
-    if (t.finish == HP_F_O) {
+    if (fin == HP_F_O) {
       r[0] = ninv * (M * Q[0] - Pp * Q[2] - Pa * Q[3]);
       r[1] = ninv * (M * Q[1] - Pb * Q[2] - Pn * Q[3]);
       r[2] = ninv * (M * Q[2] - Pn * Q[0] + Pa * Q[1]);
@@ -296,7 +298,7 @@ MF_DEV void hp_unit_finish(const HpTerm& t, const HpWorkItem& it, const cxd Q[4]
       r[3] = ninv * (M * Q[3] + Pa * Q[0] + Pn * Q[1]);
     }
   }
-  if (v == 0) o[0] = w[0], o[1] = w[1];
+  if (v == 0 && !(t.finish & HP_F_NOMOM)) o[0] = w[0], o[1] = w[1];
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[2 + hp_slot(k, nv, v)] = r[k];
 }
@@ -710,6 +712,7 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
         __syncthreads();
         MF_PROF(3);
 #ifdef __CUDA_ARCH__
+#ifndef MF_HP_EXPERIMENT_TMEM_ALLOC_ONLY
         if constexpr (P::HP_TMEM_J) {   // the JAMPs were parked in Tensor Memory during the pair and tile phases
           if (bi > 0) {
             hp_jamp_fetch<P>(tmem_base, J);
@@ -719,11 +722,14 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
           }
         }
 #endif
+#endif
         P::jamp_batch(bi, cg, abuf_h, J);
 #ifdef __CUDA_ARCH__
+#ifndef MF_HP_EXPERIMENT_TMEM_ALLOC_ONLY
         if constexpr (P::HP_TMEM_J) {
           if (bi + 1 < P::HP_NBATCH) hp_jamp_park<P>(tmem_base, J);
         }
+#endif
 #endif
         MF_PROF(4);
       }
