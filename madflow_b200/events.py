@@ -66,8 +66,11 @@ class Histogram:
 class EventSink:
     """Consumes the device event buffer after every launch of a FusedIntegrand."""
 
+    # weight spectrum for the unweighting threshold: sum |w| per logarithmic bin, 4 bins per octave from 2^-120 to 2^40
+    _WBINS, _WLOG0, _WPER = 640, -120.0, 4.0
+
     def __init__(self, integrand, histograms=(), unweight=False, capacity=1_000_000, seed=1234, wmax=None, wmax_scale=8.0,
-                 collect_only=False):
+                 collect_only=False, tail_share=0.1):
         """unweight: keep slot i with probability min(1, |w_i| / wmax) and weight sign(w_i) max(|w_i|, wmax) -- an
         unbiased sample in which all events but the few above wmax carry the same weight; the events above wmax keep
         their own, larger weight (write_lhe scales it, it is never clipped).  wmax: ONE threshold for the whole
@@ -76,7 +79,11 @@ class EventSink:
         the largest weight alone would make the efficiency collapse.  collect_only: only gather the weight statistics
         (no histograms, no selection) until freeze_threshold() -- what madflow_exec does during the last warm-up
         iteration.  Without a frozen threshold the sink falls back to the running estimate, which changes from launch
-        to launch (a mixture of thresholds: still unbiased event by event through the weights, but not one sample)."""
+        to launch (a mixture of thresholds: still unbiased event by event through the weights, but not one sample).
+        tail_share: freeze_threshold() puts the threshold where the events above it carry this share of sum |w| (from the
+        weight spectrum collected so far, summed over ranks), if that is below the other estimate: with the heavy-tailed
+        weights of a flat phase space the yield rises by orders of magnitude, at the price of a sample in which
+        `tail_share` of the weight sits in a few events that keep their own larger weight."""
         self.integrand = integrand
         self.histograms = list(histograms)
         self.unweight = bool(unweight)
@@ -86,11 +93,14 @@ class EventSink:
         self.wmax_scale = float(wmax_scale)
         self.enabled = True
         self.collect_only = bool(collect_only)
+        self.tail_share = float(tail_share)
         dev = config.device()
         n = integrand.nexternal
         self._nstat = int(rt.core().mf_weight_stats_blocks())
         self._stat_partial = torch.zeros((self._nstat, 3), dtype=torch.float64, device=dev)
         self._stats = torch.zeros(3, dtype=torch.float64, device=dev)   # max |w|, sum |w|, sum w^2
+        self._wspec = torch.zeros(self._WBINS, dtype=torch.float64, device=dev)
+        self._wedges = torch.pow(2.0, self._WLOG0 + torch.arange(self._WBINS + 1, dtype=torch.float64, device=dev) / self._WPER)
         if self.unweight:
             self._mom = torch.empty((self.capacity, n, 4), dtype=torch.float64, device=dev)
             self._w = torch.empty(self.capacity, dtype=torch.float64, device=dev)
@@ -123,6 +133,12 @@ class EventSink:
                                               self._nstat, rt.stream_ptr()))
             self._stats[0] = torch.maximum(self._stats[0], self._stat_partial[:, 0].max())
             self._stats[1:] += self._stat_partial[:, 1:].sum(dim=0)
+            if self.collect_only and self.wmax is None:
+                # weight spectrum, in an order that does not depend on scheduling: sort, prefix sums, differences at the edges
+                a = torch.sort((me if weight is None else me * weight).abs()).values
+                cs = torch.cat([a.new_zeros(1), torch.cumsum(a, 0)])
+                at = torch.searchsorted(a, self._wedges)
+                self._wspec += cs[at[1:]] - cs[at[:-1]]
         self.launches += 1
 
     @property
@@ -137,9 +153,23 @@ class EventSink:
         return min(mx, self.wmax_scale * s2 / s1) if s1 > 0.0 else 0.0
 
     def freeze_threshold(self):
-        """Fix the unweighting threshold at its current estimate and start filling histograms / keeping events."""
-        if self.unweight:
-            self.wmax = self.threshold() or None
+        """Fix the unweighting threshold -- one value for all ranks, from the statistics of all of them -- and start filling
+        histograms / keeping events."""
+        if self.unweight and self.wmax is None:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self._stats[:1], op=dist.ReduceOp.MAX)
+                dist.all_reduce(self._stats[1:], op=dist.ReduceOp.SUM)
+                dist.all_reduce(self._wspec, op=dist.ReduceOp.SUM)
+            wmax = self.threshold()
+            spec = self._wspec.cpu().numpy()
+            total = float(spec.sum())
+            if total > 0.0 and 0.0 < self.tail_share < 1.0:
+                above = total - np.cumsum(spec)                 # weight above the upper edge of every bin
+                k = int(np.argmax(above <= self.tail_share * total))
+                wmax = min(wmax, float(self._wedges[k + 1].item())) if wmax else float(self._wedges[k + 1].item())
+            self.wmax = wmax or None
         self.collect_only = False
         return self.wmax
 

@@ -1105,3 +1105,38 @@ def test_one_matrix_integration_with_pdf(mf, toy_pdf):
     assert abs(ra[0] / r0[0] - 1) < 1e-10
     with pytest.raises(ValueError):
         one_matrix_integration(m, model, pdf=pd, out_masses=[MT, MT])
+
+
+def test_unweighting_threshold_frozen_from_the_weight_spectrum(mf):
+    """EventSink(collect_only=True) gathers the weight statistics of one iteration, freeze_threshold() puts ONE threshold
+    where the events above it carry `tail_share` of sum |w|; afterwards the kept sample reproduces the iteration's
+    estimate (sum of kept weights, each standing for max(|w|, threshold)) within the sampling error and the events above
+    the threshold keep their own weight."""
+    m, model = mf.matrix.get_process("1_gg_ttx")
+    fi = mf.integrand.FusedIntegrand(m, model, sqrts=13e3, masses=[MT, MT], lab_frame=True)
+    m.set_variant("hp")
+    try:
+        v = mf.vegas.VegasFlow(fi.n_dim, 300_000, seed=9)
+        v.compile(fi)
+        v.run_integration(4, log_time=False)
+        sink = mf.events.EventSink(fi, unweight=True, capacity=300_000, seed=3, collect_only=True, tail_share=0.1)
+        v.run_iteration()
+        wmax = sink.freeze_threshold()
+        assert 0.0 < wmax <= sink.max_weight
+        spec, edges = cpu(sink._wspec), cpu(sink._wedges)
+        share = spec[edges[:-1] >= wmax * (1 - 1e-12)].sum() / spec.sum()
+        assert share <= 0.1 + 1e-12                              # the threshold sits at the 10 % tail, to bin resolution
+        assert spec[edges[:-1] >= wmax / 2 ** 0.25 * (1 - 1e-12)].sum() / spec.sum() > 0.1
+        v.freeze_grid()
+        res, sigma = v.run_iteration()
+        assert sink.wmax == wmax                                 # one threshold for the whole sample
+        mom, w = sink.events()
+        assert len(w) > 2000
+        # unbiased: every kept event stands for the threshold (or its own larger weight): the sum is the iteration's estimate
+        est = np.sum(np.sign(w) * np.maximum(np.abs(w), wmax))
+        assert abs(est / res - 1) < 6 * sigma / res + 4 / np.sqrt(len(w))
+        frac, wshare = sink.overweight()
+        assert 0.0 < frac < 0.3 and 0.0 < wshare < 0.3
+    finally:
+        m.set_variant("default")
+        fi.event_sink = None
