@@ -105,6 +105,45 @@ class Matrix:
             self._lib.smatrix(p, lay, nevt, par, d_coup, stride, config.get_constants().SQH, out)
         return out
 
+    def smatrix_pinned(self, h_ps, *params, out=None, chunk=1 << 18):
+        """smatrix for momenta (and per-event couplings) that live in PINNED host memory: the events go through the
+        device in chunks on two streams, so that the host->device copy of chunk i + 1 and the device->host copy of the
+        results of chunk i - 1 overlap the kernel of chunk i.  Returns a pinned host tensor (nevents,) (or fills `out`);
+        synchronises before returning.  This is the end-to-end path bench.py times."""
+        n = int(self.nexternal)
+        if not (isinstance(h_ps, torch.Tensor) and h_ps.device.type == "cpu" and h_ps.is_pinned()):
+            raise ValueError("smatrix_pinned: all_ps must be a pinned CPU tensor (torch.Tensor.pin_memory())")
+        if h_ps.ndim != 3 or tuple(h_ps.shape[1:]) != (n, 4) or h_ps.dtype != torch.float64:
+            raise ValueError(f"all_ps must be float64 with shape (nevents, {n}, 4)")
+        nevt = int(h_ps.shape[0])
+        par, coups = self._split_params(params)
+        coups = [c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c)) for c in coups]
+        coups = [c.reshape(-1).to(torch.complex128) for c in coups]
+        if any(c.numel() not in (1, nevt) for c in coups):
+            raise ValueError("couplings must have shape (1,) or (nevents,)")
+        if out is None:
+            out = torch.empty(nevt, dtype=torch.float64).pin_memory()
+        dev = config.device()
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_pipe_streams"):
+            self._pipe_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        sqh = config.get_constants().SQH
+        for s_ in self._pipe_streams:
+            s_.wait_stream(cur)
+        for ci, lo in enumerate(range(0, nevt, chunk)):
+            hi = min(lo + chunk, nevt)
+            with torch.cuda.stream(self._pipe_streams[ci & 1]):
+                d_ps = h_ps[lo:hi].to(dev, non_blocking=True)
+                part = [c if c.numel() == 1 else c[lo:hi] for c in coups]
+                d_coup, stride = self._pack_couplings([c.to(dev, non_blocking=True) for c in part], hi - lo)
+                d_out = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+                self._lib.smatrix(d_ps, rt.LAYOUT_AOS, hi - lo, par, d_coup, stride, sqh, d_out)
+                out[lo:hi].copy_(d_out, non_blocking=True)
+        for s_ in self._pipe_streams:
+            cur.wait_stream(s_)
+            s_.synchronize()
+        return out
+
     def matrix(self, all_ps, hel, *params):
         """One helicity configuration (matrix_method_python.inc:106-138); `hel` is a row of
         self.helicities (or its index)."""

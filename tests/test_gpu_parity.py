@@ -1140,3 +1140,23 @@ def test_unweighting_threshold_frozen_from_the_weight_spectrum(mf):
     finally:
         m.set_variant("default")
         fi.event_sink = None
+
+
+def test_smatrix_pinned_host_pipeline(mf):
+    """Matrix.smatrix_pinned (pinned host buffers, chunks on two streams) returns exactly what smatrix returns."""
+    m, model = mf.matrix.get_process("1_gg_ttxg")
+    n = 70_001
+    x = np.random.default_rng(12).random((n, 14))
+    p, w, x1, x2 = ops.ramboflow(x, 5, 13e3, [MT, MT, 0.0], xfactor="converged")
+    lab = ops.boost_to_lab(p, x1, x2)
+    a_s = 0.09 + 0.05 * np.random.default_rng(13).random(n)
+    params = model.evaluate(a_s)
+    ref = cpu(m.smatrix(lab, *params))
+    npar = len(m.param_names)
+    h_ps = torch.as_tensor(lab).pin_memory()
+    h_c = [c.cpu().pin_memory() for c in params[npar:]]
+    out = m.smatrix_pinned(h_ps, *params[:npar], *h_c, chunk=1 << 14)
+    assert out.is_pinned() and out.device.type == "cpu"
+    np.testing.assert_array_equal(out.numpy(), ref)
+    with pytest.raises(ValueError):
+        m.smatrix_pinned(torch.as_tensor(lab), *params[:npar], *h_c)      # not pinned
