@@ -246,6 +246,9 @@ def hp_config(ir, key):
                  units per phase and up to 12 terms per object (g g > t t~ g g g) the longest unit sets the phase's time
       TMEMJ      1 = the JAMP accumulators live in Tensor Memory between the JAMP phases of the batches instead of in
                  registers (frees NCOLOR/NCG complex registers for the current / pair / tile phases)
+      SLU        1 = packed units: the units of a phase sorted into warp trips of one class of objects (sequence of vertex
+                 kinds + propagator kind), one descriptor per trip and one 64-bit word per (unit, term) left to read at run
+                 time (process_kernels_hp.cuh, "SLU"); needs TSPLIT = 0
     Defaults from measurements on B200: up to 64 helicity combinations two events per
     block and all JAMPs in one thread (Tensor Memory off: with two blocks per SM it halves the rate, 2.4e7 -> 1.4e7
     events/s for g g > t t~ g g, profiles/r02j_ttxgg_tmem.log); beyond, one event per block, 8 colour groups, batches
@@ -257,10 +260,11 @@ def hp_config(ir, key):
         # g g > t t~ g g g, measured (profiles/r02k_ttxggg_tmem_tuning.log): JAMPs parked in Tensor Memory 7.9e5 -> 9.4e5
         # events/s (no more spills at 128 registers), + pass-independent pair objects kept 9.9e5; 4 colour groups 6.3e5
         return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 2048 if hp_use_plan(ir) else 4096, "MINBLOCKS": 1, "PERSIST": 0,
-                "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 3, "TMEMJ": 1}[key]
+                "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 3, "TMEMJ": 1, "SLU": 0}[key]
     # NB: 22 rows let the 64 rows of the reduced g g > t t~ g g fit in 3 batches (with two blocks per SM still resident)
     return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 22 if hp_use_plan(ir) else 21, "SCRATCH": 512, "MINBLOCKS": 2,
-            "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0}[key]
+            "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0,
+            "SLU": 1 if (hp_use_plan(ir) and ir["ncomb"] == 64) else 0}[key]
 
 
 def hp_use_plan(ir):
@@ -588,11 +592,14 @@ def emit_hp(ir):
                 urow.append(f"{item0 | cnt << 24 | glog << 28}u")
 
     begins = []
+    slu_phases = []   # per phase of the kernel, in its order: [(object, offset of its block, variants)]
     maxlevel = max([maxlevel] + [pr["ready"] for pr in pairs if pr["persist"]])   # phases = levels of currents (+ one for pairs)
     for lev in range(0, maxlevel + 2):
         begins.append(len(urow))
         todo = [(w, w["off"]) for w in wfs if w["ext"] is None and w["level"] == lev]
         todo += [(pr, pr["abs_off"]) for pr in pairs if pr["persist"] and pr["ready"] == lev]
+        if 2 <= lev <= maxlevel:
+            slu_phases.append([(obj, o_, range(obj["nv"])) for obj, o_ in todo])
         phase_units = []
         for obj, o_ in sorted(todo, key=lambda q: (len(q[0]["terms"]), type_key(q[0]), FINISH[q[0]["finish"]])):
             add_units(obj, o_, range(obj["nv"]), phase_units)
@@ -607,6 +614,7 @@ def emit_hp(ir):
         for bi, (cur_pairs, cur_amps) in enumerate(batches):
             ub, tb = len(urow), len(tile_rows)
             phase_units = []
+            slu_phases.append([(pairs[pi], pairs[pi]["abs_off"], vrange(pairs[pi]["legs"], pairs[pi]["nv"], p)) for pi in cur_pairs])
             for pi in cur_pairs:
                 pr = pairs[pi]
                 add_units(pr, pr["abs_off"], vrange(pr["legs"], pr["nv"], p), phase_units)
@@ -665,6 +673,101 @@ def emit_hp(ir):
                 jamp_terms += len(members) - 1 + len(terms0)
             jamp_cases[cg].append(f"      case {bi}: {{ " + "\n        ".join(stm) + " } break;")
 
+    # ---- class-specialised straight-line units (process_kernels_hp.cuh "SLU")
+    SLU = bool(hp_config(ir, "SLU")) and hp_available(ir)
+    slu_tables, slu_stats = "", {}
+    if SLU:
+        assert not TSPLIT, "straight-line units and units split over lanes exclude each other"
+        HP_E = hp_config(ir, "E")
+        LPU, NWARP = 32 // HP_E, HP_E * NHP * NCG // 32
+        assert 32 % HP_E == 0 and NWARP >= 1 and len(ir["couplings"]) <= 4
+        KCOST = {"ROW": 10, "COL": 10, "CUR": 10, "VVV": 14, "VVVV": 18}
+        FCOST = {"none": 1, "g": 6, "o": 10, "i": 10}
+
+        def slu_terms(obj):
+            """The terms of an object for the straight-line units: four-gluon terms over the same three lines with the
+            same coupling are merged into ONE term with integer weights (ca, cb, cc) of a (b.c), b (a.c), c (a.b); terms
+            sorted by vertex kind so that objects of the same make-up share a class."""
+            out, first = [], {}
+            for t in obj["terms"]:
+                st, ins, q = lowered(t)
+                coup, ph = ir["couplings"].index(t["coup"]), complex(*t["coef"])
+                assert ph in PHASE_CODE
+                if st != "VVVV":
+                    out.append({"kind": st, "ins": ins, "coup": coup, "ph": ph, "coefs": None})
+                    continue
+                coefs = [0, 0, 0]
+                for code in q:
+                    vec, da, db = (code >> 4) & 3, (code >> 2) & 3, code & 3
+                    assert {vec, da, db} == {0, 1, 2}
+                    coefs[vec] += -1 if code & 0x40 else 1
+                key = (tuple(ins), coup)
+                if key in first and ph / out[first[key]]["ph"] in (1, -1):
+                    o = out[first[key]]
+                    sgn = int((ph / o["ph"]).real)
+                    o["coefs"] = [a_ + sgn * b_ for a_, b_ in zip(o["coefs"], coefs)]
+                    continue
+                first.setdefault(key, len(out))
+                out.append({"kind": "VVVV", "ins": ins, "coup": coup, "ph": ph, "coefs": coefs})
+            out = [t for t in out if t["coefs"] is None or any(t["coefs"])]
+            assert out and all(t["coefs"] is None or max(map(abs, t["coefs"])) <= 2 for t in out)
+            return sorted(out, key=lambda t: PT[t["kind"]])
+
+        def desc(off, v, nlegs):
+            assert 0 <= off < (1 << 14) and 0 <= v < 32 and nlegs <= 5
+            return off | v << 14 | nlegs << 19
+
+        classes, class_keys, class_cost, words, trips, ranges = {}, [], [], [], [], []
+        term_evals = 0
+        for units_of_phase in slu_phases:
+            by_class = {}
+            for obj, o_, variants in units_of_phase:
+                terms = slu_terms(obj)
+                nomom = obj.get("mom", 2) == 0 and obj["finish"] != "none"
+                key = (tuple(t["kind"] for t in terms), obj["finish"], nomom, pidx(obj.get("mass", "ZERO")), pidx(obj.get("width", "ZERO")))
+                if key not in classes:
+                    classes[key] = len(classes)
+                    class_keys.append(key)
+                    class_cost.append(sum(KCOST[k] for k in key[0]) + FCOST[key[1]])
+                out_off = o_ - 2 if nomom else o_
+                for v in variants:
+                    uw = [(desc(out_off, v, len(obj["legs"])), 0)]
+                    for t in terms:
+                        d = [desc(wfs[w]["off"], pext(v, vmask(obj["legs"], wfs[w]["legs"])), len(wfs[w]["legs"])) for w in t["ins"]]
+                        uw.append((d[0] | (t["coup"] * 4 + PHASE_CODE[t["ph"]]) << 22, d[1]))
+                        if t["kind"] == "VVVV":
+                            ca, cb, cc = t["coefs"]
+                            uw.append((d[2], (ca + 2) | (cb + 2) << 3 | (cc + 2) << 6))
+                        term_evals += 1
+                    by_class.setdefault(classes[key], []).append(uw)
+            # trips of one class each, longest processing time first onto the least loaded warp
+            ptrips = []
+            for cls, us in by_class.items():
+                for i in range(0, len(us), LPU):
+                    ptrips.append((cls, us[i:i + LPU]))
+            load, mine = [0] * NWARP, [[] for _ in range(NWARP)]
+            for cls, us in sorted(ptrips, key=lambda q: (-class_cost[q[0]], q[0])):
+                wi = min(range(NWARP), key=lambda q: (load[q], q))
+                load[wi] += class_cost[cls]
+                mine[wi].append((cls, us))
+            for wi in range(NWARP):
+                ranges.append((len(trips), len(trips) + len(mine[wi])))
+                for cls, us in mine[wi]:
+                    kinds, fin, nomom, mi, wi_ = class_keys[cls]
+                    assert len(us) < 256 and len(kinds) <= 10 and mi < 15 and wi_ < 15
+                    trips.append((len(words), len(us) | (FINISH[fin] + (4 if nomom else 0)) << 8 | (mi + 1) << 12 | (wi_ + 1) << 16 | len(kinds) << 20,
+                                  sum(PT[k] << (3 * q) for q, k in enumerate(kinds)), 0))
+                    for j in range(len(us[0])):
+                        words += [us[u][j] if u < len(us) else (0, 0) for u in range(LPU)]
+        slu_tables = "\n".join([
+            both("uint2", "slu_words", max(len(words), 1), ", ".join(f"{{{x}u, {y}u}}" for x, y in words) or "{0u, 0u}", const=False),
+            both("uint4", "slu_trips", max(len(trips), 1), ", ".join(f"{{{x}u, {y}u, {z}u, {w_}u}}" for x, y, z, w_ in trips) or "{0u, 0u, 0u, 0u}"),
+            both("int2", "slu_ranges", max(len(ranges), 1), ", ".join(f"{{{x}, {y}}}" for x, y in ranges) or "{0, 0}")])
+        slu_stats = {"classes": len(classes), "trips": len(trips), "words": len(words), "term_evals": term_evals}
+    else:
+        slu_tables = "\n".join([both("uint2", "slu_words", 1, "{0u, 0u}", const=False), both("uint4", "slu_trips", 1, "{0u, 0u, 0u, 0u}"),
+                                both("int2", "slu_ranges", 1, "{0, 0}")])
+
     # ---- tables
     L = []
     L.append(both("mf::HpWf", "wf", len(wfs), ", ".join(f"{{{w['off']}u, {w['nv']}, {w['mask']}}}" for w in wfs)))
@@ -682,6 +785,7 @@ def emit_hp(ir):
     L.append(both("int", "level_begin", len(begins), ", ".join(map(str, begins))))
     L.append(both("mf::HpTile", "tiles", max(len(tile_rows), 1), ",\n  ".join(tile_rows) if tile_rows else "{0}", const=len(tile_rows) * 32 <= 24576))
     L.append(both("mf::HpBatch", "batches", max(len(brow), 1), ", ".join(brow) if brow else "{0, 0, 0, 0}"))
+    L.append(slu_tables)
     tables = "\n".join(L)
 
     A = ["    switch (cg) {"]
@@ -751,7 +855,7 @@ def emit_hp(ir):
         wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=nunits_cur, namps=len(plan["rows"]), unroll=unroll,
         nbatch=len(batches), npairs=len(pairs), nitems_pair=len(urow) - nunits_cur, ntiles=len(tile_rows), ncg=1 if unroll else NCG,
         jamp_terms=jamp_terms, npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
-        colour_denom=float(den[0]), reduced=reduced, nterms=len(trows),
+        colour_denom=float(den[0]), reduced=reduced, nterms=len(trows), slu=SLU, slu_stats=slu_stats,
         nb=max(len(a_) for _, a_ in batches) if batches else 1,
         scratch=max((pairs[pi]["abs_off"] - wfsize + 4 * pairs[pi]["nv"] for b_ in batches for pi in b_[0]), default=0))
 
@@ -928,6 +1032,11 @@ struct Proc {{
   MF_DEV static int level_begin(int L) {{ return MF_TAB(level_begin)[L]; }}
   MF_DEV static const mf::HpTile* tile(int i) {{ return &MF_TAB(tiles)[i]; }}
   MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
+  // packed units (process_kernels_hp.cuh "SLU"): trips per (phase, warp), one class of objects per trip
+  static constexpr bool HP_SLU = {'true' if hp['slu'] else 'false'};
+  MF_DEV static int2 slu_range(int i) {{ return MF_TAB(slu_ranges)[i]; }}
+  MF_DEV static uint4 slu_trip(int i) {{ return MF_TAB(slu_trips)[i]; }}
+  MF_DEV static const uint2* slu_words() {{ return MF_TAB(slu_words); }}
   // JAMP updates of batch `b` for colour group `cg` (warp-uniform switches): ab = the event's amplitude
   // buffer at this thread's helicity combination, row r at ab[r * HP_NHP]; JAMP registers addressed statically
   MF_DEV static void jamp_batch(int b, int cg, const cxd* ab, cxd (&J)[HP_NJ]) {{

@@ -185,6 +185,50 @@ MF_DEV void hp_quartic_term(unsigned char d, const cxd a[6], const cxd b[6], con
   }
 }
 
+// The five vertex numerators (dual form, see HpVertex): Q[k] += f * (vertex with one line open)_k, f = -i COUP phase.
+// Shared by the table-driven routine (hp_unit_terms) and the class-specialised straight-line units (slu_*).
+MF_DEV void hp_q_row(const cxd a[6], const cxd b[6], cxd f, cxd Q[4]) {  // a = O (F2), b = G
+  cxd X[4];
+  slash_row(a, b, X);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) Q[k] = fma_c(f, X[k], Q[k]);
+}
+MF_DEV void hp_q_col(const cxd a[6], const cxd b[6], cxd f, cxd Q[4]) {  // a = I (F1), b = G
+  cxd Y[4];
+  slash_col(a, b, Y);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) Q[k] = fma_c(f, Y[k], Q[k]);
+}
+MF_DEV void hp_q_cur(const cxd a[6], const cxd b[6], cxd f, cxd Q[4]) {  // a = I (F1), b = O (F2): J^mu with FFV1_0 = -i COUP (J.V)
+  const cxd tp = fma_c(a[5], b[3], a[2] * b[4]), tm = fma_c(a[4], b[2], a[3] * b[5]);  // t0 + t3, t1 + t2
+  const cxd u0 = a[2] * b[5], u1 = a[3] * b[4], u2 = a[4] * b[3], u3 = a[5] * b[2];
+  Q[0] = fma_c(f, tp + tm, Q[0]);
+  Q[1] = fma_c(f, (u0 - u3) + (u1 - u2), Q[1]);          // -J1
+  Q[2] = fma_c(f, mul_i((u0 + u3) - (u1 + u2)), Q[2]);   // -J2
+  Q[3] = fma_c(f, tp - tm, Q[3]);                        // -J3
+}
+// a = V2, b = V3 of VVV1_0(V1,V2,V3) with their momentum slots; P1 = -(P2+P3); the only kind that needs the momenta
+MF_DEV void hp_q_vvv(const cxd a[6], const cxd b[6], cxd f, cxd Q[4]) {
+  const Mom P2 = mom_of(a, 1.0), P3 = mom_of(b, 1.0);
+  const Mom d12 = Mom{-2.0 * P2.e - P3.e, -2.0 * P2.x - P3.x, -2.0 * P2.y - P3.y, -2.0 * P2.z - P3.z};  // P1-P2
+  const Mom d31 = Mom{2.0 * P3.e + P2.e, 2.0 * P3.x + P2.x, 2.0 * P3.y + P2.y, 2.0 * P3.z + P2.z};      // P3-P1
+  const cxd s3 = pdot(d12, b), s2 = pdot(d31, a), s23 = vdot(a, b);
+  const double q[4] = {P2.e - P3.e, P2.x - P3.x, P2.y - P3.y, P2.z - P3.z};
+  const cxd fm = -f;
+  Q[0] = fma_c(f, fma_c(a[2], s3, fma_c(b[2], s2, q[0] * s23)), Q[0]);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) Q[k] = fma_c(fm, fma_c(a[2 + k], s3, fma_c(b[2 + k], s2, q[k] * s23)), Q[k]);
+}
+// all four-gluon structures over the same three lines at once: K = ca a (b.c) + cb b (a.c) + cc c (a.b) with small
+// integer weights (the UFO structures VVVV1/3/4 and the relative signs of the merged terms, codegen.py)
+MF_DEV void hp_q_vvvv_merged(const cxd a[6], const cxd b[6], const cxd c[6], double ca, double cb, double cc, cxd f, cxd Q[4]) {
+  const cxd da = ca * vdot(b, c), db = cb * vdot(a, c), dc = cc * vdot(a, b);
+  const cxd fm = -f;
+  Q[0] = fma_c(f, fma_c(a[2], da, fma_c(b[2], db, c[2] * dc)), Q[0]);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) Q[k] = fma_c(fm, fma_c(a[2 + k], da, fma_c(b[2 + k], db, c[2 + k] * dc)), Q[k]);
+}
+
 // One unit of the current / pair-object phases: (object, helicity variant) of the event whose area is ev_e.  The
 // terms of the object are evaluated in turn and added up (hp_unit_terms); the propagator is applied (currents) and the
 // result stored by hp_unit_finish.  An object with many terms is split over 2^k neighbouring lanes (k = bits 28-29 of
@@ -205,38 +249,13 @@ MF_DEV void hp_unit_terms(const unsigned unit, const cxd* coup_e, const cxd* ev_
     if (t.phase & 2) f = mul_i(f);
     if (t.phase & 1) f = -f;
     switch (t.type) {
-      case HP_Q_ROW: {  // a = O (F2), b = G
-        cxd X[4];
-        slash_row(a, b, X);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) Q[k] = fma_c(f, X[k], Q[k]);
-      } break;
-      case HP_Q_COL: {  // a = I (F1), b = G
-        cxd Y[4];
-        slash_col(a, b, Y);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) Q[k] = fma_c(f, Y[k], Q[k]);
-      } break;
-      case HP_Q_CUR: {  // a = I (F1), b = O (F2): J^mu with FFV1_0 = -i COUP (J.V)
-        const cxd tp = fma_c(a[5], b[3], a[2] * b[4]), tm = fma_c(a[4], b[2], a[3] * b[5]);  // t0 + t3, t1 + t2
-        const cxd u0 = a[2] * b[5], u1 = a[3] * b[4], u2 = a[4] * b[3], u3 = a[5] * b[2];
-        Q[0] = fma_c(f, tp + tm, Q[0]);
-        Q[1] = fma_c(f, (u0 - u3) + (u1 - u2), Q[1]);          // -J1
-        Q[2] = fma_c(f, mul_i((u0 + u3) - (u1 + u2)), Q[2]);   // -J2
-        Q[3] = fma_c(f, tp - tm, Q[3]);                        // -J3
-      } break;
-      case HP_Q_VVV: {  // a = V2, b = V3 of VVV1_0(V1,V2,V3); P1 = -(P2+P3); the only kind that needs the momenta
+      case HP_Q_ROW: hp_q_row(a, b, f, Q); break;
+      case HP_Q_COL: hp_q_col(a, b, f, Q); break;
+      case HP_Q_CUR: hp_q_cur(a, b, f, Q); break;
+      case HP_Q_VVV:
         a[0] = ab[0], a[1] = ab[1], b[0] = bb[0], b[1] = bb[1];
-        const Mom P2 = mom_of(a, 1.0), P3 = mom_of(b, 1.0);
-        const Mom d12 = Mom{-2.0 * P2.e - P3.e, -2.0 * P2.x - P3.x, -2.0 * P2.y - P3.y, -2.0 * P2.z - P3.z};  // P1-P2
-        const Mom d31 = Mom{2.0 * P3.e + P2.e, 2.0 * P3.x + P2.x, 2.0 * P3.y + P2.y, 2.0 * P3.z + P2.z};      // P3-P1
-        const cxd s3 = pdot(d12, b), s2 = pdot(d31, a), s23 = vdot(a, b);
-        const double q[4] = {P2.e - P3.e, P2.x - P3.x, P2.y - P3.y, P2.z - P3.z};
-        const cxd fm = -f;
-        Q[0] = fma_c(f, fma_c(a[2], s3, fma_c(b[2], s2, q[0] * s23)), Q[0]);
-#pragma unroll
-        for (int k = 1; k < 4; ++k) Q[k] = fma_c(fm, fma_c(a[2 + k], s3, fma_c(b[2 + k], s2, q[k] * s23)), Q[k]);
-      } break;
+        hp_q_vvv(a, b, f, Q);
+        break;
       default: {  // HP_Q_VVVV: K = sum_t sign_t * in[vec_t] * (in[dotA_t] . in[dotB_t])
         cxd c[6];
         hp_load_comp(ev_e + t.in_off[2], t.in_nv[2], it.iv[2], c);
@@ -254,27 +273,11 @@ MF_DEV void hp_unit_terms(const unsigned unit, const cxd* coup_e, const cxd* ev_
   }
 }
 
-template <class P>
-MF_DEV void hp_unit_finish(const HpTerm& t, const HpWorkItem& it, const cxd Q[4], const double* par, cxd* ev_e) {
-  cxd* o = ev_e + t.out_off;
-  const int nv = t.out_nv, v = it.v;
-  if (t.finish == HP_F_NONE) {  // a vertex numerator (pair object): components only
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o[hp_slot(k, nv, v)] = Q[k];
-    return;
-  }
-  // a current: momentum slots = the sum of its inputs', propagator 1 / (P^2 - M(M - iW)) with P = -(sum)
-  cxd w[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    w[k] = ev_e[t.in_off[0] + k] + ev_e[t.in_off[1] + k];
-    if (t.nin > 2) w[k] += ev_e[t.in_off[2] + k];
-  }
+// Propagator + store of one (object, variant): Q = the summed numerators, w = the momentum slots of the object (the
+// sum of its inputs'), o = its block in the event area.  fin = HpFinish (& 3), nomom: no momentum slots are stored.
+MF_DEV void hp_finish_store(int fin, bool nomom, const cxd Q[4], const cxd w[2], double M, double W, cxd* o, int nv, int v) {
   const Mom Pm = Mom{-w[0].re, -w[1].re, -w[1].im, -w[0].im};
-  const double M = t.mass_idx < 0 ? 0.0 : par[t.mass_idx];
-  const double W = t.width_idx < 0 ? 0.0 : par[t.width_idx];
   const cxd inv = propagator(mk(1.0, 0.0), Pm, M, W);
-  const int fin = t.finish & 3;
   cxd r[4];
   if (fin == HP_F_G) {  // V^mu = numerator^mu / (P^2 - ..): undo the metric signs of the dual form
     r[0] = inv * Q[0];
@@ -298,9 +301,30 @@ MF_DEV void hp_unit_finish(const HpTerm& t, const HpWorkItem& it, const cxd Q[4]
       r[3] = ninv * (M * Q[3] + Pa * Q[0] + Pn * Q[1]);
     }
   }
-  if (v == 0 && !(t.finish & HP_F_NOMOM)) o[0] = w[0], o[1] = w[1];
+  if (v == 0 && !nomom) o[0] = w[0], o[1] = w[1];
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[2 + hp_slot(k, nv, v)] = r[k];
+}
+
+template <class P>
+MF_DEV void hp_unit_finish(const HpTerm& t, const HpWorkItem& it, const cxd Q[4], const double* par, cxd* ev_e) {
+  cxd* o = ev_e + t.out_off;
+  const int nv = t.out_nv, v = it.v;
+  if (t.finish == HP_F_NONE) {  // a vertex numerator (pair object): components only
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[hp_slot(k, nv, v)] = Q[k];
+    return;
+  }
+  // a current: momentum slots = the sum of its inputs', propagator 1 / (P^2 - M(M - iW)) with P = -(sum)
+  cxd w[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    w[k] = ev_e[t.in_off[0] + k] + ev_e[t.in_off[1] + k];
+    if (t.nin > 2) w[k] += ev_e[t.in_off[2] + k];
+  }
+  const double M = t.mass_idx < 0 ? 0.0 : par[t.mass_idx];
+  const double W = t.width_idx < 0 ? 0.0 : par[t.width_idx];
+  hp_finish_store(t.finish & 3, (t.finish & HP_F_NOMOM) != 0, Q, w, M, W, o, nv, v);
 }
 
 // The units [begin, begin + n) of a phase for the E events of the block; thread w = tid, tid + nthreads, .. takes unit
@@ -353,6 +377,127 @@ MF_DEV void hp_units(int begin, int n, int tid, int nthreads, const double* par,
     hp_unit_finish<P>(t, it, Q, par, ev + e * EVS);
   }
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed units ("SLU", codegen.hp_config SLU).  The table-driven routine above spends two thirds of its ~270 warp
+// instructions per term on fetching and decoding table rows, on address arithmetic and on per-lane type switches.
+// Here the objects of a phase are sorted into CLASSES = (sequence of vertex kinds, kind of propagator); the units of
+// a phase are packed into warp TRIPS of one class each, statically assigned to the warps of the block (longest
+// processing time first), so that everything about the kind of work is warp-uniform and comes from one descriptor
+// per trip in constant memory.  What is left per lane is one 64-bit word per (unit, term) and one per unit, read
+// coalesced by the lanes of the trip:
+//   input descriptor (22 bits) = block offset in the event area (14) | helicity variant (5) << 14 | log2 variants (3) << 19
+//   term word   .x = input A | f-index << 22      .y = input B            f-index = coupling * 4 + phase code
+//   4-gluon 2nd .x = input C                      .y = (ca + 2) | (cb + 2) << 3 | (cc + 2) << 6
+//   unit word   .x = output descriptor (offset = the block start, or start - 2 without momentum slots)
+//   trip        .x = first word   .y = units in use | HpFinish << 8 | (mass + 1) << 12 | (width + 1) << 16 | terms << 20
+//               .z = vertex kinds, 3 bits per term
+// f = -i COUP phase is looked up in a per-event table of the 4 phases of every coupling (shared memory).
+// The code stays a LOOP over the terms with a warp-uniform switch over the five vertex kinds: one function per
+// class (the first version, profiles/r02w_*) saved the same instructions but ran out of the instruction cache --
+// 14 400 instructions, 24 % of the stall samples "no instruction" -- and gained nothing.
+struct SluIn {
+  const cxd* blk;   // the block's momentum slots; components from blk + 2
+  int idx[4];       // position of the variant's component k behind blk + 2
+};
+MF_DEV SluIn slu_in(unsigned d, const cxd* ev_e) {
+  const int off = (int)(d & 0x3fffu), v = (int)((d >> 14) & 31u), lg = (int)((d >> 19) & 7u), mask = (1 << lg) - 1;
+  SluIn r;
+  r.blk = ev_e + off;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r.idx[k] = (k << lg) + (v ^ ((2 * k) & mask));
+  return r;
+}
+MF_DEV void slu_load(const SluIn& in, cxd a[6]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[2 + k] = in.blk[2 + in.idx[k]];
+}
+MF_DEV void slu_load_mom(const SluIn& in, cxd a[6]) { a[0] = in.blk[0], a[1] = in.blk[1]; }
+
+// one term of kind KIND (HpVertex) of one unit: Q += f * numerator; with want_mom also the sum of the inputs'
+// momentum slots (a current's own momentum)
+template <int KIND>
+MF_DEV void slu_term(const uint2* w, int stride, int& j, const cxd* ev_e, const cxd* ftab_e, cxd Q[4], cxd mw[2], bool want_mom) {
+  const uint2 t = w[j * stride];
+  ++j;
+  const SluIn ia = slu_in(t.x & 0x3fffffu, ev_e), ib = slu_in(t.y & 0x3fffffu, ev_e);
+  const cxd f = ftab_e[(t.x >> 22) & 15u];
+  cxd a[6], b[6];
+  slu_load(ia, a);
+  slu_load(ib, b);
+  if (KIND == HP_Q_VVV || want_mom) {
+    slu_load_mom(ia, a);
+    slu_load_mom(ib, b);
+    mw[0] = a[0] + b[0], mw[1] = a[1] + b[1];
+  }
+  if (KIND == HP_Q_ROW) hp_q_row(a, b, f, Q);
+  if (KIND == HP_Q_COL) hp_q_col(a, b, f, Q);
+  if (KIND == HP_Q_CUR) hp_q_cur(a, b, f, Q);
+  if (KIND == HP_Q_VVV) hp_q_vvv(a, b, f, Q);
+  if (KIND == HP_Q_VVVV) {
+    const uint2 t2 = w[j * stride];
+    ++j;
+    const SluIn ic = slu_in(t2.x & 0x3fffffu, ev_e);
+    cxd c[6];
+    slu_load(ic, c);
+    if (want_mom) {
+      slu_load_mom(ic, c);
+      mw[0] += c[0], mw[1] += c[1];
+    }
+    const double ca = (double)((int)(t2.y & 7u) - 2), cb = (double)((int)((t2.y >> 3) & 7u) - 2), cc = (double)((int)((t2.y >> 6) & 7u) - 2);
+    hp_q_vvvv_merged(a, b, c, ca, cb, cc, f, Q);
+  }
+}
+
+// f-table of one coupling: -i COUP x phase for the phase codes 0..3 = 1, -1, i, -i
+MF_DEV void hp_fill_ftab(cxd coup, cxd* f4) {
+  const cxd f = mul_mi(coup);
+  f4[0] = f, f4[1] = -f, f4[2] = mul_i(f), f4[3] = -mul_i(f);
+}
+
+// The trips of phase `ph` that belong to `warp`: lane = unit * E + event.  Proc::slu_range(ph * warps + warp) = first
+// and last + 1 trip; word j of unit u of a trip at [first word + j * (32/E) + u].
+template <class P>
+MF_DEV void slu_units(int ph, int warp, int lane, const cxd* ftab, const double* par, cxd* ev) {
+  constexpr int E = P::HP_E, LPU = 32 / E, NW = P::HP_THREADS / 32;
+  static_assert(32 % E == 0, "events per block divide the warp");
+  const int u = lane / E, e = lane - u * E;
+  const cxd* ftab_e = ftab + e * (4 * (P::NCOUP > 0 ? P::NCOUP : 1));
+  cxd* ev_e = ev + e * P::HP_EVSTRIDE;
+  const int2 r = P::slu_range(ph * NW + warp);
+#pragma unroll 1
+  for (int t = r.x; t < r.y; ++t) {
+    const uint4 d = P::slu_trip(t);
+    if (u >= (int)(d.y & 0xffu)) continue;
+    const uint2* w = P::slu_words() + d.x + u;
+    const int fin = (int)((d.y >> 8) & 7u), nterms = (int)(d.y >> 20);
+    cxd Q[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
+    cxd mw[2] = {mk(0.0, 0.0), mk(0.0, 0.0)};
+    unsigned kinds = d.z;
+    int j = 1;
+#pragma unroll 1
+    for (int q = 0; q < nterms; ++q, kinds >>= 3) {
+      const bool want_mom = q == 0 && fin != HP_F_NONE;   // the momentum slots come with the first term
+      switch (kinds & 7u) {
+        case HP_Q_ROW: slu_term<HP_Q_ROW>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
+        case HP_Q_COL: slu_term<HP_Q_COL>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
+        case HP_Q_CUR: slu_term<HP_Q_CUR>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
+        case HP_Q_VVV: slu_term<HP_Q_VVV>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
+        default: slu_term<HP_Q_VVVV>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
+      }
+    }
+    const unsigned od = w[0].x;
+    cxd* o = ev_e + (od & 0x3fffu);
+    const int v = (int)((od >> 14) & 31u), nv = 1 << ((od >> 19) & 7u);
+    if (fin == HP_F_NONE) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[hp_slot(k, nv, v)] = Q[k];
+    } else {
+      const int mi = (int)((d.y >> 12) & 15u) - 1, wi = (int)((d.y >> 16) & 15u) - 1;
+      hp_finish_store(fin & 3, (fin & HP_F_NOMOM) != 0, Q, mw, mi < 0 ? 0.0 : par[mi], wi < 0 ? 0.0 : par[wi], o, nv, v);
+    }
+  }
 }
 
 // vtab[mask * NCOMB + h]: the helicity variant, of an object over the leg set `mask`, that belongs to
@@ -636,7 +781,8 @@ MF_DEV double hp_colour_loop(const double* planes, int hl, int cg, const double*
 // return garbage).  Thread tid = (e * HP_NCG + colour group) * HP_NHP + helicity combination of the pass.
 template <class P>
 __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events */, const double* mom,
-                                                   const cxd* coup, const double* par, double sqh, cxd* ev,
+                                                   const cxd* coup, const cxd* ftab /* [E][NCOUP][4 phases], SLU */,
+                                                   const double* par, double sqh, cxd* ev,
                                                    const unsigned char* vtab, double* red /* [T/32] */, int only_h,
                                                    unsigned tmem_base = 0u) {
   constexpr int E = P::HP_E, NHP = P::HP_NHP, NCG = P::HP_NCG, TE = NHP * NCG, T = E * TE, EVS = P::HP_EVSTRIDE;
@@ -659,7 +805,10 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
 #pragma unroll 1
   for (int L = 2; L <= P::HP_MAXLEVEL; ++L) {
     // units (object, variant) of this level: the currents and the pair objects that stay in shared memory
-    hp_units<P, P::HP_SPLIT>(P::level_begin(L), P::level_begin(L + 1) - P::level_begin(L), tid, T, par, coup, ev);
+    if constexpr (P::HP_SLU)
+      slu_units<P>(L - 2, tid >> 5, tid & 31, ftab, par, ev);
+    else
+      hp_units<P, P::HP_SPLIT>(P::level_begin(L), P::level_begin(L + 1) - P::level_begin(L), tid, T, par, coup, ev);
     __syncthreads();
   }
   MF_PROF(1);
@@ -685,7 +834,10 @@ __device__ __forceinline__ double hp_smatrix_block(int nev /* <= E valid events 
 #pragma unroll
         for (int j = 0; j < P::HP_NJ; ++j) J[j] = mk(0.0, 0.0);
 #endif
-        hp_units<P, P::HP_SPLIT>(bt.unit_begin, bt.unit_end - bt.unit_begin, tid, T, par, coup, ev);
+        if constexpr (P::HP_SLU)
+          slu_units<P>(P::HP_MAXLEVEL - 1 + pass * P::HP_NBATCH + bi, warp, lane, ftab, par, ev);
+        else
+          hp_units<P, P::HP_SPLIT>(bt.unit_begin, bt.unit_end - bt.unit_begin, tid, T, par, coup, ev);
         __syncthreads();   // pair objects complete; the JAMP reads of the batch before are done (amplitude buffer reused)
         MF_PROF(2);
         {
@@ -802,6 +954,7 @@ struct HpSmatrixSmem {
   static constexpr int E = P::HP_E, T = P::HP_THREADS;
   double mom[E * P::NEXT * 4];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
+  cxd ftab[P::HP_SLU ? 4 * E * (P::NCOUP > 0 ? P::NCOUP : 1) : 1];   // -i COUP x {1, -1, i, -i} per event and coupling (SLU)
   double red[T / 32 + 1];
   unsigned tmem_addr;   // base of the block's Tensor Memory allocation (HP_TMEM_J)
   unsigned char vtab[P::HP_UNROLL ? (1 << P::NEXT) * P::NCOMB : 16];  // straight-line flavour only
@@ -863,9 +1016,10 @@ __global__ void __launch_bounds__(P::HP_THREADS, P::HP_MINBLOCKS) smatrix_kernel
           const double2 v = reinterpret_cast<const double2*>(a.coup)[a.coup_stride ? (long long)c * a.nevt + ev : c];
           s.coup[i] = mk(v.x, v.y);
         }
+        if constexpr (P::HP_SLU) hp_fill_ftab(s.coup[i], s.ftab + 4 * i);
       }
       __syncthreads();
-      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, a.par, a.sqh, evarea, s.vtab, s.red, only_h, tmem_base);
+      const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, s.ftab, a.par, a.sqh, evarea, s.vtab, s.red, only_h, tmem_base);
       const int e = tid / TE;
       if (tid - e * TE == 0 && e < nev) a.out[ev0 + e] = me;
       __syncthreads();

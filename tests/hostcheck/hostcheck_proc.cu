@@ -32,6 +32,16 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
   std::vector<cxd> evarea((size_t)EVS * E);
   std::vector<double> mom(E * Proc::NEXT * 4);
   std::vector<cxd> cp(E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
+  std::vector<cxd> ftab(4 * E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
+  // one phase of units: the table-driven routine, or the straight-line units warp by warp, lane by lane
+  auto units = [&](int slu_phase, int begin, int n) {
+    if (Proc::HP_SLU) {
+      for (int w = 0; w < Proc::HP_THREADS / 32; ++w)
+        for (int l = 0; l < 32; ++l) mf::slu_units<Proc>(slu_phase, w, l, ftab.data(), par, evarea.data());
+    } else {
+      mf::hp_units<Proc, Proc::HP_SPLIT>(begin, n, 0, 1, par, cp.data(), evarea.data());
+    }
+  };
   std::vector<unsigned char> vtab((1 << Proc::NEXT) * NH);
   for (int i = 0; i < (1 << Proc::NEXT) * NH; ++i) mf::hp_fill_vtab<Proc>(i, vtab.data());
   int only_h = -1;
@@ -47,12 +57,12 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
       for (int j = 0; j < Proc::NCOUP; ++j) {
         const long long o = coup_stride ? ((long long)j * nevt + ev) : j;
         cp[e * Proc::NCOUP + j] = mk(coup[2 * o], coup[2 * o + 1]);
+        mf::hp_fill_ftab(cp[e * Proc::NCOUP + j], ftab.data() + 4 * (e * Proc::NCOUP + j));
       }
     }
     for (int it = 0; it < Proc::NEXT * E * 2; ++it) mf::hp_externals<Proc>(it, E, mom.data(), par, sqh, evarea.data());
     for (int L = 2; L <= Proc::HP_MAXLEVEL; ++L) {
-      mf::hp_units<Proc, Proc::HP_SPLIT>(Proc::level_begin(L), Proc::level_begin(L + 1) - Proc::level_begin(L), 0, 1, par, cp.data(),
-                                         evarea.data());
+      units(L - 2, Proc::level_begin(L), Proc::level_begin(L + 1) - Proc::level_begin(L));
     }
     std::vector<double> me_h((size_t)E * NH, 0.0);
     if (Proc::HP_UNROLL) {
@@ -66,7 +76,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
         std::vector<cxd> J((size_t)T * NJ, mk(0.0, 0.0));
         for (int bi = 0; bi < Proc::HP_NBATCH; ++bi) {
           const mf::HpBatch bt = Proc::batch(pass * Proc::HP_NBATCH + bi);
-          mf::hp_units<Proc, Proc::HP_SPLIT>(bt.unit_begin, bt.unit_end - bt.unit_begin, 0, 1, par, cp.data(), evarea.data());
+          units(Proc::HP_MAXLEVEL - 1 + pass * Proc::HP_NBATCH + bi, bt.unit_begin, bt.unit_end - bt.unit_begin);
           // the tiles of the batch in table order
           for (int ee = 0; ee < E; ++ee)
             for (int ti = bt.tile_begin; ti < bt.tile_end; ++ti) {
