@@ -260,7 +260,8 @@ def hp_config(ir, key):
         # g g > t t~ g g g, measured (profiles/r02k_ttxggg_tmem_tuning.log): JAMPs parked in Tensor Memory 7.9e5 -> 9.4e5
         # events/s (no more spills at 128 registers), + pass-independent pair objects kept 9.9e5; 4 colour groups 6.3e5
         return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 2048 if hp_use_plan(ir) else 4096, "MINBLOCKS": 1, "PERSIST": 0,
-                "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 3, "TMEMJ": 1, "SLU": 0}[key]
+                "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 0 if hp_use_plan(ir) else 3, "TMEMJ": 1,
+                "SLU": 1 if hp_use_plan(ir) else 0}[key]
     # NB: 22 rows let the 64 rows of the reduced g g > t t~ g g fit in 3 batches (with two blocks per SM still resident)
     return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 22 if hp_use_plan(ir) else 21, "SCRATCH": 512, "MINBLOCKS": 2,
             "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0,
@@ -677,10 +678,10 @@ def emit_hp(ir):
     SLU = bool(hp_config(ir, "SLU")) and hp_available(ir)
     slu_tables, slu_stats = "", {}
     if SLU:
-        assert not TSPLIT, "straight-line units and units split over lanes exclude each other"
+        assert not TSPLIT, "packed units split long units themselves (TSPLIT belongs to the table-driven routine)"
         HP_E = hp_config(ir, "E")
         LPU, NWARP = 32 // HP_E, HP_E * NHP * NCG // 32
-        assert 32 % HP_E == 0 and NWARP >= 1 and len(ir["couplings"]) <= 4
+        assert 32 % HP_E == 0 and NWARP >= 1 and len(ir["couplings"]) <= 7
         KCOST = {"ROW": 10, "COL": 10, "CUR": 10, "VVV": 14, "VVVV": 18}
         FCOST = {"none": 1, "g": 6, "o": 10, "i": 10}
 
@@ -717,53 +718,113 @@ def emit_hp(ir):
             assert 0 <= off < (1 << 14) and 0 <= v < 32 and nlegs <= 5
             return off | v << 14 | nlegs << 19
 
-        classes, class_keys, class_cost, words, trips, ranges = {}, [], [], [], [], []
-        term_evals = 0
+        NULL_F = 31          # f-index of a null term: the entry of the f-table that is always zero
+        SPLIT_MIN = int(os.environ.get("MADFLOW_B200_HP_SLU_SPLIT_MIN", 24))   # never split units cheaper than this
+        words, trips, ranges = [], [], []
+        classes = set()
+        term_evals = null_evals = 0
         for units_of_phase in slu_phases:
+            # units of the phase by class = (vertex kinds in order, propagator); a unit = [header word, [words of term 0], ..]
             by_class = {}
             for obj, o_, variants in units_of_phase:
                 terms = slu_terms(obj)
                 nomom = obj.get("mom", 2) == 0 and obj["finish"] != "none"
                 key = (tuple(t["kind"] for t in terms), obj["finish"], nomom, pidx(obj.get("mass", "ZERO")), pidx(obj.get("width", "ZERO")))
-                if key not in classes:
-                    classes[key] = len(classes)
-                    class_keys.append(key)
-                    class_cost.append(sum(KCOST[k] for k in key[0]) + FCOST[key[1]])
+                classes.add(key)
                 out_off = o_ - 2 if nomom else o_
                 for v in variants:
-                    uw = [(desc(out_off, v, len(obj["legs"])), 0)]
+                    tw = []
                     for t in terms:
                         d = [desc(wfs[w]["off"], pext(v, vmask(obj["legs"], wfs[w]["legs"])), len(wfs[w]["legs"])) for w in t["ins"]]
-                        uw.append((d[0] | (t["coup"] * 4 + PHASE_CODE[t["ph"]]) << 22, d[1]))
+                        one = [(d[0] | (t["coup"] * 4 + PHASE_CODE[t["ph"]]) << 22, d[1])]
                         if t["kind"] == "VVVV":
                             ca, cb, cc = t["coefs"]
-                            uw.append((d[2], (ca + 2) | (cb + 2) << 3 | (cc + 2) << 6))
+                            one.append((d[2], (ca + 2) | (cb + 2) << 3 | (cc + 2) << 6))
+                        tw.append(one)
                         term_evals += 1
-                    by_class.setdefault(classes[key], []).append(uw)
-            # trips of one class each, longest processing time first onto the least loaded warp
+                    by_class.setdefault(key, []).append(((desc(out_off, v, len(obj["legs"])), 0), tw))
+
+            def cost(kinds, fin):
+                return sum(KCOST[k] for k in kinds) + FCOST[fin]
+
+            # parts: split the units of the class with the most expensive trip in two while that shortens the phase
+            # (longest-processing-time schedule of the trips on the warps of the block)
+            def part_kinds(kinds, g):
+                return tuple(k for k in sorted(PT, key=PT.get) for _ in range(-(-kinds.count(k) // g)))
+
+            def trip_cost(key, g):
+                return cost(part_kinds(key[0], g), key[1]) + (4 if g > 1 else 0)
+
+            def makespan(gs):
+                load = [0.0] * NWARP
+                costs = []
+                for key, us in by_class.items():
+                    costs += [trip_cost(key, gs[key])] * -(-len(us) * gs[key] // LPU)
+                for c in sorted(costs, reverse=True):
+                    load[load.index(min(load))] += c
+                return max(load)
+
+            gs = {key: 1 for key in by_class}
+            while by_class:
+                worst = max(by_class, key=lambda key: (trip_cost(key, gs[key]), key))
+                g = gs[worst]
+                if g >= 8 or g * 2 > LPU or len(worst[0]) < 2 * g or trip_cost(worst, g) < SPLIT_MIN:
+                    break
+                trial = dict(gs)
+                trial[worst] = 2 * g
+                if makespan(trial) >= makespan(gs):
+                    break
+                gs = trial
             ptrips = []
-            for cls, us in by_class.items():
-                for i in range(0, len(us), LPU):
-                    ptrips.append((cls, us[i:i + LPU]))
-            load, mine = [0] * NWARP, [[] for _ in range(NWARP)]
-            for cls, us in sorted(ptrips, key=lambda q: (-class_cost[q[0]], q[0])):
-                wi = min(range(NWARP), key=lambda q: (load[q], q))
-                load[wi] += class_cost[cls]
-                mine[wi].append((cls, us))
+            for key, us in by_class.items():
+                kinds, fin = key[0], key[1]
+                g = gs[key]
+                # every part evaluates the same kinds: per kind ceil(n / g) terms, short parts padded with null terms
+                per = {k: -(-kinds.count(k) // g) for k in PT}
+                pkinds = tuple(k for k in sorted(PT, key=PT.get) for _ in range(per[k]))
+                subs = []   # [(header, flat words)] per (unit, part)
+                for hdr, tw in us:
+                    for part in range(g):
+                        flat = []
+                        for k in sorted(PT, key=PT.get):
+                            mine = [w_ for w_, kk in zip(tw, kinds) if kk == k][part * per[k]:(part + 1) * per[k]]
+                            nullw = [w_ for w_, kk in zip(tw, kinds) if kk == k][:1]
+                            while len(mine) < per[k]:   # a null term: the inputs of a real one, f-index of the zero entry
+                                w0 = nullw[0]
+                                mine.append([((w0[0][0] & 0x3fffff) | NULL_F << 22, w0[0][1])] + w0[1:])
+                                null_evals += 1
+                            for w_ in mine:
+                                flat += w_
+                        subs.append([hdr] + flat)
+                upt = LPU // g   # units per trip
+                for i in range(0, len(us), upt):
+                    ptrips.append((key, g, pkinds, subs[i * g:(i + upt) * g], min(upt, len(us) - i)))
+            # trips of one class each, longest processing time first onto the least loaded warp
+            load, mine = [0.0] * NWARP, [[] for _ in range(NWARP)]
+            tcost = lambda q: cost(q[2], q[0][1]) + 4 * (q[1] > 1)
+            for q in sorted(ptrips, key=lambda q: (-tcost(q), q[0], q[1])):
+                wi = min(range(NWARP), key=lambda i: (load[i], i))
+                load[wi] += tcost(q)
+                mine[wi].append(q)
+            if os.environ.get("MADFLOW_B200_HP_SLU_VERBOSE"):
+                print(f"phase {len(ranges) // NWARP}: {len(ptrips)} trips, load max {max(load):.0f} mean {sum(load) / NWARP:.1f}; "
+                      + ", ".join(f"{'+'.join(k[0] for k in q[2])}/{q[1]}" for q in sorted(ptrips, key=lambda q: -tcost(q))[:6]))
             for wi in range(NWARP):
                 ranges.append((len(trips), len(trips) + len(mine[wi])))
-                for cls, us in mine[wi]:
-                    kinds, fin, nomom, mi, wi_ = class_keys[cls]
-                    assert len(us) < 256 and len(kinds) <= 10 and mi < 15 and wi_ < 15
-                    trips.append((len(words), len(us) | (FINISH[fin] + (4 if nomom else 0)) << 8 | (mi + 1) << 12 | (wi_ + 1) << 16 | len(kinds) << 20,
-                                  sum(PT[k] << (3 * q) for q, k in enumerate(kinds)), 0))
-                    for j in range(len(us[0])):
-                        words += [us[u][j] if u < len(us) else (0, 0) for u in range(LPU)]
+                for key, g, pkinds, subs, nunits in mine[wi]:
+                    _, fin, nomom, mi, wi_ = key
+                    assert nunits < 256 and len(pkinds) <= 10 and mi < 15 and wi_ < 15
+                    trips.append((len(words), nunits | (FINISH[fin] + (4 if nomom else 0)) << 8 | (mi + 1) << 12 | (wi_ + 1) << 16 | len(pkinds) << 20,
+                                  sum(PT[k] << (3 * q) for q, k in enumerate(pkinds)), g.bit_length() - 1))
+                    for j in range(len(subs[0])):
+                        # lanes beyond the trip's units repeat its first unit: they take part in the shuffles and store nothing
+                        words += [subs[u][j] if u < len(subs) else subs[u % g][j] for u in range(LPU)]
         slu_tables = "\n".join([
             both("uint2", "slu_words", max(len(words), 1), ", ".join(f"{{{x}u, {y}u}}" for x, y in words) or "{0u, 0u}", const=False),
             both("uint4", "slu_trips", max(len(trips), 1), ", ".join(f"{{{x}u, {y}u, {z}u, {w_}u}}" for x, y, z, w_ in trips) or "{0u, 0u, 0u, 0u}"),
             both("int2", "slu_ranges", max(len(ranges), 1), ", ".join(f"{{{x}, {y}}}" for x, y in ranges) or "{0, 0}")])
-        slu_stats = {"classes": len(classes), "trips": len(trips), "words": len(words), "term_evals": term_evals}
+        slu_stats = {"classes": len(classes), "trips": len(trips), "words": len(words), "term_evals": term_evals, "null_evals": null_evals,
+                     "split": any(t_[3] for t_ in trips)}
     else:
         slu_tables = "\n".join([both("uint2", "slu_words", 1, "{0u, 0u}", const=False), both("uint4", "slu_trips", 1, "{0u, 0u, 0u, 0u}"),
                                 both("int2", "slu_ranges", 1, "{0, 0}")])
@@ -1034,6 +1095,7 @@ struct Proc {{
   MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
   // packed units (process_kernels_hp.cuh "SLU"): trips per (phase, warp), one class of objects per trip
   static constexpr bool HP_SLU = {'true' if hp['slu'] else 'false'};
+  static constexpr bool HP_SLU_SPLIT = {'true' if hp['slu_stats'].get('split') else 'false'};   // some units are split over lanes
   MF_DEV static int2 slu_range(int i) {{ return MF_TAB(slu_ranges)[i]; }}
   MF_DEV static uint4 slu_trip(int i) {{ return MF_TAB(slu_trips)[i]; }}
   MF_DEV static const uint2* slu_words() {{ return MF_TAB(slu_words); }}

@@ -388,11 +388,11 @@ MF_DEV void hp_units(int begin, int n, int tid, int nthreads, const double* par,
 // per trip in constant memory.  What is left per lane is one 64-bit word per (unit, term) and one per unit, read
 // coalesced by the lanes of the trip:
 //   input descriptor (22 bits) = block offset in the event area (14) | helicity variant (5) << 14 | log2 variants (3) << 19
-//   term word   .x = input A | f-index << 22      .y = input B            f-index = coupling * 4 + phase code
+//   term word   .x = input A | f-index << 22      .y = input B            f-index = coupling * 4 + phase code (31: null term)
 //   4-gluon 2nd .x = input C                      .y = (ca + 2) | (cb + 2) << 3 | (cc + 2) << 6
 //   unit word   .x = output descriptor (offset = the block start, or start - 2 without momentum slots)
 //   trip        .x = first word   .y = units in use | HpFinish << 8 | (mass + 1) << 12 | (width + 1) << 16 | terms << 20
-//               .z = vertex kinds, 3 bits per term
+//               .z = vertex kinds, 3 bits per term     .w = log2(parts per unit)
 // f = -i COUP phase is looked up in a per-event table of the 4 phases of every coupling (shared memory).
 // The code stays a LOOP over the terms with a warp-uniform switch over the five vertex kinds: one function per
 // class (the first version, profiles/r02w_*) saved the same instructions but ran out of the instruction cache --
@@ -422,7 +422,7 @@ MF_DEV void slu_term(const uint2* w, int stride, int& j, const cxd* ev_e, const 
   const uint2 t = w[j * stride];
   ++j;
   const SluIn ia = slu_in(t.x & 0x3fffffu, ev_e), ib = slu_in(t.y & 0x3fffffu, ev_e);
-  const cxd f = ftab_e[(t.x >> 22) & 15u];
+  const cxd f = ftab_e[(t.x >> 22) & 31u];
   cxd a[6], b[6];
   slu_load(ia, a);
   slu_load(ib, b);
@@ -450,43 +450,82 @@ MF_DEV void slu_term(const uint2* w, int stride, int& j, const cxd* ev_e, const 
   }
 }
 
-// f-table of one coupling: -i COUP x phase for the phase codes 0..3 = 1, -1, i, -i
+// f-table of an event: SLU_NF entries, [coupling * 4 + phase code] = -i COUP x {1, -1, i, -i}; the rest, in particular
+// the last one (the f-index of a null term), is zero
+constexpr int SLU_NF = 32;
 MF_DEV void hp_fill_ftab(cxd coup, cxd* f4) {
   const cxd f = mul_mi(coup);
   f4[0] = f, f4[1] = -f, f4[2] = mul_i(f), f4[3] = -mul_i(f);
 }
 
-// The trips of phase `ph` that belong to `warp`: lane = unit * E + event.  Proc::slu_range(ph * warps + warp) = first
-// and last + 1 trip; word j of unit u of a trip at [first word + j * (32/E) + u].
+// the terms of one lane's share of a unit: `kinds` = 3 bits per term (warp-uniform), words from w[stride], w[2 stride], ..
+MF_DEV void slu_terms(const uint2* w, int stride, unsigned kinds, int nterms, bool want_mom, const cxd* ev_e, const cxd* ftab_e,
+                      cxd Q[4], cxd mw[2]) {
+  int j = 1;
+#pragma unroll 1
+  for (int q = 0; q < nterms; ++q, kinds >>= 3) {
+    const bool wm = q == 0 && want_mom;   // the momentum slots come with the first term
+    switch (kinds & 7u) {
+      case HP_Q_ROW: slu_term<HP_Q_ROW>(w, stride, j, ev_e, ftab_e, Q, mw, wm); break;
+      case HP_Q_COL: slu_term<HP_Q_COL>(w, stride, j, ev_e, ftab_e, Q, mw, wm); break;
+      case HP_Q_CUR: slu_term<HP_Q_CUR>(w, stride, j, ev_e, ftab_e, Q, mw, wm); break;
+      case HP_Q_VVV: slu_term<HP_Q_VVV>(w, stride, j, ev_e, ftab_e, Q, mw, wm); break;
+      default: slu_term<HP_Q_VVVV>(w, stride, j, ev_e, ftab_e, Q, mw, wm); break;
+    }
+  }
+}
+
+// The trips of phase `ph` that belong to `warp`.  Proc::slu_range(ph * warps + warp) = first and last + 1 trip.  A
+// unit with many terms is split into g = 2^k PARTS evaluated by neighbouring lanes (every part the same sequence of
+// vertex kinds, padded with null terms whose f-index points at a zero) and added up with warp shuffles in the fixed
+// order of a binary tree; part 0 applies the propagator and stores.  lane = ((unit * g) + part) * E + event; word j of
+// (unit, part) at [first word + j * (32/E) + unit * g + part]; lanes beyond the trip's units repeat its first unit
+// (they take part in the shuffles) and store nothing.
 template <class P>
 MF_DEV void slu_units(int ph, int warp, int lane, const cxd* ftab, const double* par, cxd* ev) {
   constexpr int E = P::HP_E, LPU = 32 / E, NW = P::HP_THREADS / 32;
   static_assert(32 % E == 0, "events per block divide the warp");
-  const int u = lane / E, e = lane - u * E;
-  const cxd* ftab_e = ftab + e * (4 * (P::NCOUP > 0 ? P::NCOUP : 1));
+  const int lu = lane / E, e = lane - lu * E;
+  const cxd* ftab_e = ftab + e * SLU_NF;
   cxd* ev_e = ev + e * P::HP_EVSTRIDE;
   const int2 r = P::slu_range(ph * NW + warp);
 #pragma unroll 1
   for (int t = r.x; t < r.y; ++t) {
     const uint4 d = P::slu_trip(t);
-    if (u >= (int)(d.y & 0xffu)) continue;
-    const uint2* w = P::slu_words() + d.x + u;
+    const int glog = P::HP_SLU_SPLIT ? (int)d.w : 0, part = lu & ((1 << glog) - 1);   // HP_SLU_SPLIT false: no trip is split
+    const bool active = (lu >> glog) < (int)(d.y & 0xffu);
     const int fin = (int)((d.y >> 8) & 7u), nterms = (int)(d.y >> 20);
     cxd Q[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
     cxd mw[2] = {mk(0.0, 0.0), mk(0.0, 0.0)};
-    unsigned kinds = d.z;
-    int j = 1;
+#ifdef __CUDA_ARCH__
+    const uint2* w = P::slu_words() + d.x + lu;
+    slu_terms(w, LPU, d.z, nterms, fin != HP_F_NONE && part == 0, ev_e, ftab_e, Q, mw);
+    if constexpr (P::HP_SLU_SPLIT) {
 #pragma unroll 1
-    for (int q = 0; q < nterms; ++q, kinds >>= 3) {
-      const bool want_mom = q == 0 && fin != HP_F_NONE;   // the momentum slots come with the first term
-      switch (kinds & 7u) {
-        case HP_Q_ROW: slu_term<HP_Q_ROW>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
-        case HP_Q_COL: slu_term<HP_Q_COL>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
-        case HP_Q_CUR: slu_term<HP_Q_CUR>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
-        case HP_Q_VVV: slu_term<HP_Q_VVV>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
-        default: slu_term<HP_Q_VVVV>(w, LPU, j, ev_e, ftab_e, Q, mw, want_mom); break;
+      for (int o = (1 << glog) >> 1; o > 0; o >>= 1) {   // lane p adds lane p + o: the sum arrives in part 0
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          Q[k].re += __shfl_down_sync(0xffffffffu, Q[k].re, o * E);
+          Q[k].im += __shfl_down_sync(0xffffffffu, Q[k].im, o * E);
+        }
       }
     }
+    if (!active || part != 0) continue;
+#else
+    // on the host the lane of part 0 evaluates all parts in turn and adds them in the order of the device's tree
+    if (!active || part != 0) continue;
+    const uint2* w = P::slu_words() + d.x + lu;
+    cxd Qp[8][4];
+    for (int pp = 0; pp < (1 << glog); ++pp) {
+      for (int k = 0; k < 4; ++k) Qp[pp][k] = mk(0.0, 0.0);
+      cxd mwp[2];
+      slu_terms(w + pp, LPU, d.z, nterms, fin != HP_F_NONE && pp == 0, ev_e, ftab_e, Qp[pp], pp == 0 ? mw : mwp);
+    }
+    for (int o = (1 << glog) >> 1; o > 0; o >>= 1)
+      for (int pp = 0; pp < o; ++pp)
+        for (int k = 0; k < 4; ++k) Qp[pp][k] += Qp[pp + o][k];
+    for (int k = 0; k < 4; ++k) Q[k] = Qp[0][k];
+#endif
     const unsigned od = w[0].x;
     cxd* o = ev_e + (od & 0x3fffu);
     const int v = (int)((od >> 14) & 31u), nv = 1 << ((od >> 19) & 7u);
@@ -954,7 +993,7 @@ struct HpSmatrixSmem {
   static constexpr int E = P::HP_E, T = P::HP_THREADS;
   double mom[E * P::NEXT * 4];
   cxd coup[E * (P::NCOUP > 0 ? P::NCOUP : 1)];
-  cxd ftab[P::HP_SLU ? 4 * E * (P::NCOUP > 0 ? P::NCOUP : 1) : 1];   // -i COUP x {1, -1, i, -i} per event and coupling (SLU)
+  cxd ftab[P::HP_SLU ? E * SLU_NF : 1];   // -i COUP x {1, -1, i, -i} per event and coupling, zero beyond (SLU)
   double red[T / 32 + 1];
   unsigned tmem_addr;   // base of the block's Tensor Memory allocation (HP_TMEM_J)
   unsigned char vtab[P::HP_UNROLL ? (1 << P::NEXT) * P::NCOMB : 16];  // straight-line flavour only
@@ -1016,8 +1055,11 @@ __global__ void __launch_bounds__(P::HP_THREADS, P::HP_MINBLOCKS) smatrix_kernel
           const double2 v = reinterpret_cast<const double2*>(a.coup)[a.coup_stride ? (long long)c * a.nevt + ev : c];
           s.coup[i] = mk(v.x, v.y);
         }
-        if constexpr (P::HP_SLU) hp_fill_ftab(s.coup[i], s.ftab + 4 * i);
+        if constexpr (P::HP_SLU) hp_fill_ftab(s.coup[i], s.ftab + e * SLU_NF + 4 * c);
       }
+      if constexpr (P::HP_SLU)
+        for (int i = tid; i < E * SLU_NF; i += T)
+          if (i % SLU_NF >= 4 * P::NCOUP) s.ftab[i] = mk(0.0, 0.0);
       __syncthreads();
       const double me = hp_smatrix_block<P>(nev, s.mom, s.coup, s.ftab, a.par, a.sqh, evarea, s.vtab, s.red, only_h, tmem_base);
       const int e = tid / TE;

@@ -32,7 +32,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
   std::vector<cxd> evarea((size_t)EVS * E);
   std::vector<double> mom(E * Proc::NEXT * 4);
   std::vector<cxd> cp(E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
-  std::vector<cxd> ftab(4 * E * (Proc::NCOUP > 0 ? Proc::NCOUP : 1));
+  std::vector<cxd> ftab((size_t)E * mf::SLU_NF, mk(0.0, 0.0));
   // one phase of units: the table-driven routine, or the straight-line units warp by warp, lane by lane
   auto units = [&](int slu_phase, int begin, int n) {
     if (Proc::HP_SLU) {
@@ -57,7 +57,7 @@ extern "C" int hostcheck_smatrix_hp(const double* p, long long nevt, const doubl
       for (int j = 0; j < Proc::NCOUP; ++j) {
         const long long o = coup_stride ? ((long long)j * nevt + ev) : j;
         cp[e * Proc::NCOUP + j] = mk(coup[2 * o], coup[2 * o + 1]);
-        mf::hp_fill_ftab(cp[e * Proc::NCOUP + j], ftab.data() + 4 * (e * Proc::NCOUP + j));
+        mf::hp_fill_ftab(cp[e * Proc::NCOUP + j], ftab.data() + e * mf::SLU_NF + 4 * j);
       }
     }
     for (int it = 0; it < Proc::NEXT * E * 2; ++it) mf::hp_externals<Proc>(it, E, mom.data(), par, sqh, evarea.data());
