@@ -815,8 +815,7 @@ def emit_hp(ir):
                     _, fin, nomom, mi, wi_ = key
                     assert nunits < 256 and len(pkinds) <= 10 and mi < 15 and wi_ < 15
                     trips.append((len(words), nunits | (FINISH[fin] + (4 if nomom else 0)) << 8 | (mi + 1) << 12 | (wi_ + 1) << 16 | len(pkinds) << 20,
-                                  sum(PT[k] << (3 * q) for q, k in enumerate(pkinds)),
-                                  (g.bit_length() - 1) | sum(pkinds.count(k) << (4 + 4 * PT[k]) for k in PT)))
+                                  sum(PT[k] << (3 * q) for q, k in enumerate(pkinds)), g.bit_length() - 1))
                     for j in range(len(subs[0])):
                         # lanes beyond the trip's units repeat its first unit: they take part in the shuffles and store nothing
                         words += [subs[u][j] if u < len(subs) else subs[u % g][j] for u in range(LPU)]
@@ -825,7 +824,7 @@ def emit_hp(ir):
             both("uint4", "slu_trips", max(len(trips), 1), ", ".join(f"{{{x}u, {y}u, {z}u, {w_}u}}" for x, y, z, w_ in trips) or "{0u, 0u, 0u, 0u}"),
             both("int2", "slu_ranges", max(len(ranges), 1), ", ".join(f"{{{x}, {y}}}" for x, y in ranges) or "{0, 0}")])
         slu_stats = {"classes": len(classes), "trips": len(trips), "words": len(words), "term_evals": term_evals, "null_evals": null_evals,
-                     "split": any(t_[3] & 15 for t_ in trips)}
+                     "split": any(t_[3] for t_ in trips)}
     else:
         slu_tables = "\n".join([both("uint2", "slu_words", 1, "{0u, 0u}", const=False), both("uint4", "slu_trips", 1, "{0u, 0u, 0u, 0u}"),
                                 both("int2", "slu_ranges", 1, "{0, 0}")])

@@ -392,7 +392,7 @@ MF_DEV void hp_units(int begin, int n, int tid, int nthreads, const double* par,
 //   4-gluon 2nd .x = input C                      .y = (ca + 2) | (cb + 2) << 3 | (cc + 2) << 6
 //   unit word   .x = output descriptor (offset = the block start, or start - 2 without momentum slots)
 //   trip        .x = first word   .y = units in use | HpFinish << 8 | (mass + 1) << 12 | (width + 1) << 16 | terms << 20
-//               .z = vertex kinds, 3 bits per term     .w = log2(parts per unit) | terms of each kind (4 bits per kind) << 4
+//               .z = vertex kinds, 3 bits per term     .w = log2(parts per unit)
 // f = -i COUP phase is looked up in a per-event table of the 4 phases of every coupling (shared memory).
 // The code stays a LOOP over the terms with a warp-uniform switch over the five vertex kinds: one function per
 // class (the first version, profiles/r02w_*) saved the same instructions but ran out of the instruction cache --
@@ -458,64 +458,6 @@ MF_DEV void hp_fill_ftab(cxd coup, cxd* f4) {
   f4[0] = f, f4[1] = -f, f4[2] = mul_i(f), f4[3] = -mul_i(f);
 }
 
-// the same with the term's words already in registers
-template <int KIND>
-MF_DEV void slu_term_w(uint2 t, uint2 t2, const cxd* ev_e, const cxd* ftab_e, cxd Q[4], cxd mw[2], bool want_mom) {
-  const SluIn ia = slu_in(t.x & 0x3fffffu, ev_e), ib = slu_in(t.y & 0x3fffffu, ev_e);
-  const cxd f = ftab_e[(t.x >> 22) & 31u];
-  cxd a[6], b[6];
-  slu_load(ia, a);
-  slu_load(ib, b);
-  if (KIND == HP_Q_VVV || want_mom) {
-    slu_load_mom(ia, a);
-    slu_load_mom(ib, b);
-    mw[0] = a[0] + b[0], mw[1] = a[1] + b[1];
-  }
-  if (KIND == HP_Q_ROW) hp_q_row(a, b, f, Q);
-  if (KIND == HP_Q_COL) hp_q_col(a, b, f, Q);
-  if (KIND == HP_Q_CUR) hp_q_cur(a, b, f, Q);
-  if (KIND == HP_Q_VVV) hp_q_vvv(a, b, f, Q);
-  if (KIND == HP_Q_VVVV) {
-    const SluIn ic = slu_in(t2.x & 0x3fffffu, ev_e);
-    cxd c[6];
-    slu_load(ic, c);
-    if (want_mom) {
-      slu_load_mom(ic, c);
-      mw[0] += c[0], mw[1] += c[1];
-    }
-    const double ca = (double)((int)(t2.y & 7u) - 2), cb = (double)((int)((t2.y >> 3) & 7u) - 2), cc = (double)((int)((t2.y >> 6) & 7u) - 2);
-    hp_q_vvvv_merged(a, b, c, ca, cb, cc, f, Q);
-  }
-}
-
-// the terms of one lane's share of a unit, one warp-uniform loop per vertex kind (the terms are sorted by kind; `counts`
-// = 4 bits per kind), no indirect branch; the word after next is in flight while a term is evaluated
-MF_DEV void slu_terms_by_kind(const uint2* w, int stride, unsigned counts, bool want_mom, const cxd* ev_e, const cxd* ftab_e,
-                              cxd Q[4], cxd mw[2]) {
-  uint2 tw = w[stride], tw2 = w[2 * stride];
-  int j = 2;   // the next word to fetch is j + 1
-#define MF_SLU_KIND(KIND)                                                                 \
-  _Pragma("unroll 1") for (int i = (int)((counts >> (4 * KIND)) & 15u); i > 0; --i) {       \
-    const uint2 c1 = tw;                                                                  \
-    tw = tw2, tw2 = w[++j * stride];                                                      \
-    slu_term_w<KIND>(c1, tw, ev_e, ftab_e, Q, mw, want_mom);                              \
-    want_mom = false;                                                                     \
-  }
-  MF_SLU_KIND(HP_Q_ROW)
-  MF_SLU_KIND(HP_Q_COL)
-  MF_SLU_KIND(HP_Q_CUR)
-  MF_SLU_KIND(HP_Q_VVV)
-#undef MF_SLU_KIND
-#pragma unroll 1
-  for (int i = (int)((counts >> (4 * HP_Q_VVVV)) & 15u); i > 0; --i) {   // two words per term
-    const uint2 c1 = tw, c2 = tw2;
-    tw = w[(j + 1) * stride], tw2 = w[(j + 2) * stride];
-    j += 2;
-    slu_term_w<HP_Q_VVVV>(c1, c2, ev_e, ftab_e, Q, mw, want_mom);
-    want_mom = false;
-  }
-}
-
 // the terms of one lane's share of a unit: `kinds` = 3 bits per term (warp-uniform), words from w[stride], w[2 stride], ..
 MF_DEV void slu_terms(const uint2* w, int stride, unsigned kinds, int nterms, bool want_mom, const cxd* ev_e, const cxd* ftab_e,
                       cxd Q[4], cxd mw[2]) {
@@ -539,13 +481,8 @@ MF_DEV void slu_terms(const uint2* w, int stride, unsigned kinds, int nterms, bo
 // order of a binary tree; part 0 applies the propagator and stores.  lane = ((unit * g) + part) * E + event; word j of
 // (unit, part) at [first word + j * (32/E) + unit * g + part]; lanes beyond the trip's units repeat its first unit
 // (they take part in the shuffles) and store nothing.
-#ifdef MF_SLU_NOINLINE   // A/B switch: the unit phases as a function of their own (one copy, its own register allocation)
-#define MF_SLU_FN __host__ __device__ __noinline__
-#else
-#define MF_SLU_FN MF_DEV
-#endif
 template <class P>
-MF_SLU_FN void slu_units(int ph, int warp, int lane, const cxd* ftab, const double* par, cxd* ev) {
+MF_DEV void slu_units(int ph, int warp, int lane, const cxd* ftab, const double* par, cxd* ev) {
   constexpr int E = P::HP_E, LPU = 32 / E, NW = P::HP_THREADS / 32;
   static_assert(32 % E == 0, "events per block divide the warp");
   const int lu = lane / E, e = lane - lu * E;
@@ -555,18 +492,14 @@ MF_SLU_FN void slu_units(int ph, int warp, int lane, const cxd* ftab, const doub
 #pragma unroll 1
   for (int t = r.x; t < r.y; ++t) {
     const uint4 d = P::slu_trip(t);
-    const int glog = P::HP_SLU_SPLIT ? (int)(d.w & 15u) : 0, part = lu & ((1 << glog) - 1);   // HP_SLU_SPLIT false: no trip is split
+    const int glog = P::HP_SLU_SPLIT ? (int)d.w : 0, part = lu & ((1 << glog) - 1);   // HP_SLU_SPLIT false: no trip is split
     const bool active = (lu >> glog) < (int)(d.y & 0xffu);
     const int fin = (int)((d.y >> 8) & 7u), nterms = (int)(d.y >> 20);
     cxd Q[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
     cxd mw[2] = {mk(0.0, 0.0), mk(0.0, 0.0)};
 #ifdef __CUDA_ARCH__
     const uint2* w = P::slu_words() + d.x + lu;
-#ifdef MF_SLU_KINDLOOPS
-    slu_terms_by_kind(w, LPU, d.w >> 4, fin != HP_F_NONE && part == 0, ev_e, ftab_e, Q, mw);
-#else
     slu_terms(w, LPU, d.z, nterms, fin != HP_F_NONE && part == 0, ev_e, ftab_e, Q, mw);
-#endif
     if constexpr (P::HP_SLU_SPLIT) {
 #pragma unroll 1
       for (int o = (1 << glog) >> 1; o > 0; o >>= 1) {   // lane p adds lane p + o: the sum arrives in part 0
