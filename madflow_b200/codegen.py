@@ -819,6 +819,7 @@ def emit_hp(ir):
                     for j in range(len(subs[0])):
                         # lanes beyond the trip's units repeat its first unit: they take part in the shuffles and store nothing
                         words += [subs[u][j] if u < len(subs) else subs[u % g][j] for u in range(LPU)]
+        words += [(0, 0)] * 128    # the kernel reads up to three words ahead of a unit's last one
         slu_tables = "\n".join([
             both("uint2", "slu_words", max(len(words), 1), ", ".join(f"{{{x}u, {y}u}}" for x, y in words) or "{0u, 0u}", const=False),
             both("uint4", "slu_trips", max(len(trips), 1), ", ".join(f"{{{x}u, {y}u, {z}u, {w_}u}}" for x, y, z, w_ in trips) or "{0u, 0u, 0u, 0u}"),
@@ -1095,6 +1096,8 @@ struct Proc {{
   MF_DEV static mf::HpBatch batch(int i) {{ return MF_TAB(batches)[i]; }}
   // packed units (process_kernels_hp.cuh "SLU"): trips per (phase, warp), one class of objects per trip
   static constexpr bool HP_SLU = {'true' if hp['slu'] else 'false'};
+  // the words of the next term are fetched while the current one is evaluated (tables beyond L1; measured per process)
+  static constexpr bool HP_SLU_PREFETCH = {'true' if hp['slu_stats'].get('words', 0) * 8 > int(os.environ.get("MADFLOW_B200_HP_SLU_PREFETCH_BYTES", 65536)) else 'false'};
   static constexpr bool HP_SLU_SPLIT = {'true' if hp['slu_stats'].get('split') else 'false'};   // some units are split over lanes
   MF_DEV static int2 slu_range(int i) {{ return MF_TAB(slu_ranges)[i]; }}
   MF_DEV static uint4 slu_trip(int i) {{ return MF_TAB(slu_trips)[i]; }}
