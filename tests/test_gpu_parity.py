@@ -1083,6 +1083,49 @@ def test_plugin_written_vertex_routine_on_the_gpu(mf, tmp_path, monkeypatch):
     np.testing.assert_allclose(cpu(out), ref, rtol=REL_ME)
 
 
+def test_packed_units_equal_the_table_driven_units_on_the_gpu(mf, tmp_path, monkeypatch):
+    """g g > t t~ g g: the default library (packed units: warp trips of one class, merged four-gluon terms) against a
+    library of the same process built with the table-driven unit routine (MADFLOW_B200_HP_SLU=0, the A/B partner and the
+    path of every other process) on 4000 points with running couplings: equal to 1e-13, both within 1e-12 of the oracle
+    (recycled wavefunctions); one helicity row as well."""
+    import shutil
+
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    from madflow_b200 import codegen, procgen
+
+    ir = procgen.generate_ir(2)
+    monkeypatch.setenv("MADFLOW_B200_HP_SLU", "0")
+    src = str(tmp_path / "proc_tab.cu")
+    text = codegen.emit_process_source(ir)
+    monkeypatch.delenv("MADFLOW_B200_HP_SLU")
+    assert "HP_SLU = false" in text and "HP_SLU = true" in codegen.emit_process_source(ir)
+    open(src, "w").write(text)
+    tab = mf.rt.ProcessLib(codegen.compile_source(src, str(tmp_path / "libmfp_1_gg_ttxgg_tab.so")))
+    dflt = mf.rt.ProcessLib(codegen.lib_path(ir))
+    npts = 4000
+    x = np.random.default_rng(31).random((npts, 18))
+    p, w, x1, x2 = ops.ramboflow(x, 6, 13e3, [MT, MT, 0.0, 0.0], xfactor="converged")
+    lab = ops.boost_to_lab(p, x1, x2)
+    a_s = 0.09 + 0.05 * np.random.default_rng(32).random(npts)
+    params = sm_params(alpha_s=a_s)
+    coup = torch.as_tensor(np.stack([params[c] for c in ir["couplings"]])).cuda().contiguous()
+    mom = torch.as_tensor(lab).cuda().contiguous()
+    outs = []
+    for lib in (dflt, tab):
+        out = torch.empty(npts, dtype=torch.float64, device="cuda")
+        lib.smatrix(mom, 0, npts, [MT, WT], coup, 1, SQH_REF, out)
+        outs.append(cpu(out))
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-13)
+    np.testing.assert_allclose(outs[0], omatrix.smatrix_recycled(ir, lab, params), rtol=REL_ME)
+    rows = []
+    for lib in (dflt, tab):
+        out = torch.empty(npts, dtype=torch.float64, device="cuda")
+        lib.smatrix(mom, 0, npts, [MT, WT], coup, 1, SQH_REF, out, only_comb=37)
+        rows.append(cpu(out))
+    np.testing.assert_allclose(rows[0], rows[1], rtol=1e-11, atol=1e-300)
+
+
 def test_one_matrix_integration_with_pdf(mf, toy_pdf):
     """utilities.one_matrix_integration(pdf=, flavours=): the reference's regression harness (utilities.py:42-90,
     tests/test_integration.py) -- luminosity of the given flavour at the fixed scale q, frozen couplings, COM momenta, no

@@ -138,6 +138,41 @@ def test_helicity_parallel_data_flow_on_host(irs, k):
     np.testing.assert_allclose(one, omatrix.matrix(ir, p, ir["helicities"][row], params), rtol=1e-11)
 
 
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+def test_packed_units_equal_the_table_driven_units_on_host(irs, monkeypatch):
+    """The two implementations of the unit phases of g g > t t~ g g -- packed units (warp trips of one class, merged
+    four-gluon terms, one 64-bit word per term: the default) and the table-driven routine (MADFLOW_B200_HP_SLU=0, the
+    path of every other process) -- executed on the CPU on the same points: equal to 1e-13 and both equal to the oracle.
+    Also the bookkeeping of the packing: every (object, helicity variant) of the plan is evaluated, no null term without
+    a split unit, and the split of g g > t t~ g g g pads less than 10 % of its term evaluations."""
+    import copy
+
+    import hostcheck as hc
+
+    ir = irs[2]
+    p = _points(2, n=6, seed=21)
+    a_s = 0.09 + 0.05 * np.random.default_rng(5).random(6)
+    params = sm_params(alpha_s=a_s)
+    coup = np.stack([params[c] for c in ir["couplings"]])
+    ref = omatrix.smatrix(ir, p, params)
+    stats = codegen.emit_hp(ir)[4]
+    assert stats["slu"] and stats["slu_stats"]["null_evals"] == 0 and not stats["slu_stats"]["split"]
+    packed = hc.smatrix(hc.process(ir), ir, p, [MT, WT], coup, SQH_REF, hp=True)
+    monkeypatch.setenv("MADFLOW_B200_HP_SLU", "0")
+    tab_ir = copy.deepcopy(ir)
+    tab_ir["name"] = ir["name"] + "_tabledriven"     # not a built-in name: its source stays with the test artefacts
+    tab_stats = codegen.emit_hp(tab_ir)[4]
+    assert not tab_stats["slu"]
+    table = hc.smatrix(hc.process(tab_ir), tab_ir, p, [MT, WT], coup, SQH_REF, hp=True)
+    monkeypatch.delenv("MADFLOW_B200_HP_SLU")
+    np.testing.assert_allclose(packed, table, rtol=1e-13)
+    np.testing.assert_allclose(packed, ref, rtol=1e-12)
+    # merged four-gluon terms: fewer term evaluations than work items of the table-driven routine
+    assert stats["slu_stats"]["term_evals"] == 1196
+    big = codegen.emit_hp(irs[3])[4]["slu_stats"]
+    assert big["split"] and 0 < big["null_evals"] < 0.1 * big["term_evals"]
+
+
 def _mandelstam(p):
     dot = lambda a, b: a[:, 0] * b[:, 0] - np.sum(a[:, 1:] * b[:, 1:], axis=1)
     s = dot(p[:, 0] + p[:, 1], p[:, 0] + p[:, 1])
