@@ -3,7 +3,7 @@
 # inside, reference arm), ncu launch list, ncu --set full captures of g g > t t~ g g (g), phase timers.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=r02f
+T=r02final
 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/${T}_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 > gpurun_out/${T}_smoke.log
 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${T}_bench_1gpu_reference.json
