@@ -246,6 +246,7 @@ def hp_config(ir, key):
                  units per phase and up to 12 terms per object (g g > t t~ g g g) the longest unit sets the phase's time
       TMEMJ      1 = the JAMP accumulators live in Tensor Memory between the JAMP phases of the batches instead of in
                  registers (frees NCOLOR/NCG complex registers for the current / pair / tile phases)
+      MT         tiles of the amplitude phase in flight per warp (x events per block)
       SLU        1 = packed units: the units of a phase sorted into warp trips of one class of objects (sequence of vertex
                  kinds + propagator kind), one descriptor per trip and one 64-bit word per (unit, term) left to read at run
                  time (process_kernels_hp.cuh, "SLU"); needs TSPLIT = 0
@@ -261,11 +262,11 @@ def hp_config(ir, key):
         # events/s (no more spills at 128 registers), + pass-independent pair objects kept 9.9e5; 4 colour groups 6.3e5
         return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 2048 if hp_use_plan(ir) else 4096, "MINBLOCKS": 1, "PERSIST": 0,
                 "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 0 if hp_use_plan(ir) else 3, "TMEMJ": 1,
-                "SLU": 1 if hp_use_plan(ir) else 0}[key]
+                "SLU": 1 if hp_use_plan(ir) else 0, "MT": 1 if hp_use_plan(ir) else 2}[key]
     # NB: 22 rows let the 64 rows of the reduced g g > t t~ g g fit in 3 batches (with two blocks per SM still resident)
     return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 22 if hp_use_plan(ir) else 21, "SCRATCH": 512, "MINBLOCKS": 2,
             "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0,
-            "SLU": 1 if (hp_use_plan(ir) and ir["ncomb"] == 64) else 0}[key]
+            "SLU": 1 if (hp_use_plan(ir) and ir["ncomb"] == 64) else 0, "MT": 2}[key]
 
 
 def hp_use_plan(ir):
@@ -1073,7 +1074,8 @@ struct Proc {{
   static constexpr bool HP_TMEM_J = {'true' if (hp_config(ir, "TMEMJ") and not hp['unroll']) else 'false'};
   // tile descriptors per warp and trip (x HP_E tiles in flight): 2 tiles in flight measured best -- more only adds
   // padded tiles at the end of a batch (g g > t t~ g g: 17.7e6 events/s with 2, 16.5e6 with 4, 14.5e6 with 8)
-  static constexpr int HP_TILES_IN_FLIGHT = {max(1, int(os.environ.get("MADFLOW_B200_HP_MT", 2)) // hp_e)};
+  // g g > t t~ g g g with packed units: 1 (no spills at 128 registers, 1.24e6 -> 1.30e6 events/s; 4: 1.18e6)
+  static constexpr int HP_TILES_IN_FLIGHT = {max(1, hp_config(ir, "MT") // hp_e)};
   // colour contraction: 0 in-thread, 1 generated code over colour groups, 2 tensor cores, 3 CUDA-core loop
   // (2 and 3 read the block-symmetrised matrix d_cfsym and JAMP planes of HP_PLANE doubles per colour)
   static constexpr int HP_COLOUR = {hp['cmode']}, HP_NCP = {hp['ncp']}, HP_PLANE = HP_NHP + 4;
