@@ -721,6 +721,7 @@ def emit_hp(ir):
 
         NULL_F = 31          # f-index of a null term: the entry of the f-table that is always zero
         SPLIT_MIN = int(os.environ.get("MADFLOW_B200_HP_SLU_SPLIT_MIN", 24))   # never split units cheaper than this
+        SPLIT_MAX = int(os.environ.get("MADFLOW_B200_HP_SLU_SPLIT_MAX", 0))    # 0: off
         words, trips, ranges = [], [], []
         classes = set()
         term_evals = null_evals = 0
@@ -766,16 +767,25 @@ def emit_hp(ir):
                 return max(load)
 
             gs = {key: 1 for key in by_class}
+            for key in by_class:   # optional: units costlier than SPLIT_MAX are split whatever the schedule says
+                while (SPLIT_MAX and trip_cost(key, gs[key]) > SPLIT_MAX and gs[key] < 8 and gs[key] * 2 <= LPU
+                       and len(key[0]) >= 2 * gs[key]):
+                    gs[key] *= 2
             while by_class:
-                worst = max(by_class, key=lambda key: (trip_cost(key, gs[key]), key))
-                g = gs[worst]
-                if g >= 8 or g * 2 > LPU or len(worst[0]) < 2 * g or trip_cost(worst, g) < SPLIT_MIN:
+                # the split (of any class) that shortens the phase most; stop when none does
+                best, best_span = None, makespan(gs)
+                for key in sorted(by_class, key=lambda key: (-trip_cost(key, gs[key]), key)):
+                    g = gs[key]
+                    if g >= 8 or g * 2 > LPU or len(key[0]) < 2 * g or trip_cost(key, g) < SPLIT_MIN:
+                        continue
+                    trial = dict(gs)
+                    trial[key] = 2 * g
+                    span = makespan(trial)
+                    if span < best_span:
+                        best, best_span = trial, span
+                if best is None:
                     break
-                trial = dict(gs)
-                trial[worst] = 2 * g
-                if makespan(trial) >= makespan(gs):
-                    break
-                gs = trial
+                gs = best
             ptrips = []
             for key, us in by_class.items():
                 kinds, fin = key[0], key[1]
