@@ -264,7 +264,14 @@ def hp_config(ir, key):
                 "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 0 if hp_use_plan(ir) else 3, "TMEMJ": 1,
                 "SLU": 1 if hp_use_plan(ir) else 0, "MT": 1 if hp_use_plan(ir) else 2}[key]
     # NB: 22 rows let the 64 rows of the reduced g g > t t~ g g fit in 3 batches (with two blocks per SM still resident)
-    return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 22 if hp_use_plan(ir) else 21, "SCRATCH": 512, "MINBLOCKS": 2,
+    # MINBLOCKS: g g > t t~ g (32 combinations, straight-line amplitudes) runs 4.6 % faster with three blocks per SM at 168
+    # registers, spills included (1.41e8 -> 1.48e8 events/s; four blocks: 1.03e8), profiles/r02zt_*, r02zu_*
+    # the four-quark six-point processes (<= 40 calls, 6 colour flows): four blocks per SM at 128 registers, +22...24 %
+    # (q q~ > t t~ q q~ 6.6e7 -> 8.0e7, q q' > t t~ q q' 1.13e8 -> 1.39e8); the 73-call light-line processes stay at two
+    # (three: -6 %), profiles/r02zv_*
+    small6 = ir["ncomb"] == 64 and not hp_use_plan(ir) and len(ir["calls"]) <= 40
+    return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 22 if hp_use_plan(ir) else 21, "SCRATCH": 512,
+            "MINBLOCKS": 3 if (ir["ncomb"] == 32 and len(ir["calls"]) > 24) else (4 if small6 else 2),
             "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0,
             "SLU": 1 if (hp_use_plan(ir) and ir["ncomb"] == 64) else 0, "MT": 2}[key]
 
@@ -871,7 +878,7 @@ def emit_hp(ir):
         A.append("      break;")
     A.append("    default: break;")
     A.append("    }")
-    unroll = len(plan["rows"]) <= HP_UNROLL_MAX_AMPS and not reduced
+    unroll = len(plan["rows"]) <= int(os.environ.get("MADFLOW_B200_HP_UNROLL_MAX", HP_UNROLL_MAX_AMPS)) and not reduced
     if not hp_available(ir):
         unroll = False
     cmode = "thread" if unroll else hp_colour_mode(ir, NCG)

@@ -227,7 +227,7 @@ class MultiProcessIntegrand:
             if fi.matrix.variant != "hp":
                 fi.matrix.set_variant("hp")   # the kernel pipeline that keeps the events in device memory
         if len(self.parts) > 16:
-            raise ValueError(f"{len(self.parts)} subprocesses: mf_vegas_accumulate_sum takes at most 8 terms per event "
+            raise ValueError(f"{len(self.parts)} subprocesses: mf_vegas_accumulate_sum takes at most 16 terms per event "
                              "(ACC_MAX_TERMS in csrc/pipeline_kernels.cuh)")
         self.n_dim, self.nexternal = first.n_dim, first.nexternal
         self.max_events_per_launch = min(fi.max_events_per_launch for fi in self.parts)
@@ -240,7 +240,9 @@ class MultiProcessIntegrand:
         if self._common_blocks is None:
             for fi in self.parts:
                 fi._lib.set_integrand_blocks(0)
-            self._common_blocks = min(fi.nblocks() for fi in self.parts)
+            # the largest: a library whose kernel keeps fewer blocks resident runs them in waves (its blocks walk fewer
+            # segments each), while the smallest would leave the SMs of the small kernels half empty
+            self._common_blocks = max(fi.nblocks() for fi in self.parts)
         for fi in self.parts:
             fi._lib.set_integrand_blocks(self._common_blocks)
         return self._common_blocks
