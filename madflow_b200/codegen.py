@@ -247,6 +247,8 @@ def hp_config(ir, key):
       TMEMJ      1 = the JAMP accumulators live in Tensor Memory between the JAMP phases of the batches instead of in
                  registers (frees NCOLOR/NCG complex registers for the current / pair / tile phases)
       MT         tiles of the amplitude phase in flight per warp (x events per block)
+      PREFIN     1 = the momenta / couplings of the next group of events are fetched into registers while the current
+                 group is evaluated (smatrix_kernel_hp)
       SLU        1 = packed units: the units of a phase sorted into warp trips of one class of objects (sequence of vertex
                  kinds + propagator kind), one descriptor per trip and one 64-bit word per (unit, term) left to read at run
                  time (process_kernels_hp.cuh, "SLU"); needs TSPLIT = 0
@@ -262,7 +264,7 @@ def hp_config(ir, key):
         # events/s (no more spills at 128 registers), + pass-independent pair objects kept 9.9e5; 4 colour groups 6.3e5
         return {"E": 1, "NCG": 8, "NB": 64, "SCRATCH": 2048 if hp_use_plan(ir) else 4096, "MINBLOCKS": 1, "PERSIST": 0,
                 "PERSIST_FREE": 3500 if hp_use_plan(ir) else 0, "TSPLIT": 0 if hp_use_plan(ir) else 3, "TMEMJ": 1,
-                "SLU": 1 if hp_use_plan(ir) else 0, "MT": 1 if hp_use_plan(ir) else 2}[key]
+                "SLU": 1 if hp_use_plan(ir) else 0, "MT": 1 if hp_use_plan(ir) else 2, "PREFIN": 1}[key]
     # NB: 22 rows let the 64 rows of the reduced g g > t t~ g g fit in 3 batches (with two blocks per SM still resident)
     # MINBLOCKS: g g > t t~ g (32 combinations, straight-line amplitudes) runs 4.6 % faster with three blocks per SM at 168
     # registers, spills included (1.41e8 -> 1.48e8 events/s; four blocks: 1.03e8), profiles/r02zt_*, r02zu_*
@@ -273,7 +275,7 @@ def hp_config(ir, key):
     return {"E": max(1, 128 // ir["ncomb"]), "NCG": 1, "NB": 22 if hp_use_plan(ir) else 21, "SCRATCH": 512,
             "MINBLOCKS": 3 if (ir["ncomb"] == 32 and len(ir["calls"]) > 24) else (4 if small6 else 2),
             "PERSIST": 8 if hp_use_plan(ir) else 0, "PERSIST_FREE": 0, "TSPLIT": 0, "TMEMJ": 0,
-            "SLU": 1 if (hp_use_plan(ir) and ir["ncomb"] == 64) else 0, "MT": 2}[key]
+            "SLU": 1 if (hp_use_plan(ir) and ir["ncomb"] == 64) else 0, "MT": 2, "PREFIN": 0}[key]
 
 
 def hp_use_plan(ir):
@@ -1117,6 +1119,7 @@ struct Proc {{
   static constexpr bool HP_SLU = {'true' if hp['slu'] else 'false'};
   // the words of the next term are fetched while the current one is evaluated (tables beyond L1; measured per process)
   static constexpr bool HP_SLU_PREFETCH = {'true' if hp['slu_stats'].get('words', 0) * 8 > int(os.environ.get("MADFLOW_B200_HP_SLU_PREFETCH_BYTES", 65536)) else 'false'};
+  static constexpr bool HP_PREFETCH_INPUTS = {'true' if hp_config(ir, "PREFIN") else 'false'};
   static constexpr bool HP_SLU_SPLIT = {'true' if hp['slu_stats'].get('split') else 'false'};   // some units are split over lanes
   MF_DEV static int2 slu_range(int i) {{ return MF_TAB(slu_ranges)[i]; }}
   MF_DEV static uint4 slu_trip(int i) {{ return MF_TAB(slu_trips)[i]; }}

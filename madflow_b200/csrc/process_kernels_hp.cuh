@@ -1055,9 +1055,9 @@ __global__ void __launch_bounds__(P::HP_THREADS, P::HP_MINBLOCKS) smatrix_kernel
   // The inputs of the NEXT group of events (one momentum component and one coupling per thread) are fetched into
   // registers as soon as the current group's sit in shared memory, so that their DRAM latency runs under the whole
   // evaluation of the current group instead of in front of its first barrier.  Measured: g g > t t~ g g g (one event per
-  // block of 16 warps) +9 %, g g > t t~ g g (two blocks per SM hide the latency already; 6 more registers) -1.3 %: only
-  // for one event per block.
-  constexpr bool PREF = E == 1 && P::NEXT * 4 <= T && (P::NCOUP > 0 ? P::NCOUP : 1) <= T;
+  // block of 16 warps) +9 %, g g > t t~ g g (two blocks per SM hide the latency already; 6 more registers) -1.3 %,
+  // g g > t t~ g -2.5 %: per process (codegen.hp_config PREFIN).
+  constexpr bool PREF = P::HP_PREFETCH_INPUTS && E * P::NEXT * 4 <= T && E * (P::NCOUP > 0 ? P::NCOUP : 1) <= T;
   auto load_mom = [&](long long ev0, int nev, int i) {
     const int e = i / (P::NEXT * 4), r = i - e * (P::NEXT * 4);
     const long long ev = ev0 + (e < nev ? e : 0);  // pad a partial group with a valid event
