@@ -11,6 +11,7 @@ out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", "--
 rows = list(csv.reader(out.splitlines()))
 fname, cols, ix = "", None, None
 lines = []
+cur = None   # [samples, instructions, file, line, source, stalls] of the source line whose SASS rows follow
 for r in rows:
     if not r:
         continue
@@ -23,16 +24,23 @@ for r in rows:
         for k, c in enumerate(cols):
             ix.setdefault(c, k)
         continue
-    if cols is None or len(r) < len(cols):
+    if cols is None:
         continue
-    if not r[0]:      # a SASS row: the source line above it carries the sum
+    if r[0]:          # a source row: only its line number and text are used -- quotes or commas in the source text shift
+        cur = [0, 0, fname, r[0], r[1].strip()[:70], collections.Counter()]   # its other columns; the SASS rows below carry the numbers
+        lines.append(cur)
+        continue
+    if cur is None or len(r) < len(cols):
         continue
     try:
-        s = int(r[ix["# Samples"]])
+        cur[0] += int(r[ix["# Samples"]] or 0)
+        cur[1] += int(r[ix["Instructions Executed"]] or 0)
     except ValueError:
         continue
-    stalls = {c[6:]: int(float(r[k])) for k, c in enumerate(cols) if c.startswith("stall_") and "Not Issued" not in c and r[k] not in ("", "0")}
-    lines.append((s, int(r[ix["Instructions Executed"]] or 0), fname, r[ix["Line No"]], r[ix["Source"]].strip()[:70], stalls))
+    for k, c in enumerate(cols):
+        if c.startswith("stall_") and "Not Issued" not in c and r[k] not in ("", "0"):
+            cur[5][c[6:]] += int(float(r[k]))
+lines = [tuple(l) for l in lines if l[0] > 0]
 total = sum(l[0] for l in lines)
 byfile = collections.Counter()
 for l in lines:

@@ -6,7 +6,7 @@ for r in rows:
     if not r: continue
     if r[0] in ("File Path","File Name"): fname=r[1].split('/')[-1]; continue
     if r[0]=="Line No": cols=r; continue
-    if cols is None or len(r)<len(cols) or not r[0]: continue
+    if cols is None or len(r)<len(cols) or r[0]: continue   # SASS rows only: source text with quotes or commas shifts the columns of a source row
     for k,c in enumerate(cols):
         if c.startswith("stall_") and "Not Issued" not in c and r[k] not in ("","0"):
             try: v=int(float(r[k]))
