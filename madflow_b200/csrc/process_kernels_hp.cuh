@@ -520,6 +520,9 @@ MF_DEV void slu_units(int ph, int warp, int lane, const cxd* ftab, const double*
     cxd mw[2] = {mk(0.0, 0.0), mk(0.0, 0.0)};
 #ifdef __CUDA_ARCH__
     const uint2* w = P::slu_words() + d.x + lu;
+    // the unit's header word: with tables beyond L1 fetched before the terms (needed right after them; g g > t t~ g g g
+    // +1.1 %), else after them (g g > t t~ g g: one more live register through the terms costs 2 %)
+    const unsigned od_early = P::HP_SLU_PREFETCH ? w[0].x : 0u;
     slu_terms<P::HP_SLU_PREFETCH>(w, LPU, d.z, nterms, fin != HP_F_NONE && part == 0, ev_e, ftab_e, Q, mw);
     if constexpr (P::HP_SLU_SPLIT) {
 #pragma unroll 1
@@ -536,6 +539,9 @@ MF_DEV void slu_units(int ph, int warp, int lane, const cxd* ftab, const double*
     // on the host the lane of part 0 evaluates all parts in turn and adds them in the order of the device's tree
     if (!active || part != 0) continue;
     const uint2* w = P::slu_words() + d.x + lu;
+    // the unit's header word: with tables beyond L1 fetched before the terms (needed right after them; g g > t t~ g g g
+    // +1.1 %), else after them (g g > t t~ g g: one more live register through the terms costs 2 %)
+    const unsigned od_early = P::HP_SLU_PREFETCH ? w[0].x : 0u;
     cxd Qp[8][4];
     for (int pp = 0; pp < (1 << glog); ++pp) {
       for (int k = 0; k < 4; ++k) Qp[pp][k] = mk(0.0, 0.0);
@@ -547,7 +553,7 @@ MF_DEV void slu_units(int ph, int warp, int lane, const cxd* ftab, const double*
         for (int k = 0; k < 4; ++k) Qp[pp][k] += Qp[pp + o][k];
     for (int k = 0; k < 4; ++k) Q[k] = Qp[0][k];
 #endif
-    const unsigned od = w[0].x;
+    const unsigned od = P::HP_SLU_PREFETCH ? od_early : w[0].x;
     cxd* o = ev_e + (od & 0x3fffu);
     const int v = (int)((od >> 14) & 31u), nv = 1 << ((od >> 19) & 7u);
     if (fin == HP_F_NONE) {
