@@ -893,6 +893,7 @@ def emit_hp(ir):
     else:
         C = "    return 0.0;  // not used: the colour contraction of this process is table driven (d_cfsym)"
     cf, den = ir["color_num"], ir["color_denom"]
+    have_frag = False
     if cmode in ("mma", "loop"):
         assert len(set(den)) == 1 and all(cf[i][j] == cf[j][i] for i in range(ncolor) for j in range(ncolor))
         # block-symmetrised colour matrix: blocks of 8x8 colours; below the block diagonal 0, on it cf, above 2 cf
@@ -904,8 +905,24 @@ def emit_hp(ir):
                     v = cf[a_][b_] * (0 if b_ // 8 < a_ // 8 else (1 if b_ // 8 == a_ // 8 else 2))
                 vals.append(f"{float(v)!r}")
         tables += "\n" + both("double", "cfsym", ncp * ncp, ", ".join(vals), const=False)
+        # the same matrix in the order of the tensor-core A fragments: [row block i][pair of k-blocks][lane][2], lane =
+        # 4 r + k holds cfsym[8 i + r][4 kk + k] for kk = 2 kk2, 2 kk2 + 1 -- one coalesced 16-byte load per lane and pair
+        if cmode == "mma" and (ncp // 4) % 2 == 0 and os.environ.get("MADFLOW_B200_HP_CFFRAG", "1") == "1":
+            frag = []
+            for i in range(ncp // 8):
+                for kk2 in range(ncp // 8):
+                    for lane in range(32):
+                        r_, k_ = lane >> 2, lane & 3
+                        for q in range(2):
+                            frag.append(vals[(8 * i + r_) * ncp + 4 * (2 * kk2 + q) + k_])
+            # (single precision would hold these small integers exactly and halve the bytes: measured, no gain)
+            tables += "\n" + both("double", "cfsym_frag", len(frag), ", ".join(frag), const=False)
+            have_frag = True
+        else:
+            tables += "\n" + both("double", "cfsym_frag", 2, "0.0, 0.0", const=False)
     else:
         tables += "\n" + both("double", "cfsym", 1, "0.0", const=False)
+        tables += "\n" + both("double", "cfsym_frag", 2, "0.0, 0.0", const=False)
     # straight-line flavour of the amplitude phase for short amplitude lists (whole vertices per helicity combination)
     U = ["    cxd " + ", ".join(f"J{j} = mk(0.0, 0.0)" for j in range(len(ir["jamp"]))) + ";",
          "    cxd a[6], b[6], c[6], d[6];"]
@@ -937,7 +954,7 @@ def emit_hp(ir):
         wfsize=wfsize, maxlevel=maxlevel, nwf=len(wfs), nitems=nunits_cur, namps=len(plan["rows"]), unroll=unroll,
         nbatch=len(batches), npairs=len(pairs), nitems_pair=len(urow) - nunits_cur, ntiles=len(tile_rows), ncg=1 if unroll else NCG,
         jamp_terms=jamp_terms, npass=1 if unroll else NPASS, cmode={"thread": 0, "groups": 1, "mma": 2, "loop": 3}[cmode], ncp=ncp,
-        colour_denom=float(den[0]), reduced=reduced, nterms=len(trows), slu=SLU, slu_stats=slu_stats,
+        colour_denom=float(den[0]), reduced=reduced, cf_frag=have_frag, nterms=len(trows), slu=SLU, slu_stats=slu_stats,
         nb=max(len(a_) for _, a_ in batches) if batches else 1,
         scratch=max((pairs[pi]["abs_off"] - wfsize + 4 * pairs[pi]["nv"] for b_ in batches for pi in b_[0]), default=0))
 
@@ -1107,6 +1124,8 @@ struct Proc {{
   // that threads working on the same object of different events hit different banks
   static constexpr int HP_EVSTRIDE = HP_E > 1 ? HP_EVSIZE + ((8 / HP_E) - HP_EVSIZE % 8 + 8) % 8 : HP_EVSIZE;
   MF_DEV static const double* cfsym() {{ return MF_TAB(cfsym); }}
+  static constexpr bool HP_CF_FRAG = {'true' if hp['cf_frag'] else 'false'};   // cfsym also stored in tensor-core fragment order
+  MF_DEV static const double* cfsym_frag() {{ return MF_TAB(cfsym_frag); }}
   MF_DEV static mf::HpWf wf(int w) {{ return MF_TAB(wf)[w]; }}
   MF_DEV static mf::HpExt ext(int leg) {{ return MF_TAB(ext)[leg]; }}
   MF_DEV static mf::HpTerm term(int i) {{ return mf::hp_fetch32(&MF_TAB(terms)[i]); }}

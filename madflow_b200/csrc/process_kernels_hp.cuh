@@ -809,10 +809,21 @@ __device__ __forceinline__ double hp_colour_mma(const double* planes /* shared: 
 #pragma unroll 1
     for (int i = 0; i < NCP / 8; ++i) {
       double c0 = 0.0, c1 = 0.0;
-      const double* arow = cf + (8 * i + r) * NCP + k;
+      if constexpr (P::HP_CF_FRAG) {   // A fragments of two k-blocks with one coalesced 16-byte load per lane
+        const double2* af = reinterpret_cast<const double2*>(P::cfsym_frag()) + (size_t)i * (NKK / 2) * 32 + lane;
 #pragma unroll
-      for (int kk = 0; kk < NKK; ++kk)
-        if (kk >= 2 * i) dmma_m8n8k4(c0, c1, __ldg(arow + 4 * kk), B[kk]);
+        for (int kk2 = 0; kk2 < NKK / 2; ++kk2)
+          if (kk2 >= i) {
+            const double2 a2 = __ldg(af + kk2 * 32);
+            dmma_m8n8k4(c0, c1, a2.x, B[2 * kk2]);
+            dmma_m8n8k4(c0, c1, a2.y, B[2 * kk2 + 1]);
+          }
+      } else {
+        const double* arow = cf + (8 * i + r) * NCP + k;
+#pragma unroll
+        for (int kk = 0; kk < NKK; ++kk)
+          if (kk >= 2 * i) dmma_m8n8k4(c0, c1, __ldg(arow + 4 * kk), B[kk]);
+      }
       const double* jr = plane + (8 * i + r) * PL + h0;
       if (keep0) me += jr[0] * c0;
       if (keep1) me += jr[1] * c1;
