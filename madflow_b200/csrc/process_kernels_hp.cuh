@@ -10,7 +10,9 @@
 //   phase 1   external wavefunctions: n legs x 2 helicities x E events
 //   phase 2   off-shell currents level by level (level = number of legs); the work items of a
 //             level are (current, event, helicity variant), spread over all threads of the block;
-//             table driven (HpItem), one copy of each ALOHA routine in the instruction stream
+//             table driven, one copy of each vertex routine in the instruction stream: hp_units
+//             (term rows + work items), or -- g g > t t~ g g (g) -- the packed units slu_units
+//             (warp trips of one class of objects, one 64-bit word per (unit, term), see "SLU")
 //   phase 3   amplitudes, batch by batch: (a) the pair objects of the batch (see HpPair), (b) the
 //             amplitudes of ALL helicity combinations on the FP64 tensor cores: amplitude[vq][vx] =
 //             sum_k Q_k[vq] x_k[vx] is a (variants of Q x 4)(4 x variants of x) complex matrix
